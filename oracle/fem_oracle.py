@@ -1,0 +1,422 @@
+"""CPU ORACLE (test infrastructure, NOT product code).
+
+A plain NumPy restatement of the reference's Cook's-membrane hot path, written
+from the reference's algorithm and citing the file:line each function follows
+(paths are relative to the upstream repository).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline / ``--impl
+reference`` legs may import this module; the shipped CUDA path never does.
+
+Parity status: PINNED against the reference's own NumPy twin
+(src/fem_solver.py + src/mat_subroutine.py) run unmodified in the build
+container -- see tests/golden/make_golden.py and tests/golden/ref_numpy_twin.npz.
+The TensorFlow twin (src/fem_solver_tf.py) cannot be imported in this
+environment (no tensorflow wheel); it differs from the NumPy twin only in the
+linear solver (dense pivoted LU, fem_solver_tf.py:137, vs SuperLU,
+fem_solver.py:95), which this oracle follows by using a dense LU solve.
+
+Two forms are provided and cross-checked in tests/test_oracle.py:
+  * a loop form (element loop / Gauss loop / dense B matrices) that mirrors the
+    reference statement by statement -- slow, used for small cases;
+  * a batched torch-float64 form (``TorchOracle``) with the same formulas that
+    also yields reverse-mode gradients, standing in for ``tape.gradient``
+    (main_custom_training.py:252-256).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# fem_preprocess.py:19  (literal, 15 digits -- NOT 1/sqrt(3) to full precision)
+SQT13 = 0.577350269189626
+# fem_preprocess.py:32-42  Pdevs rows/cols [0,4,8,3,7,2] (fem_postprocess.py:168,179-183)
+_TWO3 = 0.666666666666667
+_ONE3 = 0.333333333333333
+PDEV6 = np.array(
+    [
+        [_TWO3, -_ONE3, -_ONE3, 0, 0, 0],
+        [-_ONE3, _TWO3, -_ONE3, 0, 0, 0],
+        [-_ONE3, -_ONE3, _TWO3, 0, 0, 0],
+        [0, 0, 0, 0.5, 0, 0],
+        [0, 0, 0, 0, 0.5, 0],
+        [0, 0, 0, 0, 0, 0.5],
+    ],
+    dtype=np.float64,
+)
+
+
+# --------------------------------------------------------------------------- mesh
+def read_mesh(path):
+    """FEAP-style mesh reader.  Follows fem_preprocess.py:114-289
+    (header line 2 = nnodes nele nmat ndm ndf nen; sections 'COORdinates ALL',
+    'ELEMents ALL', 'BOUNdary conditions', 'FORCe conditions'; the second
+    column of every record is dropped, fem_preprocess.py:213-221)."""
+    with open(path, "r", newline=None) as f:
+        lines = [ln.rstrip("\r\n") for ln in f.read().splitlines()]
+    hdr = lines[1].split()
+    nnodes, nele, ndm, ndf, nen = int(hdr[0]), int(hdr[1]), int(hdr[3]), int(hdr[4]), int(hdr[5])
+    assert ndm == 2 and ndf == 2 and nen == 4
+
+    def find(tag, start=0):
+        for i in range(start, len(lines)):
+            if lines[i].strip() == tag:
+                return i
+        return -1
+
+    i = find("COORdinates ALL")
+    coord = np.array([[float(t) for t in lines[i + 1 + k].split()] for k in range(nnodes)])
+    coord = np.delete(coord[:, :4], 1, axis=1)  # (id, x, y)
+    i = find("ELEMents ALL", i)
+    elem = np.array([[int(t) for t in lines[i + 1 + k].split()] for k in range(nele)], dtype=np.int64)
+    elem = np.delete(elem, 1, axis=1)  # (id, mat, n1..n4)
+    conn = elem[:, 2 : 2 + nen]
+
+    def block(tag, start, conv):
+        j = find(tag, start)
+        rows = []
+        if j >= 0:
+            k = j + 1
+            while k < len(lines) and lines[k].strip():
+                rows.append([conv(t) for t in lines[k].split()])
+                k += 1
+        return j, rows
+
+    j, bc = block("BOUNdary conditions", i, int)
+    bc = np.delete(np.array(bc, dtype=np.int64), 1, axis=1) if bc else np.zeros((0, 3), np.int64)
+    j2, ld = block("FORCe conditions", max(j, i), float)
+    ld = np.delete(np.array(ld, dtype=np.float64), 1, axis=1) if ld else np.zeros((0, 3))
+    return dict(nnodes=nnodes, nele=nele, coord=coord, conn=conn, bc=bc, load=ld)
+
+
+def assign_dof(mesh):
+    """DOF maps.  Follows fem_preprocess.py:291-443: ID[c, n] = 2 n + c + 1
+    (1-based), LM[:, e] = ID[:, IEN[e]].flatten('F'), supports from the
+    boundary flags, Pf = nodal loads gathered at the free dofs (x loads only
+    where the x entry is non-zero, same for y, fem_preprocess.py:362-371)."""
+    nnodes, nele = mesh["nnodes"], mesh["nele"]
+    ndof = 2 * nnodes
+    ID = np.arange(1, ndof + 1).reshape(nnodes, 2).T
+    conn = mesh["conn"]
+    supp = []
+    for row in mesh["bc"]:
+        n = int(row[0])
+        if row[1] == 1:
+            supp.append(ID[0, n - 1])
+        if row[2] == 1:
+            supp.append(ID[1, n - 1])
+    supp_dof = np.unique(np.array(supp, dtype=np.int64))
+    free_dof = np.setdiff1d(np.arange(1, ndof + 1), supp_dof)
+    LM = np.zeros((8, nele), dtype=np.int64)
+    for e in range(nele):
+        LM[:, e] = ID[:, conn[e] - 1].flatten(order="F")
+    P = np.zeros(ndof)
+    for row in mesh["load"]:
+        n = int(row[0])
+        if row[1] != 0:
+            P[ID[0, n - 1] - 1] += row[1]
+        if row[2] != 0:
+            P[ID[1, n - 1] - 1] += row[2]
+    return dict(ID=ID, IEN=conn.copy(), LM=LM, free_dof=free_dof, supp_dof=supp_dof, ndof=ndof,
+                Pf=P[free_dof - 1].copy())
+
+
+def cook_mesh_text(nx, ny, total_load=50.0, digits=6):
+    """Cook's membrane nx x ny written in the reference's FEAP text format
+    (same bilinear map that reproduces Armero_cooksm_20x10.txt; SURVEY 8d
+    config 4): corners (0,0),(48,44),(48,60),(0,44), ids row-major nx+1 per
+    row, clamp column i=0, load in +y lumped on the right edge.  With the
+    shipped file's 7 significant digits (digits=6) the 20x10 coordinates parse
+    to the same doubles as the reference mesh."""
+    out = ["FEAP * * PLANE strain problem", f"{(nx+1)*(ny+1):10d}{nx*ny:10d}{1:10d}{2:10d}{2:10d}{4:10d}", " ", "",
+           "COORdinates ALL"]
+    for j in range(ny + 1):
+        for i in range(nx + 1):
+            xi, eta = i / nx, j / ny
+            X = 48.0 * xi
+            Y = 44.0 * xi + eta * (44.0 * (1.0 - xi) + 16.0 * xi)
+            out.append(f"{j*(nx+1)+i+1:9d} 0 {X: .{digits}E} {Y: .{digits}E}")
+    out += ["", "ELEMents ALL"]
+    e = 0
+    for j in range(ny):
+        for i in range(nx):
+            e += 1
+            n1 = j * (nx + 1) + i + 1
+            out.append(f"{e:6d}   0     1 {n1:6d} {n1+1:6d} {n1+nx+2:6d} {n1+nx+1:6d}")
+    out += ["", "BOUNdary conditions"]
+    for j in range(ny + 1):
+        out.append(f"{j*(nx+1)+1:10d}   0   1   1")
+    out += ["", "FORCe conditions"]
+    for j in range(ny + 1):
+        w = total_load / ny * (0.5 if j in (0, ny) else 1.0)
+        out.append(f"{j*(nx+1)+nx+1:9d} 0 {0.0: .{digits}E} {w: .{digits}E}")
+    out += [" ", "END", ""]
+    return "\n".join(out)
+
+
+# ----------------------------------------------------------------------- element
+def gauss_2x2():
+    """fem_preprocess.py:553-558 (int2d, l=2): points g*(lr,lz), weights 1."""
+    lr = np.array([-1, 1, 1, -1], dtype=np.float64)
+    lz = np.array([-1, -1, 1, 1], dtype=np.float64)
+    sg = np.zeros((3, 4))
+    sg[0], sg[1], sg[2] = SQT13 * lr, SQT13 * lz, 1.0
+    return sg
+
+
+def shapef(s, xl):
+    """fem_preprocess.py:904-971 (= shapef_tf 1223-1285), flg = 0."""
+    sh, th = 0.5 * s[0], 0.5 * s[1]
+    sp, tp, sm, tm = 0.5 + sh, 0.5 + th, 0.5 - sh, 0.5 - th
+    xo = xl[0, 0] - xl[0, 1] + xl[0, 2] - xl[0, 3]
+    xs = -xl[0, 0] + xl[0, 1] + xl[0, 2] - xl[0, 3] + xo * s[1]
+    xt = -xl[0, 0] - xl[0, 1] + xl[0, 2] + xl[0, 3] + xo * s[0]
+    yo = xl[1, 0] - xl[1, 1] + xl[1, 2] - xl[1, 3]
+    ys = -xl[1, 0] + xl[1, 1] + xl[1, 2] - xl[1, 3] + yo * s[1]
+    yt = -xl[1, 0] - xl[1, 1] + xl[1, 2] + xl[1, 3] + yo * s[0]
+    xsj1 = xs * yt - xt * ys
+    xsj = 0.0625 * xsj1
+    xsj1 = 1.0 / xsj1 if xsj1 != 0.0 else 1.0
+    xs, xt, ys, yt = (xs + xs) * xsj1, (xt + xt) * xsj1, (ys + ys) * xsj1, (yt + yt) * xsj1
+    ytm, ysm, ytp, ysp = yt * tm, ys * sm, yt * tp, ys * sp
+    xtm, xsm, xtp, xsp = xt * tm, xs * sm, xt * tp, xs * sp
+    shp = np.zeros((3, 4))
+    shp[0] = [-ytm + ysm, ytm + ysp, ytp - ysp, -ytp - ysm]
+    shp[1] = [xtm - xsm, -xtm - xsp, -xtp + xsp, xtp + xsm]
+    shp[2] = [sm * tm, sp * tm, sp * tp, sm * tp]
+    return shp, xsj
+
+
+def isotropic_elasticity(eps, E, v):
+    """mat_subroutine_tf.py:333-390 (plane-strain branch that the TF file
+    executes unconditionally): lambda/mu, 4x4 Ce, sig[0:4] = Ce @ eps[0:4],
+    Ct[{0,1,3}^2] = Ce[{0,1,3}^2]."""
+    l = v * E / ((1 + v) * (1 - 2 * v))
+    mu = 0.5 * E / (1 + v)
+    Ce = np.array([[l + 2 * mu, l, l, 0], [l, l + 2 * mu, l, 0], [l, l, l + 2 * mu, 0], [0, 0, 0, mu]])
+    sig = np.zeros(6)
+    sig[0:4] = Ce @ eps[0:4]
+    Ct = np.zeros((6, 6))
+    idx = [0, 1, 3]
+    Ct[np.ix_(idx, idx)] = Ce[np.ix_(idx, idx)]
+    return sig, Ct
+
+
+def solid_2d(ul, xl, E, v, thk):
+    """mat_subroutine_tf.py:23-110: 2x2 Gauss loop, strain (112-145), plane
+    strain eps[2]=0 (54-56), material, Ct -> [0,1,3]^2 (75-76), dvol=thk*jac,
+    p += dvol*Bm^T sig[0,1,3] (147-159, zero body force), kt += dvol*Bm^T Ct Bm,
+    Bm rows (dNx | dNy | dNy,dNx) (161-227)."""
+    sg = gauss_2x2()
+    p = np.zeros(8)
+    kt = np.zeros((8, 8))
+    eps_out = np.zeros((6, 4))
+    sig_out = np.zeros((6, 4))
+    for ipt in range(4):
+        shp, xsj = shapef(sg[0:2, ipt], xl)
+        jac = xsj * sg[2, ipt]
+        eps = np.zeros(6)
+        eps[0] = shp[0] @ ul[0]
+        eps[1] = shp[1] @ ul[1]
+        eps[3] = shp[0] @ ul[1] + shp[1] @ ul[0]
+        eps[2] = 0.0
+        sig, Ct = isotropic_elasticity(eps, E, v)
+        Ct3 = Ct[np.ix_([0, 1, 3], [0, 1, 3])]
+        dvol = thk * jac
+        Bm = np.zeros((3, 8))
+        for i in range(4):
+            Bm[0, 2 * i] = shp[0, i]
+            Bm[1, 2 * i + 1] = shp[1, i]
+            Bm[2, 2 * i] = shp[1, i]
+            Bm[2, 2 * i + 1] = shp[0, i]
+        p += dvol * (Bm.T @ sig[[0, 1, 3]])
+        kt += dvol * (Bm.T @ Ct3 @ Bm)
+        eps_out[:, ipt] = eps
+        sig_out[:, ipt] = sig
+    return p, kt, eps_out, sig_out
+
+
+# ------------------------------------------------------------------------ solver
+class LoopOracle:
+    """Statement-by-statement restatement of fem_solver_tf.py:86-185,229-341."""
+
+    def __init__(self, mesh, dof, thk=10.0):
+        self.mesh, self.dof, self.thk = mesh, dof, thk
+        self.xy = mesh["coord"][:, 1:3]
+
+    def assemble(self, u, E, v):
+        """fem_solver_tf.py:229-341: element loop, gather ul by LM, xl by IEN,
+        scatter (duplicates add) into dense Kg and F_int."""
+        d, m = self.dof, self.mesh
+        ndof, nele = d["ndof"], m["nele"]
+        Kg = np.zeros((ndof, ndof))
+        Fint = np.zeros(ndof)
+        strain = np.zeros((6, 4, nele))
+        stress = np.zeros((6, 4, nele))
+        for e in range(nele):
+            lm = d["LM"][:, e] - 1
+            ul = u[lm].reshape(4, 2).T
+            xl = self.xy[d["IEN"][e] - 1].T
+            p, kt, eps, sig = solid_2d(ul, xl, E, v, self.thk)
+            Fint[lm] += p
+            Kg[np.ix_(lm, lm)] += kt
+            strain[:, :, e], stress[:, :, e] = eps, sig
+        return Kg, Fint, strain, stress
+
+    def solve(self, E, v):
+        """fem_solver_tf.py:86-185: zero predictor, assemble, one dense solve on
+        the free block, update, assemble again for stresses; exit_flag = 1."""
+        d = self.dof
+        free = d["free_dof"] - 1
+        u = np.zeros(d["ndof"])
+        Kg, Fint, _, _ = self.assemble(u, E, v)
+        Fext = np.zeros(d["ndof"])
+        Fext[free] = d["Pf"]
+        R = Fint[free] - Fext[free]
+        duf = np.linalg.solve(Kg[np.ix_(free, free)], -R)
+        u[free] = u[free] + duf
+        _, Fint, strain, stress = self.assemble(u, E, v)
+        return u, Fint, strain, stress
+
+
+def von_mises(stress_e, nipt_id):
+    """fem_postprocess.py:163-185: sqrt(0.5*sum((Pdev6 @ sigma)^2)) at the
+    requested Gauss points (1-based) -- the reference's non-standard formula."""
+    s = stress_e[:, np.asarray(nipt_id) - 1]
+    return np.sqrt(0.5 * np.sum((PDEV6 @ s) ** 2, axis=0))
+
+
+def theta_to_material(x, theta_mean, theta_std):
+    """data_generation_2sam_more_loss.py:181-186."""
+    E = np.exp(theta_std[0] * x[..., 0] + theta_mean[0])
+    v = 0.5 / (1.0 + np.exp(-theta_std[1] * x[..., 1] - theta_mean[1]))
+    return E, v
+
+
+def fem_fh_loop(oracle, x, theta_mean, theta_std, node_id=231, ele_id=12, nipt_id=(1, 3)):
+    """data_generation_2sam_more_loss.py:169-192 for a batch x[N,2] (serial)."""
+    x = np.atleast_2d(x)
+    y = np.zeros((x.shape[0], 2))
+    h = np.zeros((x.shape[0], 2))
+    for i in range(x.shape[0]):
+        E, v = theta_to_material(x[i], theta_mean, theta_std)
+        u, _, _, stress = oracle.solve(float(E), float(v))
+        y[i] = u[2 * node_id - 2 : 2 * node_id]
+        h[i] = von_mises(stress[:, :, ele_id - 1], nipt_id)
+    return y, h
+
+
+# ------------------------------------------------------------ batched torch form
+class TorchOracle:
+    """Batched float64 torch-CPU form of the same formulas (dense Kg, dense LU
+    solve) whose autograd stands in for TensorFlow's tape.gradient
+    (main_custom_training.py:252-256).  Geometry (shape-function derivatives,
+    dvol) is evaluated once with ``shapef`` above."""
+
+    def __init__(self, mesh, dof, thk=10.0, theta_mean=(math.log(20.0), 0.0), theta_std=(0.1, 0.015),
+                 node_id=231, ele_id=12, nipt_id=(1, 3)):
+        import torch
+
+        self.torch = torch
+        self.mesh, self.dof = mesh, dof
+        nele = mesh["nele"]
+        xy = mesh["coord"][:, 1:3]
+        sg = gauss_2x2()
+        B = np.zeros((nele, 4, 3, 8))
+        dvol = np.zeros((nele, 4))
+        for e in range(nele):
+            xl = xy[dof["IEN"][e] - 1].T
+            for g in range(4):
+                shp, xsj = shapef(sg[0:2, g], xl)
+                dvol[e, g] = thk * xsj * sg[2, g]
+                for i in range(4):
+                    B[e, g, 0, 2 * i] = shp[0, i]
+                    B[e, g, 1, 2 * i + 1] = shp[1, i]
+                    B[e, g, 2, 2 * i] = shp[1, i]
+                    B[e, g, 2, 2 * i + 1] = shp[0, i]
+        self.B = torch.from_numpy(B)
+        self.dvol = torch.from_numpy(dvol)
+        self.lm = torch.from_numpy(dof["LM"].T.copy() - 1)  # [nele, 8]
+        self.free = torch.from_numpy(dof["free_dof"] - 1)
+        self.Pf = torch.from_numpy(dof["Pf"].copy())
+        self.ndof = dof["ndof"]
+        self.theta_mean = torch.tensor(theta_mean, dtype=torch.float64)
+        self.theta_std = torch.tensor(theta_std, dtype=torch.float64)
+        self.node_id, self.ele_id = node_id, ele_id
+        self.nipt = torch.tensor([g - 1 for g in nipt_id])
+        self.P6 = torch.from_numpy(PDEV6)
+
+    def material(self, x):
+        t = self.torch
+        E = t.exp(self.theta_std[0] * x[:, 0] + self.theta_mean[0])
+        v = 0.5 / (1.0 + t.exp(-self.theta_std[1] * x[:, 1] - self.theta_mean[1]))
+        return E, v
+
+    def fields(self, x):
+        """x[N,2] -> u[N,ndof], strain/stress[N,6,4,nele] (all differentiable)."""
+        t = self.torch
+        N = x.shape[0]
+        E, v = self.material(x)
+        lam = v * E / ((1 + v) * (1 - 2 * v))
+        mu = 0.5 * E / (1 + v)
+        z = t.zeros_like(lam)
+        C3 = t.stack([t.stack([lam + 2 * mu, lam, z], -1), t.stack([lam, lam + 2 * mu, z], -1),
+                      t.stack([z, z, mu], -1)], -2)  # [N,3,3]
+        # kt[n,e] = sum_g dvol * B^T C B
+        CB = t.einsum("nij,egjk->negik", C3, self.B)
+        Ke = t.einsum("eg,egia,negib->neab", self.dvol, self.B, CB)
+        nele = self.B.shape[0]
+        rows = self.lm[:, :, None].expand(nele, 8, 8).reshape(-1)
+        cols = self.lm[:, None, :].expand(nele, 8, 8).reshape(-1)
+        Kg = t.zeros((N, self.ndof * self.ndof), dtype=t.float64)
+        Kg = Kg.index_add(1, rows * self.ndof + cols, Ke.reshape(N, -1)).reshape(N, self.ndof, self.ndof)
+        Kff = Kg[:, self.free][:, :, self.free]
+        uf = t.linalg.solve(Kff, self.Pf.expand(N, -1).unsqueeze(-1)).squeeze(-1)
+        u = t.zeros((N, self.ndof), dtype=t.float64).index_copy(1, self.free, uf)
+        ue = u[:, self.lm]  # [N,nele,8]
+        eps3 = t.einsum("egia,nea->negi", self.B, ue)  # [N,nele,4,3] (xx,yy,gxy)
+        exx, eyy, gxy = eps3[..., 0], eps3[..., 1], eps3[..., 2]
+        l_, m_ = lam[:, None, None], mu[:, None, None]
+        sxx = (l_ + 2 * m_) * exx + l_ * eyy
+        syy = l_ * exx + (l_ + 2 * m_) * eyy
+        szz = l_ * exx + l_ * eyy
+        sxy = m_ * gxy
+        zz = t.zeros_like(sxx)
+        stress = t.stack([sxx, syy, szz, sxy, zz, zz], 1).permute(0, 1, 3, 2)  # [N,6,4,nele]
+        strain = t.stack([exx, eyy, zz, gxy, zz, zz], 1).permute(0, 1, 3, 2)
+        return u, strain, stress
+
+    def fem_fh(self, x):
+        """Batched MeasurementData.fem_fh_fun_loop_rev: x[N,2] -> y[N,2], h[N,2]."""
+        t = self.torch
+        u, _, stress = self.fields(x)
+        y = u[:, 2 * self.node_id - 2 : 2 * self.node_id]
+        s = stress[:, :, :, self.ele_id - 1][:, :, self.nipt]  # [N,6,2]
+        h = t.sqrt(0.5 * t.sum(t.einsum("ij,njk->nik", self.P6, s) ** 2, dim=1))
+        return y, h
+
+    def vjp(self, x_np, gy_np, gh_np):
+        t = self.torch
+        x = t.tensor(x_np, dtype=t.float64, requires_grad=True)
+        y, h = self.fem_fh(x)
+        (gx,) = t.autograd.grad((y * t.tensor(gy_np)).sum() + (h * t.tensor(gh_np)).sum(), x)
+        return y.detach().numpy(), h.detach().numpy(), gx.numpy()
+
+
+# ----------------------------------------------------------------- ELBO (step 1)
+def elbo_step1_torch(torch_oracle, y_batch, mu, sig2, e_data, sig_e):
+    """main_custom_training.py:183-235 with log_theta_sig = log(sig2):
+    loss = term1 - term2 - term3, including the [B, B*S] broadcast of
+    (y_point - f_data) at main_custom_training.py:205,210-214.
+    Returns (loss, term1, term2, term3) as torch scalars."""
+    t = torch_oracle.torch
+    d = mu.shape[-1]
+    dy = y_batch.shape[-1]
+    term1 = -0.5 * t.mean(t.sum(t.log(sig2), dim=-1), dim=0) - 0.5 * d * math.log(2.0 * math.pi) - 0.5 * d
+    std = t.sqrt(sig2).unsqueeze(1)
+    theta = (e_data * std + mu.unsqueeze(1)).reshape(-1, d)
+    f, _ = torch_oracle.fem_fh(theta)  # [B*S, 2]
+    l1 = -0.5 * dy * math.log(2.0 * math.pi * sig_e)
+    l2 = -0.5 / sig_e * t.sum((y_batch.unsqueeze(1) - f) ** 2, dim=-1)  # [B, B*S]
+    term2 = l1 + t.mean(l2)
+    term3 = -0.5 * d * math.log(2.0 * math.pi) - 0.5 * t.mean(t.sum(sig2 + mu ** 2, dim=-1), dim=0)
+    return term1 - term2 - term3, term1, term2, term3
