@@ -1,0 +1,145 @@
+/* vbfem.h -- C ABI of libvbfem.so: B200 (sm_100a) batched Cook's-membrane FEM
+ * forward + adjoint, the hot path inside the variational-Bayes ELBO.
+ *
+ * The upstream project (nfeng2022/Variational-Bayesian-Inference-for-
+ * Computational-Mechanics) is pure Python and has no FFI; the seam this
+ * library sits behind is the Python callable
+ *     MeasurementData.fem_fh_fun_loop_rev(x[N,2]) -> (y[N,2], h[N,2])
+ *     (src/data_generation_2sam_more_loss.py:169-192)
+ * and, one level down, FemSolver.fea_solution (src/fem_solver_tf.py:13-73).
+ * Every entry point cites the reference code it replaces.  All paths below
+ * are relative to the upstream repository.
+ *
+ * Conventions
+ *   - plain C types only; 0 = success, negative = error (vbfem_last_error()).
+ *   - *_dev pointers are device pointers on the handle's GPU (obtained from
+ *     torch / DLPack by the Python wrapper); *_host pointers are host memory.
+ *   - everything is float64, row-major; index arrays handed in by the caller
+ *     use the reference's 1-based numbering.
+ *   - calls are stream-ordered on `stream` (a cudaStream_t passed as void*,
+ *     NULL = default stream) and do not synchronise, except the *_host
+ *     variants, vbfem_status and vbfem_create/destroy.
+ *   - one handle per GPU; calls on one handle are not re-entrant.
+ */
+#ifndef VBFEM_H
+#define VBFEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vbfem_handle vbfem_t;
+
+/* Sample-independent model description = the slice of
+ * fem_preprocess.PreProcessing.model_data the hot path reads
+ * (src/fem_preprocess.py:114-443, model_property_cards.py:25-29) plus the
+ * MeasurementData class attributes (src/data_generation_2sam_more_loss.py:16-21,
+ * main_custom_training.py:32-38). */
+typedef struct vbfem_mesh {
+    int32_t nnodes;          /* mesh_info['nnodes'] */
+    int32_t nele;            /* mesh_info['nele'] */
+    const double *coord;     /* [nnodes][2] = mesh_info['coord'][:, 1:3] */
+    const int32_t *ien;      /* [nele][4]  = dof_info['IEN'], 1-based node ids */
+    int32_t nfree;           /* dof_info['nfree'] */
+    const int32_t *free_dof; /* [nfree] = dof_info['free_dof'], 1-based, dof = 2(n-1)+c+1 */
+    const double *pf;        /* [nfree] = loading['Pf'] (dense) */
+    double thk;              /* section[0]['thk'] */
+    int32_t obs_node;        /* MeasurementData.node_id (1-based) */
+    int32_t obs_ele;         /* MeasurementData.ele_id (1-based) */
+    int32_t obs_gp[2];       /* MeasurementData.nipt_id (1-based Gauss points) */
+    double theta_mean[2];    /* MeasurementData.theta_mean */
+    double theta_std[2];     /* MeasurementData.theta_std */
+} vbfem_mesh;
+
+/* Index of the integers returned by vbfem_info(). */
+enum {
+    VBFEM_INFO_NFREE = 0,     /* n: order of the banded system */
+    VBFEM_INFO_HALF_BW = 1,   /* b: half bandwidth under the internal numbering */
+    VBFEM_INFO_NDOF = 2,
+    VBFEM_INFO_NELE = 3,
+    VBFEM_INFO_NCOLORS = 4,   /* element colours used by the atomics-free assembly */
+    VBFEM_INFO_BAND_IN_SMEM = 5,
+    VBFEM_INFO_SMEM_BYTES = 6,
+    VBFEM_INFO_CTAS_PER_SM = 7,
+    VBFEM_INFO_NUM_SMS = 8,
+    VBFEM_INFO_BLOCK_THREADS = 9,
+    VBFEM_INFO_COUNT = 16
+};
+
+/* Build the per-GPU context: internal DOF renumbering, band profile, element
+ * colouring, device tables, workspace.  Replaces the setup the reference does
+ * in fem_preprocess.py:291-443 + fem_solver_tf.py:378-396 (host side). */
+int vbfem_create(vbfem_t **out, const vbfem_mesh *mesh, int device);
+void vbfem_destroy(vbfem_t *h);
+const char *vbfem_last_error(void);
+int vbfem_info(const vbfem_t *h, int64_t *out /* [VBFEM_INFO_COUNT] */);
+
+/* y,h = fem_fh_fun_loop_rev(x): for each sample theta->(E,nu)
+ * (data_generation_2sam_more_loss.py:181-186), assemble
+ * (fem_solver_tf.py:229-341, mat_subroutine_tf.py:23-110), solve
+ * (fem_solver_tf.py:129-153), observe u at obs_node and the von Mises stress
+ * at (obs_ele, obs_gp) (fem_postprocess.py:172-185).  With keep_factor != 0
+ * the factor and solution are kept in the library workspace for
+ * vbfem_backward. */
+int vbfem_forward(vbfem_t *h, int64_t n_samples, const double *x_dev /* [N][2] */,
+                  double *y_dev /* [N][2] */, double *h_dev /* [N][2] */,
+                  int keep_factor, void *stream);
+
+/* gx = d(sum(gy*y) + sum(gh*h))/dx for the batch of the last
+ * vbfem_forward(keep_factor=1): the discrete adjoint that tape.gradient
+ * (main_custom_training.py:252-256) derives through the TF graph, computed
+ * with the stored factor. */
+int vbfem_backward(vbfem_t *h, int64_t n_samples, const double *gy_dev, const double *gh_dev,
+                   double *gx_dev /* [N][2] */, void *stream);
+
+/* Fused forward + adjoint in one launch (no workspace round trip). */
+int vbfem_forward_backward(vbfem_t *h, int64_t n_samples, const double *x_dev,
+                           const double *gy_dev, const double *gh_dev,
+                           double *y_dev, double *h_dev, double *gx_dev, void *stream);
+
+/* Full fields for fem_test.py / fem_postprocess: u = sol_data['u_n1'] [N][ndof],
+ * eps/sig = out_data['ele_strain'/'ele_stress'][:, :, :, 1] as [N][6][4][nele],
+ * fint = sol_data['F_int'] [N][ndof]  (fem_solver_tf.py:310-341).
+ * Any output pointer may be NULL.  If emat_dev != NULL it holds (E, nu) per
+ * sample [N][2] and x_dev is ignored (fem_test.py uses the card values). */
+int vbfem_fields(vbfem_t *h, int64_t n_samples, const double *x_dev, const double *emat_dev,
+                 double *u_dev, double *sig_dev, double *eps_dev, double *fint_dev, void *stream);
+
+/* Step-1 ELBO pieces (main_custom_training.py:183-235) for the flat sample
+ * range [j_begin, j_end) of the B*S reparameterised samples
+ * theta[b,s] = e[s]*sqrt(sig2[b]) + mu[b] (main_custom_training.py:199-209),
+ * including the [B, B*S] broadcast of (y_point - f_data)
+ * (main_custom_training.py:205,210-214).
+ *   sums_dev[0..1] = sum_j f_j (per component), sums_dev[2] = sum_j |f_j|^2
+ *   gmu_dev[B][2], gsig2_dev[B][2] = d(loss)/d(mu), d(loss)/d(sig2) through
+ *   term2 only, restricted to the given sample range.
+ * The caller (one rank per GPU) all-reduces these partials and adds the
+ * closed-form term1/term3 parts. */
+int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                     const double *mu_dev, const double *sig2_dev, const double *e_dev,
+                     const double *ybatch_dev, double sig_e, double *sums_dev, double *gmu_dev,
+                     double *gsig2_dev, double *f_dev /* optional [j_end-j_begin][2] */, void *stream);
+
+/* Per-sample status words of the last launch (0 = ok, bit0 = non-positive or
+ * non-finite pivot).  Synchronises.  Returns the number of flagged samples,
+ * or a negative error. */
+int64_t vbfem_status(vbfem_t *h, int32_t *flags_host /* [N] or NULL */, int64_t n_samples);
+
+/* Host-buffer entry points (what a NumPy/TF caller uses): copy in from host
+ * memory, run, copy out, synchronise. */
+int vbfem_forward_host(vbfem_t *h, int64_t n_samples, const double *x_host, double *y_host,
+                       double *h_host);
+int vbfem_forward_backward_host(vbfem_t *h, int64_t n_samples, const double *x_host,
+                                const double *gy_host, const double *gh_host, double *y_host,
+                                double *h_host, double *gx_host);
+
+/* Roofline denominators measured on this GPU: dependent-free DFMA loop
+ * (TFLOP/s) and a device copy (GB/s, read+write bytes). */
+int vbfem_measure_peaks(int device, double *fp64_tflops, double *copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBFEM_H */
