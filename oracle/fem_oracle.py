@@ -420,3 +420,76 @@ def elbo_step1_torch(torch_oracle, y_batch, mu, sig2, e_data, sig_e):
     term2 = l1 + t.mean(l2)
     term3 = -0.5 * d * math.log(2.0 * math.pi) - 0.5 * t.mean(t.sum(sig2 + mu ** 2, dim=-1), dim=0)
     return term1 - term2 - term3, term1, term2, term3
+
+
+# ------------------------------------------------------ sparse form (large meshes)
+class SparseOracle:
+    """The reference NumPy twin's own solver route -- CSR assembly by
+    (loc_i, loc_j) triplets and ``scipy.sparse.linalg.spsolve``
+    (fem_solver.py:68-126, 244-250) -- vectorised over elements, for meshes
+    where the dense LU of the TF path (6560^2 at 80x40) is too slow on a CPU.
+    Same element formulas as ``solid_2d``."""
+
+    def __init__(self, mesh, dof, thk=10.0, theta_mean=(math.log(20.0), 0.0), theta_std=(0.1, 0.015)):
+        self.mesh, self.dof, self.thk = mesh, dof, thk
+        self.theta_mean, self.theta_std = np.asarray(theta_mean), np.asarray(theta_std)
+        nele = mesh["nele"]
+        xy = mesh["coord"][:, 1:3]
+        sg = gauss_2x2()
+        self.B = np.zeros((nele, 4, 3, 8))
+        self.dvol = np.zeros((nele, 4))
+        for e in range(nele):
+            xl = xy[dof["IEN"][e] - 1].T
+            for g in range(4):
+                shp, xsj = shapef(sg[0:2, g], xl)
+                self.dvol[e, g] = thk * xsj * sg[2, g]
+                self.B[e, g, 0, 0::2] = shp[0]
+                self.B[e, g, 1, 1::2] = shp[1]
+                self.B[e, g, 2, 0::2] = shp[1]
+                self.B[e, g, 2, 1::2] = shp[0]
+        self.lm = dof["LM"].T - 1
+
+    def solve(self, E, v):
+        import scipy.sparse as sp
+        from scipy.sparse.linalg import spsolve
+
+        lam = v * E / ((1 + v) * (1 - 2 * v))
+        mu = 0.5 * E / (1 + v)
+        C3 = np.array([[lam + 2 * mu, lam, 0], [lam, lam + 2 * mu, 0], [0, 0, mu]])
+        Ke = np.einsum("eg,egia,ij,egjb->eab", self.dvol, self.B, C3, self.B)
+        ndof = self.dof["ndof"]
+        rows = np.repeat(self.lm[:, :, None], 8, axis=2).ravel()
+        cols = np.repeat(self.lm[:, None, :], 8, axis=1).ravel()
+        K = sp.csr_matrix((Ke.ravel(), (rows, cols)), shape=(ndof, ndof))
+        free = self.dof["free_dof"] - 1
+        uf = spsolve(K[free][:, free].tocsc(), self.dof["Pf"])
+        u = np.zeros(ndof)
+        u[free] = uf
+        eps3 = np.einsum("egia,ea->egi", self.B, u[self.lm])
+        exx, eyy, gxy = eps3[..., 0], eps3[..., 1], eps3[..., 2]
+        z = np.zeros_like(exx)
+        stress = np.stack([(lam + 2 * mu) * exx + lam * eyy, lam * exx + (lam + 2 * mu) * eyy,
+                           lam * (exx + eyy), mu * gxy, z, z]).transpose(0, 2, 1)  # [6,4,nele]
+        return u, stress
+
+    def fem_fh(self, x, node_id, ele_id, nipt_id=(1, 3)):
+        x = np.atleast_2d(x)
+        y, h = np.zeros((len(x), 2)), np.zeros((len(x), 2))
+        for i, xi in enumerate(x):
+            E, v = theta_to_material(xi, self.theta_mean, self.theta_std)
+            u, stress = self.solve(float(E), float(v))
+            y[i] = u[2 * node_id - 2: 2 * node_id]
+            h[i] = von_mises(stress[:, :, ele_id - 1], nipt_id)
+        return y, h
+
+
+def read_mesh_text(text):
+    """``read_mesh`` on an in-memory string."""
+    import os
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write(text)
+    try:
+        return read_mesh(f.name)
+    finally:
+        os.unlink(f.name)

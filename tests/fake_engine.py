@@ -1,0 +1,36 @@
+"""Test double for CookFemEngine.elbo_step1_partials backed by the CPU oracle
+(test infrastructure: lets the sharding / all-reduce host logic run on CPU)."""
+import os
+
+import numpy as np
+import torch
+
+import fem_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleEngine:
+    def __init__(self):
+        g = np.load(os.path.join(ROOT, "tests", "golden", "ref_numpy_twin.npz"))
+        mesh = {"nnodes": 231, "nele": 200, "coord": g["coord"], "conn": g["IEN"]}
+        dof = {"IEN": g["IEN"], "LM": g["LM"], "free_dof": g["free_dof"], "ndof": 462, "Pf": g["Pf"]}
+        self.oracle = fo.TorchOracle(mesh, dof)
+
+    def elbo_step1_partials(self, mu, sig2, e_data, y_batch, sig_e, j_begin=0, j_end=None, want_f=False):
+        B, S = mu.shape[0], e_data.shape[0]
+        j_end = B * S if j_end is None else j_end
+        with torch.enable_grad():  # called from inside autograd.Function.forward
+            mu = mu.clone().requires_grad_(True)
+            sig2 = sig2.clone().requires_grad_(True)
+            theta = (e_data * sig2.sqrt().unsqueeze(1) + mu.unsqueeze(1)).reshape(-1, 2)[j_begin:j_end]
+            f, _ = self.oracle.fem_fh(theta)
+        fd = f.detach()
+        sums = torch.stack([fd[:, 0].sum(), fd[:, 1].sum(), (fd ** 2).sum()])
+        g = (B * fd - y_batch.sum(0)) / (sig_e * B * (B * S))  # d(loss)/d f_j through -term2
+        if j_end > j_begin:
+            with torch.enable_grad():
+                gmu, gsig2 = torch.autograd.grad((f * g).sum(), [mu, sig2])
+        else:
+            gmu, gsig2 = torch.zeros_like(mu), torch.zeros_like(sig2)
+        return sums, gmu, gsig2, (fd if want_f else None)

@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (i) the
+reference's own outputs (golden vectors of the unmodified NumPy twin), (ii) the
+CPU oracle on the same seeded inputs, (iii) size-independent properties at the
+benchmark's full size.  Tolerance: 1e-9 relative, float64 (BASELINE.json
+north_star); most checks hold to ~1e-12."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import model_from_golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _t(a, eng):
+    import torch
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=eng.device)
+
+
+def test_native_library_is_loaded(engine, pkg):
+    maps = open("/proc/self/maps").read()
+    assert "libvbfem.so" in maps
+    assert engine.info["nfree"] == 440 and engine.info["half_bw"] == 25  # short-side numbering
+    assert engine.info["band_in_smem"] == 1
+
+
+def test_forward_matches_reference_golden(engine, golden):
+    y, h = engine.forward(_t(golden["x"], engine))
+    assert relerr(y.cpu().numpy(), golden["y"]) < TOL
+    assert relerr(h.cpu().numpy(), golden["h"]) < TOL
+    assert engine.status(len(golden["x"]))[0] == 0
+
+
+def test_fields_config1_matches_fem_test(engine, golden):
+    """fem_test.py case (cards E=20, nu=0.3): u, stress, strain, F_int."""
+    out = engine.fields(emat=_t([[20.0, 0.3]], engine))
+    assert relerr(out["u"][0].cpu().numpy(), golden["c1_u"]) < TOL
+    assert relerr(out["stress"][0].cpu().numpy(), golden["c1_stress"]) < TOL
+    assert relerr(out["strain"][0].cpu().numpy(), golden["c1_strain"]) < TOL
+    assert relerr(out["fint"][0].cpu().numpy(), golden["c1_Fint"]) < 1e-8  # F_int_f ~ Pf, reactions
+    u = out["u"][0].cpu().numpy()
+    assert abs(np.abs(u).sum() - 605.7948267813301) < 1e-7
+
+
+def test_fields_theta_samples(engine, golden):
+    out = engine.fields(x=_t(golden["x"], engine), want=("u", "stress"))
+    assert relerr(out["u"].cpu().numpy(), golden["u"]) < TOL
+    assert relerr(out["stress"].cpu().numpy(), golden["stress"]) < TOL
+
+
+def test_fea_solution_drop_in(pkg, golden):
+    """fem_test.py flow on the new backend: initialise from the mesh text, call
+    FemSolver.fea_solution, read results where upstream's scripts read them."""
+    P = pkg.PreProcessing
+    P.modeldata_initialization_topopt(pkg.cook_membrane_feap(20, 10))
+    pkg.FemSolver.fea_solution(input_data=None)
+    step_id = len(P.out_data["step"])
+    assert step_id == 2
+    assert relerr(P.sol_data["u_n1"].ravel(), golden["c1_u"]) < TOL
+    assert relerr(P.out_data["step"][1]["nodal_disp"], golden["c1_nodal_disp"]) < TOL
+    vm = pkg.PostProcessing.von_mises_stress(step_id, 12, np.array([1, 3]))
+    assert relerr(vm, golden["c1_vm"]) < TOL
+    assert P.out_data["step"][1]["tol_vec"][0] < 1e-9  # energy-norm check of src/fem_solver.py:106-124
+
+
+def test_forward_adjoint_vs_oracle_seeded(engine, torch_oracle):
+    n = 256
+    x = np.random.default_rng(0).standard_normal((n, 2))
+    gy = np.random.default_rng(1).standard_normal((n, 2))
+    gh = np.random.default_rng(1).standard_normal((n, 2))
+    yo, ho, gxo = torch_oracle.vjp(x, gy, gh)
+    y, h, gx = engine.forward_backward(_t(x, engine), _t(gy, engine), _t(gh, engine))
+    assert relerr(y.cpu().numpy(), yo) < TOL
+    assert relerr(h.cpu().numpy(), ho) < TOL
+    assert relerr(gx.cpu().numpy(), gxo) < TOL
+    # per-sample relative check on the larger gradient component
+    g = gx.cpu().numpy()
+    assert np.max(np.abs(g - gxo) / np.maximum(np.abs(gxo), 1e-6 * np.abs(gxo).max())) < 1e-7
+    # split forward(keep) + backward gives the same numbers as the fused launch
+    y2, h2 = engine.forward(_t(x, engine), keep_factor=True)
+    gx2 = engine.backward(_t(gy, engine), _t(gh, engine))
+    assert relerr(y2.cpu().numpy(), y.cpu().numpy()) < 1e-13
+    assert relerr(gx2.cpu().numpy(), g) < 1e-12
+
+
+def test_survey_gradient_pin(engine):
+    y, h, gx = engine.forward_backward(_t([[1.0, -1.0]], engine), _t([[0.3, -0.7]], engine),
+                                       _t([[1.1, 0.4]], engine))
+    g = gx.cpu().numpy()[0]
+    assert abs(g[0] - 0.47551330398298) < 1e-10 and abs(g[1] - 0.00314673223922) < 1e-10
+
+
+def test_full_batch_properties(engine):
+    """N=4096 (benchmark size): u ~ 1/E, stresses independent of E under load
+    control, status clean, gradient consistent with finite differences of the
+    CUDA forward itself."""
+    n = 4096
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, 2))
+    y, h = engine.forward(_t(x, engine))
+    assert engine.status(n)[0] == 0
+    xs = x.copy()
+    d = rng.standard_normal(n)
+    xs[:, 0] += d
+    y2, h2 = engine.forward(_t(xs, engine))
+    y, h, y2, h2 = (a.cpu().numpy() for a in (y, h, y2, h2))
+    assert relerr(y2, y * np.exp(-0.1 * d)[:, None]) < 1e-10
+    assert relerr(h2, h) < 1e-10
+    gy, gh = rng.standard_normal((n, 2)), rng.standard_normal((n, 2))
+    _, _, gx = engine.forward_backward(_t(x, engine), _t(gy, engine), _t(gh, engine))
+    eps = 1e-5
+    for k in range(2):
+        xp, xm = x.copy(), x.copy()
+        xp[:, k] += eps
+        xm[:, k] -= eps
+        yp, hp = engine.forward(_t(xp, engine))
+        ym, hm = engine.forward(_t(xm, engine))
+        fd = (((yp - ym).cpu().numpy() * gy).sum(1) + ((hp - hm).cpu().numpy() * gh).sum(1)) / (2 * eps)
+        g = gx.cpu().numpy()[:, k]
+        assert np.max(np.abs(fd - g)) < 2e-6 * max(1.0, np.abs(g).max())
+
+
+def test_edge_cases(engine, torch_oracle):
+    import torch
+    # empty batch
+    y, h = engine.forward(torch.empty(0, 2, dtype=torch.float64, device=engine.device))
+    assert y.shape == (0, 2) and h.shape == (0, 2)
+    # single sample and ragged sizes around the resident-CTA count
+    resident = engine.info["num_sms"] * engine.info["ctas_per_sm"]
+    for n in (1, 3, resident - 1, resident + 1):
+        x = np.random.default_rng(n).standard_normal((n, 2))
+        y, h = engine.forward(_t(x, engine))
+        idx = np.unique(np.array([0, n // 2, n - 1]))
+        yo, ho = torch_oracle.fem_fh(torch.tensor(x[idx]))
+        assert relerr(y.cpu().numpy()[idx], yo.numpy()) < TOL
+        assert relerr(h.cpu().numpy()[idx], ho.numpy()) < TOL
+    # nearly incompressible (nu -> 0.4999): still positive definite, still accurate to 1e-7
+    x = np.array([[0.0, 500.0], [2.0, -500.0]])
+    y, h = engine.forward(_t(x, engine))
+    yo, ho = torch_oracle.fem_fh(torch.tensor(x))
+    assert relerr(y.cpu().numpy(), yo.numpy()) < 1e-7
+    assert engine.status(2)[0] == 0
+    # nu == 0.5 exactly (lambda = inf): flagged, not silently wrong
+    y, h = engine.forward(_t([[0.0, 1e6]], engine))
+    assert engine.status(1)[0] == 1
+
+
+def test_host_entry_points_equal_device_entry_points(engine):
+    n = 300
+    rng = np.random.default_rng(5)
+    x, gy, gh = rng.standard_normal((n, 2)), rng.standard_normal((n, 2)), rng.standard_normal((n, 2))
+    y, h, gx = engine.forward_backward(_t(x, engine), _t(gy, engine), _t(gh, engine))
+    yh, hh, gxh = engine.forward_backward_host(x, gy, gh)
+    assert np.array_equal(yh, y.cpu().numpy()) and np.array_equal(hh, h.cpu().numpy())
+    assert np.array_equal(gxh, gx.cpu().numpy())
+    yf, hf = engine.forward_host(x)
+    assert np.array_equal(yf, yh) and np.array_equal(hf, hh)
+
+
+def test_measurement_data_drop_in_autograd(pkg, golden, golden_model, torch_oracle):
+    """MeasurementData.fem_fh_fun_loop_rev as the differentiable operator
+    (the role it plays at main_custom_training.py:191-196)."""
+    import torch
+    P, M = pkg.PreProcessing, pkg.MeasurementData
+    P.reset()
+    P.model_data = golden_model
+    M.theta_mean, M.theta_std = np.array([math.log(20.0), 0.0]), np.array([0.1, 0.015])
+    M.node_id, M.ele_id, M.nipt_id = 231, 12, np.array([1, 3], dtype=int)
+    dev = torch.device("cuda", 0)
+    x = torch.tensor(golden["x"], device=dev, requires_grad=True)
+    y, h = M.fem_fh_fun_loop_rev(x)
+    w = torch.linspace(0.5, 1.5, 32, dtype=torch.float64, device=dev).reshape(16, 2)
+    ((y * w).sum() + (h * w.flip(0)).sum()).backward()
+    _, _, gxo = torch_oracle.vjp(golden["x"], w.cpu().numpy(), w.flip(0).cpu().numpy())
+    assert relerr(y.detach().cpu().numpy(), golden["y"]) < TOL
+    assert relerr(x.grad.cpu().numpy(), gxo) < TOL
+    # NumPy in -> NumPy out (eager callers: generate_data_fem, postprocess_lib)
+    yn, hn = M.fem_fh_fun_loop_rev(golden["x"])
+    assert isinstance(yn, np.ndarray) and relerr(hn, golden["h"]) < TOL
+    assert relerr(M.fem_f_fun(golden["x"][1]), golden["y"][1]) < TOL
+    assert relerr(M.fem_h_fun(golden["x"][1]), golden["h"][1]) < TOL
+
+
+def test_elbo_step1_fused_vs_oracle(pkg, engine, torch_oracle):
+    import torch
+    import fem_oracle as fo
+    rng = np.random.default_rng(9)
+    B, S = 4, 6
+    mu = rng.standard_normal((B, 2)) * 0.3
+    ls = rng.standard_normal((B, 2)) * 0.2
+    e = rng.standard_normal((S, 2))
+    yb = rng.standard_normal((B, 2)) * 0.5 + np.array([-4.2, 5.7])
+    # oracle
+    mu_o = torch.tensor(mu, requires_grad=True)
+    ls_o = torch.tensor(ls, requires_grad=True)
+    ref, *_ = fo.elbo_step1_torch(torch_oracle, torch.tensor(yb), mu_o, torch.exp(ls_o), torch.tensor(e), 0.1)
+    ref.backward()
+    # CUDA, unsharded
+    mu_c = _t(mu, engine).requires_grad_(True)
+    ls_c = _t(ls, engine).requires_grad_(True)
+    loss_fn = pkg.elbo.Step1Loss(engine, _t(e, engine), 0.1)
+    loss = loss_fn(_t(yb, engine), mu_c, torch.exp(ls_c), ls_c)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    assert relerr(mu_c.grad.cpu().numpy(), mu_o.grad.numpy()) < TOL
+    assert relerr(ls_c.grad.cpu().numpy(), ls_o.grad.numpy()) < TOL
+    # shard-count invariance: partials of 1, 2, 3, 8 shards add up to the same numbers
+    full = engine.elbo_step1_partials(mu_c.detach(), torch.exp(ls_c.detach()), _t(e, engine), _t(yb, engine), 0.1)
+    for world in (2, 3, 8):
+        acc = [torch.zeros_like(t) for t in full[:3]]
+        for r in range(world):
+            lo, hi = pkg.elbo.shard_range(B * S, r, world)
+            part = engine.elbo_step1_partials(mu_c.detach(), torch.exp(ls_c.detach()), _t(e, engine),
+                                              _t(yb, engine), 0.1, lo, hi)
+            for a, p in zip(acc, part[:3]):
+                a += p
+        for a, f in zip(acc, full[:3]):
+            assert relerr(a.cpu().numpy(), f.cpu().numpy()) < 1e-12
+
+
+def test_refined_mesh_80x40(pkg):
+    """Config 4: Cook 80x40 through the same entry points (band spills to HBM)
+    against the sparse CPU oracle; gradient against central differences."""
+    import fem_oracle as fo
+    txt = pkg.cook_membrane_feap(80, 40)
+    P = pkg.PreProcessing
+    md = P.modeldata_initialization_topopt(txt)
+    eng = pkg.CookFemEngine(md, device=0, node_id=3321, ele_id=12)
+    assert eng.info["nfree"] == 6560 and eng.info["half_bw"] == 85
+    m = fo.read_mesh_text(fo.cook_mesh_text(80, 40))
+    so = fo.SparseOracle(m, fo.assign_dof(m))
+    x = np.random.default_rng(4).standard_normal((6, 2))
+    yo, ho = so.fem_fh(x, 3321, 12)
+    y, h = eng.forward(_t(x, eng))
+    assert relerr(y.cpu().numpy(), yo) < TOL and relerr(h.cpu().numpy(), ho) < TOL
+    gy, gh = np.ones((6, 2)), np.full((6, 2), 0.5)
+    _, _, gx = eng.forward_backward(_t(x, eng), _t(gy, eng), _t(gh, eng))
+    eps = 1e-5
+    for k in range(2):
+        xp, xm = x.copy(), x.copy()
+        xp[:, k] += eps
+        xm[:, k] -= eps
+        yp, hp = so.fem_fh(xp, 3321, 12)
+        ym, hm = so.fem_fh(xm, 3321, 12)
+        fd = (((yp - ym) * gy).sum(1) + ((hp - hm) * gh).sum(1)) / (2 * eps)
+        assert np.max(np.abs(fd - gx.cpu().numpy()[:, k])) < 1e-6 * max(1.0, np.abs(fd).max())
+    eng.close()

@@ -1,0 +1,172 @@
+"""CPU tests of the host-side logic and of the C-ABI library as an artefact
+(loads, exports every declared symbol, refuses to run without a GPU)."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, relerr
+
+
+def test_feap_roundtrip_matches_reference_preprocessor(pkg, golden):
+    """Product pre-processor on the generated 20x10 input vs the reference's
+    pre-processor state (model_file.mat content captured in the golden file)."""
+    P = pkg.PreProcessing
+    md = P.modeldata_initialization_topopt(pkg.cook_membrane_feap(20, 10))
+    assert md["mesh_info"]["nnodes"] == 231 and md["mesh_info"]["nele"] == 200
+    assert np.max(np.abs(md["mesh_info"]["coord"] - golden["coord"])) < 1e-12
+    di = md["dof_info"]
+    for k in ("IEN", "LM", "ID", "free_dof", "supp_dof"):
+        assert np.array_equal(di[k], golden[k]), k
+    assert di["ndof"] == 462 and di["nfree"] == 440 and di["nsupp"] == 22
+    assert np.max(np.abs(md["loading"]["Pf"].ravel() - golden["Pf"])) < 1e-14
+    assert P.out_data["ele_stress"].shape == (6, 4, 200, 2)
+    assert md["section"][0]["thk"] == 10 and md["material"][0]["E"] == 20.0
+
+
+def test_feap_parser_handles_crlf_and_trailing_blocks(pkg):
+    txt = pkg.cook_membrane_feap(4, 2).replace("\n", "\r\n") + "Parameters\r\nL = 48\r\nMATErial 1\r\nEND\r\n"
+    m = pkg.fem_preprocess.parse_feap(txt)
+    assert m["nnodes"] == 15 and m["nele"] == 8
+    assert m["support"].shape == (3, 3) and m["nodal_load"].shape == (3, 3)
+    assert abs(m["nodal_load"][:, 2].sum() - 50.0) < 1e-12
+
+
+def test_feap_rejects_bad_input(pkg):
+    with pytest.raises(ValueError):
+        pkg.fem_preprocess.parse_feap("x\n 4 1 1 3 3 8\n\nCOORdinates ALL\n")
+    with pytest.raises(ValueError):  # no loads
+        txt = pkg.cook_membrane_feap(2, 2).split("FORCe conditions")[0] + "\nEND\n"
+        pkg.PreProcessing.modeldata_initialization_topopt(txt)
+
+
+def test_von_mises_host_matches_reference(pkg, golden):
+    P = pkg.PreProcessing
+    P.modeldata_initialization_topopt(pkg.cook_membrane_feap(20, 10))
+    P.out_data["ele_stress"][:, :, :, 1] = golden["c1_stress"]
+    vm = pkg.PostProcessing.von_mises_stress(2, 12, np.array([1, 3]))
+    assert relerr(vm, golden["c1_vm"]) < 1e-14
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg._lib.load()
+    hdr = open(os.path.join(ROOT, "include", "vbfem.h")).read()
+    declared = set(re.findall(r"\b(vbfem_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg._lib.SYMBOLS)
+    for s in declared:
+        assert getattr(lib, s) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    for s in declared:
+        assert re.search(rf"\bT {s}\b", out), s
+
+
+def test_library_is_sm100a_only(pkg):
+    out = subprocess.run(["cuobjdump", "-lelf", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback(pkg, golden_model):
+    """Without a CUDA device the product path must fail loudly, not compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.VbfemError, match="no CUDA device|CPU fallback"):
+        pkg.CookFemEngine(golden_model, device=0)
+
+
+def test_product_does_not_import_oracle():
+    pk = os.path.join(ROOT, "variational-bayesian-inference-for-computational-mechanics_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "fem_oracle" not in src and "/root/reference" not in src, f
+
+
+def test_shard_range_partitions(pkg):
+    for total in (0, 1, 7, 6400, 65536):
+        for world in (1, 2, 3, 8):
+            r = [pkg.elbo.shard_range(total, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_term2_from_sums_equals_broadcast(pkg):
+    import torch
+    rng = np.random.default_rng(3)
+    B, S = 5, 7
+    f = torch.tensor(rng.standard_normal((B * S, 2)))
+    yb = torch.tensor(rng.standard_normal((B, 2)))
+    sums = torch.stack([f[:, 0].sum(), f[:, 1].sum(), (f ** 2).sum()])
+    t2 = pkg.elbo.term2_from_sums(sums, yb, B * S, 0.1)
+    l2 = -0.5 / 0.1 * ((yb.unsqueeze(1) - f) ** 2).sum(-1)  # [B, B*S], main_custom_training.py:210
+    ref = -0.5 * 2 * math.log(2 * math.pi * 0.1) + l2.mean()
+    assert abs(float(t2 - ref)) < 1e-13 * abs(float(ref))
+
+
+def test_step1_model_shape_and_param_count(pkg):
+    import torch
+    m = pkg.elbo.make_step1_model()
+    assert sum(p.numel() for p in m.parameters()) == 1884
+    mu, sig, ls = m(torch.zeros(4, 2, dtype=torch.float64))
+    assert mu.shape == (4, 2) and torch.allclose(sig, torch.exp(ls))
+
+
+_WORKER = r'''
+import os, sys, math
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import importlib
+pkg = importlib.import_module("variational-bayesian-inference-for-computational-mechanics_b200")
+import fem_oracle as fo
+from fake_engine import OracleEngine
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rng = np.random.default_rng(11)
+B, S = 3, 5
+mu = torch.tensor(rng.standard_normal((B, 2)) * 0.3, requires_grad=True)
+ls = torch.tensor(rng.standard_normal((B, 2)) * 0.2, requires_grad=True)
+e = torch.tensor(rng.standard_normal((S, 2)))
+yb = torch.tensor(rng.standard_normal((B, 2)) * 0.5 + np.array([-4.2, 5.7]))
+eng = OracleEngine()
+loss_fn = pkg.elbo.Step1Loss(eng, e, 0.1, group=None, rank=rank, world=world)
+loss = loss_fn(yb, mu, torch.exp(ls), ls)
+loss.backward()
+# single-process oracle of the same thing
+mu2 = mu.detach().clone().requires_grad_(True); ls2 = ls.detach().clone().requires_grad_(True)
+ref, *_ = fo.elbo_step1_torch(eng.oracle, yb, mu2, torch.exp(ls2), e, 0.1)
+ref.backward()
+err = max(abs(float(loss - ref)) / abs(float(ref)),
+          float((mu.grad - mu2.grad).abs().max() / mu2.grad.abs().max()),
+          float((ls.grad - ls2.grad).abs().max() / ls2.grad.abs().max()))
+print("RANK", rank, "ERR", err, flush=True)
+assert err < 1e-10, err
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2])
+def test_step1_loss_sharded_over_gloo_ranks(tmp_path, world):
+    """World-size-2 gloo run of the sharded ELBO step: every rank owns a slice
+    of the Monte-Carlo samples, one all-reduce, result equals the unsharded
+    oracle (value and gradients)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", OMP_NUM_THREADS="2")
+    procs = []
+    for r in range(world):
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), WORLD_SIZE=str(world)),
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ERR" in o

@@ -1,0 +1,116 @@
+"""CPU tests: the oracle against the reference's own outputs (golden vectors
+produced by running the unmodified NumPy twin, tests/golden/make_golden.py)."""
+import math
+
+import numpy as np
+import pytest
+
+import fem_oracle as fo
+from conftest import relerr
+
+TM, TS = (math.log(20.0), 0.0), (0.1, 0.015)
+
+
+def test_mesh_generator_matches_reference_mesh(golden):
+    m = fo.read_mesh_text(fo.cook_mesh_text(20, 10)) if hasattr(fo, "read_mesh_text") else None
+    if m is None:
+        import tempfile, os
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+            f.write(fo.cook_mesh_text(20, 10))
+        m = fo.read_mesh(f.name)
+        os.unlink(f.name)
+    assert np.array_equal(m["conn"], golden["IEN"])
+    assert np.max(np.abs(m["coord"] - golden["coord"])) < 1e-12
+    d = fo.assign_dof(m)
+    assert np.array_equal(d["LM"], golden["LM"])
+    assert np.array_equal(d["ID"], golden["ID"])
+    assert np.array_equal(d["free_dof"], golden["free_dof"])
+    assert np.array_equal(d["supp_dof"], golden["supp_dof"])
+    assert np.max(np.abs(d["Pf"] - golden["Pf"])) < 1e-14  # reference file carries 1e-15 x-loads
+    assert abs(d["Pf"].sum() - 50.0) < 1e-12
+
+
+def test_shape_function_jacobian_pin(golden, oracle_mesh):
+    mesh, dof = oracle_mesh
+    xl = mesh["coord"][dof["IEN"][0] - 1, 1:3].T
+    sg = fo.gauss_2x2()
+    jac = [fo.shapef(sg[0:2, g], xl)[1] * sg[2, g] for g in range(4)]
+    assert relerr(jac, golden["jac_ele1"]) < 1e-14
+
+
+def test_loop_oracle_config1_fields(golden, oracle_mesh):
+    """fem_test.py case (E=20, nu=0.3): every field of the reference run."""
+    lo = fo.LoopOracle(*oracle_mesh)
+    u, fint, strain, stress = lo.solve(20.0, 0.3)
+    assert relerr(u, golden["c1_u"]) < 1e-11
+    assert relerr(stress, golden["c1_stress"]) < 1e-11
+    assert relerr(strain, golden["c1_strain"]) < 1e-11
+    assert relerr(fint, golden["c1_Fint"]) < 1e-10
+    assert relerr(fo.von_mises(stress[:, :, 11], (1, 3)), golden["c1_vm"]) < 1e-11
+    assert abs(np.abs(u).sum() - 605.7948267813301) < 1e-8
+    assert abs(np.abs(stress).sum() - 761.706958610109) < 1e-8
+
+
+def test_loop_oracle_theta_samples(golden, oracle_mesh):
+    lo = fo.LoopOracle(*oracle_mesh)
+    y, h = fo.fem_fh_loop(lo, golden["x"][:3], TM, TS)
+    assert relerr(y, golden["y"][:3]) < 1e-11
+    assert relerr(h, golden["h"][:3]) < 1e-11
+
+
+def test_torch_oracle_matches_reference(golden, torch_oracle):
+    import torch
+    x = torch.tensor(golden["x"])
+    y, h = torch_oracle.fem_fh(x)
+    u, _, stress = torch_oracle.fields(x)
+    assert relerr(y.numpy(), golden["y"]) < 1e-11
+    assert relerr(h.numpy(), golden["h"]) < 1e-11
+    assert relerr(u.numpy(), golden["u"]) < 1e-11
+    assert relerr(stress.numpy(), golden["stress"]) < 1e-11
+
+
+def test_survey_known_answers(torch_oracle):
+    """SURVEY.md 8(c) table (values printed by the reference NumPy twin)."""
+    import torch
+    y, h = torch_oracle.fem_fh(torch.tensor([[0.0, 0.0], [1.0, -1.0]], dtype=torch.float64))
+    assert relerr(y[0].numpy(), [-4.218023950076504, 5.692883043125291]) < 1e-11
+    assert relerr(h[1].numpy(), [0.2771999778329789, 0.2524508932200516]) < 1e-11
+
+
+def test_torch_oracle_gradient_vs_finite_differences(torch_oracle):
+    x = np.array([[1.0, -1.0], [-0.4, 2.0]])
+    gy = np.array([[0.3, -0.7], [1.0, 0.2]])
+    gh = np.array([[1.1, 0.4], [-0.5, 2.0]])
+    _, _, gx = torch_oracle.vjp(x, gy, gh)
+    import torch
+    eps = 1e-5
+    for i in range(2):
+        for k in range(2):
+            xp, xm = x.copy(), x.copy()
+            xp[i, k] += eps
+            xm[i, k] -= eps
+            yp, hp = torch_oracle.fem_fh(torch.tensor(xp))
+            ym, hm = torch_oracle.fem_fh(torch.tensor(xm))
+            fd = ((yp - ym).numpy() * gy).sum() / (2 * eps) + ((hp - hm).numpy() * gh).sum() / (2 * eps)
+            assert abs(fd - gx[i, k]) < 1e-7 * max(1.0, abs(gx[i, k]))
+    # survey pin: at x=(1,-1), gy=(0.3,-0.7), gh=(1.1,0.4)
+    assert abs(gx[0, 0] - 0.47551330398298) < 1e-10
+    assert abs(gx[0, 1] - 0.00314673223922) < 1e-10
+
+
+def test_elbo_broadcast_quirk(torch_oracle):
+    """term2 averages over all B x (B*S) pairs (main_custom_training.py:205-214)."""
+    import torch
+    rng = np.random.default_rng(7)
+    B, S = 3, 4
+    mu = torch.tensor(rng.standard_normal((B, 2)) * 0.3)
+    sig2 = torch.tensor(np.exp(rng.standard_normal((B, 2)) * 0.2))
+    e = torch.tensor(rng.standard_normal((S, 2)))
+    yb = torch.tensor(rng.standard_normal((B, 2)) + np.array([-4.2, 5.7]))
+    loss, t1, t2, t3 = fo.elbo_step1_torch(torch_oracle, yb, mu, sig2, e, 0.1)
+    theta = (e * sig2.sqrt().unsqueeze(1) + mu.unsqueeze(1)).reshape(-1, 2)
+    f, _ = torch_oracle.fem_fh(theta)
+    tot = sum(((yb[b] - f[j]) ** 2).sum() for b in range(B) for j in range(B * S))
+    ref = -0.5 * 2 * math.log(2 * math.pi * 0.1) - 0.5 / 0.1 * tot / (B * B * S)
+    assert abs(float(t2) - float(ref)) < 1e-12 * abs(float(ref))
+    assert abs(float(loss) - float(t1 - t2 - t3)) < 1e-14

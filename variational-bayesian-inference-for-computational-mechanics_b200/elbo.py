@@ -1,0 +1,142 @@
+"""Step-1 ELBO of the variational Bayesian network around the fused CUDA op
+(upstream main_custom_training.py:183-235, 252-258).
+
+loss = term1 - term2 - term3  (= -ELBO), where term2 -- the Monte-Carlo data
+term -- needs one FEM solve per reparameterised sample
+theta[b,s] = e[s] * sqrt(sig2[b]) + mu[b].  The library evaluates, in one
+launch, reparameterisation -> FEM forward -> data-term cotangent -> FEM adjoint
+-> reduction to d(loss)/d(mu, sig2) for a contiguous shard of the flattened
+[B*S] sample axis.  Ranks (one per GPU) own disjoint shards; the only
+collective is one all-reduce(sum) of 3 + 4B doubles per step.
+
+Upstream's data term averages (y_b - f_j)^2 over ALL B x (B*S) pairs because
+f_data is not reshaped back to [B, S, .] (main_custom_training.py:205,210-214);
+that is reproduced here through the sufficient statistics sum_j f_j and
+sum_j |f_j|^2.
+"""
+from __future__ import annotations
+
+import math
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous split of ``total`` samples over ``world`` ranks (first
+    ``total % world`` ranks get one extra)."""
+    q, r = divmod(int(total), int(world))
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def term1(log_theta_sig, theta_dim=2):
+    """main_custom_training.py:183-185."""
+    return (-0.5 * log_theta_sig.sum(dim=-1).mean(dim=0) - 0.5 * theta_dim * math.log(2.0 * math.pi)
+            - 0.5 * theta_dim)
+
+
+def term3(theta_mean, theta_sig, theta_dim=2):
+    """main_custom_training.py:226-229."""
+    return (-0.5 * theta_dim * math.log(2.0 * math.pi)
+            - 0.5 * (theta_sig + theta_mean ** 2).sum(dim=-1).mean(dim=0))
+
+
+def term2_from_sums(sums, y_batch, n_samples, sig_e, y_dim=2):
+    """term2 (main_custom_training.py:199-214) from sum_j f_j (sums[0:2]) and
+    sum_j |f_j|^2 (sums[2]) over all ``n_samples`` = B*S samples."""
+    B = y_batch.shape[0]
+    ysum = y_batch.sum(dim=0)
+    ysq = (y_batch ** 2).sum()
+    tot = B * sums[2] - 2.0 * (sums[0] * ysum[0] + sums[1] * ysum[1]) + n_samples * ysq
+    l1 = -0.5 * y_dim * math.log(2.0 * math.pi * sig_e)
+    return l1 - 0.5 / sig_e * tot / (B * n_samples)
+
+
+def _data_term_function():
+    import torch
+
+    class NegTerm2(torch.autograd.Function):
+        """-term2(mu, sig2) with gradients from the fused FEM adjoint."""
+
+        @staticmethod
+        def forward(ctx, mu, sig2, loss_obj, y_batch):
+            B, S = mu.shape[0], loss_obj.e_data.shape[0]
+            lo, hi = shard_range(B * S, loss_obj.rank, loss_obj.world)
+            sums, gmu, gsig2, _ = loss_obj.engine.elbo_step1_partials(
+                mu.detach().contiguous(), sig2.detach().contiguous(), loss_obj.e_data, y_batch.contiguous(),
+                loss_obj.sig_e, lo, hi)
+            buf = torch.cat([sums, gmu.reshape(-1), gsig2.reshape(-1)])
+            if loss_obj.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=loss_obj.group)
+            ctx.save_for_backward(buf[3:3 + 2 * B].reshape(B, 2), buf[3 + 2 * B:].reshape(B, 2))
+            return -term2_from_sums(buf[:3], y_batch, B * S, loss_obj.sig_e)
+
+        @staticmethod
+        def backward(ctx, g):
+            gmu, gsig2 = ctx.saved_tensors
+            return g * gmu, g * gsig2, None, None
+
+    return NegTerm2
+
+
+_NegTerm2 = None
+
+
+class Step1Loss:
+    """vi_pred_loss_step1 (main_custom_training.py:231-235) on the fused op.
+
+    ``engine`` needs one method, ``elbo_step1_partials`` (CookFemEngine has it);
+    ``group``/``rank``/``world`` describe the torch.distributed process group
+    whose ranks share the Monte-Carlo samples."""
+
+    def __init__(self, engine, e_data, sig_e, group=None, rank=0, world=1):
+        self.engine, self.e_data, self.sig_e = engine, e_data.contiguous(), float(sig_e)
+        self.group, self.rank, self.world = group, int(rank), int(world)
+
+    def __call__(self, y_batch, theta_mean, theta_sig, log_theta_sig):
+        global _NegTerm2
+        if _NegTerm2 is None:
+            _NegTerm2 = _data_term_function()
+        neg_t2 = _NegTerm2.apply(theta_mean, theta_sig, self, y_batch)
+        return term1(log_theta_sig) + neg_t2 - term3(theta_mean, theta_sig)
+
+
+def make_step1_model(num_neuron=20, num_layers=3, y_dim=2, theta_dim=2, device=None, seed=0):
+    """The two float64 MLPs of main_custom_training.py:130-153,176 (Dense+ReLU
+    x3, linear head): returns a module mapping y[B,2] ->
+    (theta_mean, theta_sig = exp(log_theta_sig), log_theta_sig)."""
+    import torch
+    from torch import nn
+
+    def mlp():
+        layers, d = [], y_dim
+        for _ in range(num_layers):
+            layers += [nn.Linear(d, num_neuron), nn.ReLU()]
+            d = num_neuron
+        layers.append(nn.Linear(d, theta_dim))
+        return nn.Sequential(*layers)
+
+    class Step1Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mean_net, self.logsig_net = mlp(), mlp()
+
+        def forward(self, y):
+            m, ls = self.mean_net(y), self.logsig_net(y)
+            return m, torch.exp(ls), ls
+
+    g = torch.Generator().manual_seed(seed)
+    model = Step1Model().double()
+    with torch.no_grad():  # Keras default init: Glorot-uniform kernels, zero biases
+        for mod in model.modules():
+            if isinstance(mod, nn.Linear):
+                lim = math.sqrt(6.0 / (mod.in_features + mod.out_features))
+                mod.weight.copy_((torch.rand(mod.weight.shape, generator=g, dtype=torch.float64) * 2 - 1) * lim)
+                mod.bias.zero_()
+    return model.to(device) if device is not None else model
+
+
+def make_step1_optimizer(model, lr=1e-3):
+    """Adam as configured at main_custom_training.py:243."""
+    import torch
+
+    return torch.optim.Adam(model.parameters(), lr=lr, betas=(0.99, 0.999), eps=1e-10)

@@ -1,0 +1,273 @@
+"""Solver front end: the reference's ``FemSolver.fea_solution`` entry point and
+the batched engine behind it, both running on libvbfem.so (CUDA, sm_100a).
+
+* ``CookFemEngine`` owns one library handle per GPU and exposes the batched
+  forward / adjoint / field calls on torch CUDA tensors (device pointers are
+  handed to the C ABI as plain addresses; launches are ordered on torch's
+  current stream) and on NumPy host arrays (``*_host``).
+* ``FemSolver.fea_solution`` keeps upstream's calling convention
+  (src/fem_solver_tf.py:13-73 / src/fem_solver.py:13-66): no arguments that
+  matter, reads ``PreProcessing.model_data`` (cards E, v), writes
+  ``sol_data['u_n1']``, ``sol_data['F_int']``, ``out_data['ele_stress'|
+  'ele_strain'][..., 1]`` and appends ``out_data['step'][1]`` -- so
+  ``fem_test.py`` and ``fem_postprocess`` work unchanged on the new backend.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from .fem_preprocess import PreProcessing
+
+
+def _as_c(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_double if dtype == np.float64 else ctypes.c_int32))
+
+
+class CookFemEngine:
+    """One libvbfem handle (= one GPU).  Not re-entrant."""
+
+    def __init__(self, model_data=None, device=None, theta_mean=(math.log(20.0), 0.0), theta_std=(0.1, 0.015),
+                 node_id=231, ele_id=12, nipt_id=(1, 3)):
+        import torch
+
+        self.torch = torch
+        self.lib = _lib.load()
+        md = model_data if model_data is not None else PreProcessing.model_data
+        if not md:
+            raise ValueError("PreProcessing.model_data is empty: call modeldata_initialization_topopt first")
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device_index = int(device)
+        mi, di = md["mesh_info"], md["dof_info"]
+        self.nnodes, self.nele, self.ndof = int(mi["nnodes"]), int(mi["nele"]), int(di["ndof"])
+        self.nfree = int(di["nfree"])
+        keep = []
+        mesh = _lib.VbfemMesh()
+        mesh.nnodes, mesh.nele, mesh.nfree = self.nnodes, self.nele, self.nfree
+        a, mesh.coord = _as_c(np.asarray(mi["coord"])[:, 1:3], np.float64); keep.append(a)
+        a, mesh.ien = _as_c(di["IEN"], np.int32); keep.append(a)
+        a, mesh.free_dof = _as_c(di["free_dof"], np.int32); keep.append(a)
+        pf = md["loading"]["Pf"]
+        pf = pf.toarray() if hasattr(pf, "toarray") else np.asarray(pf)
+        a, mesh.pf = _as_c(pf.reshape(-1), np.float64); keep.append(a)
+        mesh.thk = float(md["section"][0]["thk"]) if "section" in md else 10.0
+        mesh.obs_node, mesh.obs_ele = int(node_id), int(ele_id)
+        mesh.obs_gp[0], mesh.obs_gp[1] = int(nipt_id[0]), int(nipt_id[1])
+        for k in range(2):
+            mesh.theta_mean[k] = float(theta_mean[k])
+            mesh.theta_std[k] = float(theta_std[k])
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.vbfem_create(ctypes.byref(h), ctypes.byref(mesh), self.device_index), "vbfem_create")
+        self._h = h
+        self.device = torch.device("cuda", self.device_index)
+        info = (ctypes.c_int64 * _lib.INFO_COUNT)()
+        _lib.check(self.lib.vbfem_info(self._h, info), "vbfem_info")
+        self.info = {name: int(info[i]) for i, name in enumerate(_lib.INFO_NAMES)}
+        self.launches = 0  # kernels launched through this engine (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.vbfem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t, n, name, cols=2):
+        if t.device != self.device or t.dtype != self.torch.float64 or not t.is_contiguous() \
+                or tuple(t.shape) != (n, cols):
+            raise ValueError(f"{name} must be a contiguous float64 [{n},{cols}] tensor on {self.device}")
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _new(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
+
+    # ------------------------------------------------------------ device entry points
+    def forward(self, x, keep_factor=False):
+        """x[N,2] -> y[N,2], h[N,2]  (MeasurementData.fem_fh_fun_loop_rev,
+        src/data_generation_2sam_more_loss.py:169-192)."""
+        n = x.shape[0]
+        y, h = self._new(n, 2), self._new(n, 2)
+        if n:
+            _lib.check(self.lib.vbfem_forward(self._h, n, self._chk(x, n, "x"), ctypes.c_void_p(y.data_ptr()),
+                                              ctypes.c_void_p(h.data_ptr()), int(bool(keep_factor)), self._stream()),
+                       "vbfem_forward")
+            self.launches += 1
+        return y, h
+
+    def backward(self, gy, gh):
+        """(gy, gh) -> gx for the batch of the last forward(keep_factor=True)."""
+        n = gy.shape[0]
+        gx = self._new(n, 2)
+        if n:
+            _lib.check(self.lib.vbfem_backward(self._h, n, self._chk(gy, n, "gy"), self._chk(gh, n, "gh"),
+                                               ctypes.c_void_p(gx.data_ptr()), self._stream()), "vbfem_backward")
+            self.launches += 1
+        return gx
+
+    def forward_backward(self, x, gy, gh):
+        n = x.shape[0]
+        y, h, gx = self._new(n, 2), self._new(n, 2), self._new(n, 2)
+        if n:
+            _lib.check(self.lib.vbfem_forward_backward(
+                self._h, n, self._chk(x, n, "x"), self._chk(gy, n, "gy"), self._chk(gh, n, "gh"),
+                ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(h.data_ptr()), ctypes.c_void_p(gx.data_ptr()),
+                self._stream()), "vbfem_forward_backward")
+            self.launches += 1
+        return y, h, gx
+
+    def fields(self, x=None, emat=None, want=("u", "stress", "strain", "fint")):
+        """Full fields per sample: u[N,ndof], stress/strain[N,6,4,nele],
+        F_int[N,ndof] (src/fem_solver_tf.py:310-341).  Give either x (theta
+        parameterisation) or emat[N,2] = (E, nu)."""
+        src = x if x is not None else emat
+        n = src.shape[0]
+        null = ctypes.c_void_p(0)
+        out = {}
+        if "u" in want:
+            out["u"] = self._new(n, self.ndof)
+        if "stress" in want:
+            out["stress"] = self._new(n, 6, 4, self.nele)
+        if "strain" in want:
+            out["strain"] = self._new(n, 6, 4, self.nele)
+        if "fint" in want:
+            out["fint"] = self._new(n, self.ndof)
+        p = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else null
+        if n:
+            _lib.check(self.lib.vbfem_fields(
+                self._h, n, self._chk(x, n, "x") if x is not None else null,
+                self._chk(emat, n, "emat") if emat is not None else null,
+                p("u"), p("stress"), p("strain"), p("fint"), self._stream()), "vbfem_fields")
+            self.launches += 1
+        return out
+
+    def elbo_step1_partials(self, mu, sig2, e_data, y_batch, sig_e, j_begin=0, j_end=None, want_f=False):
+        """Fused reparameterisation + FEM forward + data-term adjoint for the flat
+        sample range [j_begin, j_end) of the B*S samples
+        (main_custom_training.py:199-214).  Returns (sums[3], gmu[B,2], gsig2[B,2], f|None):
+        range-restricted partial sums that the caller all-reduces."""
+        B, S = int(mu.shape[0]), int(e_data.shape[0])
+        j_end = B * S if j_end is None else int(j_end)
+        sums, gmu, gsig2 = self._new(3), self._new(B, 2), self._new(B, 2)
+        f = self._new(max(j_end - j_begin, 0), 2) if want_f else None
+        _lib.check(self.lib.vbfem_elbo_step1(
+            self._h, B, S, int(j_begin), j_end, self._chk(mu, B, "mu"), self._chk(sig2, B, "sig2"),
+            self._chk(e_data, S, "e_data"), self._chk(y_batch, B, "y_batch"), float(sig_e),
+            ctypes.c_void_p(sums.data_ptr()), ctypes.c_void_p(gmu.data_ptr()), ctypes.c_void_p(gsig2.data_ptr()),
+            ctypes.c_void_p(f.data_ptr()) if want_f else ctypes.c_void_p(0), self._stream()), "vbfem_elbo_step1")
+        self.launches += 3
+        return sums, gmu, gsig2, f
+
+    def status(self, n):
+        """Per-sample status words of the last launch; returns (n_bad, flags)."""
+        flags = np.zeros(int(n), dtype=np.int32)
+        bad = self.lib.vbfem_status(self._h, flags.ctypes.data_as(ctypes.c_void_p), int(n))
+        _lib.check(int(bad), "vbfem_status")
+        return int(bad), flags
+
+    # -------------------------------------------------------------- host entry points
+    def forward_host(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+        n = x.shape[0]
+        y, h = np.empty((n, 2)), np.empty((n, 2))
+        _lib.check(self.lib.vbfem_forward_host(self._h, n, x.ctypes.data_as(ctypes.c_void_p),
+                                               y.ctypes.data_as(ctypes.c_void_p),
+                                               h.ctypes.data_as(ctypes.c_void_p)), "vbfem_forward_host")
+        self.launches += 1 if n else 0
+        return y, h
+
+    def forward_backward_host(self, x, gy, gh):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+        gy = np.ascontiguousarray(gy, dtype=np.float64).reshape(-1, 2)
+        gh = np.ascontiguousarray(gh, dtype=np.float64).reshape(-1, 2)
+        n = x.shape[0]
+        if gy.shape[0] != n or gh.shape[0] != n:
+            raise ValueError("x, gy, gh must have the same number of rows")
+        y, h, gx = np.empty((n, 2)), np.empty((n, 2)), np.empty((n, 2))
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(self.lib.vbfem_forward_backward_host(self._h, n, p(x), p(gy), p(gh), p(y), p(h), p(gx)),
+                   "vbfem_forward_backward_host")
+        self.launches += 1 if n else 0
+        return y, h, gx
+
+
+_engines = {}
+
+
+def default_engine(device=None, **obs):
+    """Engine for the current ``PreProcessing.model_data`` on ``device`` (cached
+    per (model, device, observation setup))."""
+    import torch
+
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    key = (id(PreProcessing.model_data.get("dof_info")), int(device), repr(sorted(obs.items())))
+    eng = _engines.get(key)
+    if eng is None:
+        eng = CookFemEngine(PreProcessing.model_data, device, **obs)
+        _engines[key] = eng
+    return eng
+
+
+class FemSolver:
+    """Drop-in for upstream ``FemSolver`` (src/fem_solver_tf.py:8-73)."""
+
+    @classmethod
+    def fea_solution(cls, input_data=None, device=None):
+        md = PreProcessing.model_data
+        if md["solution_control"]["solver"] != 1:
+            raise ValueError("Illegal solver option")  # src/fem_solver_tf.py:27-28
+        cls.global_linear_solver(device)
+
+    @classmethod
+    def global_linear_solver(cls, device=None):
+        """Load control with one step (src/fem_solver_tf.py:31-73): solve at the
+        card values of (E, v) and publish the fields where upstream does."""
+        import torch
+
+        md, od, sd = PreProcessing.model_data, PreProcessing.out_data, PreProcessing.sol_data
+        eng = default_engine(device)
+        mat = md["material"][0]
+        emat = torch.tensor([[float(mat["E"]), float(mat["v"])]], dtype=torch.float64, device=eng.device)
+        out = eng.fields(emat=emat)
+        bad, _ = eng.status(1)
+        if bad:
+            raise ValueError("Illegal exiting flag")  # src/fem_solver_tf.py:72-73
+        u = out["u"][0].cpu().numpy()
+        nn = md["mesh_info"]["nnodes"]
+        sd["u_n1"] = u.reshape(-1, 1)
+        sd["u_n"] = np.zeros_like(sd["u_n1"])
+        sd["du_n1"] = sd["u_n1"].copy()
+        sd["F_int"] = out["fint"][0].cpu().numpy().reshape(-1, 1)
+        sd["load_factor"] = 1.0
+        od["ele_stress"][:, :, :, 1] = out["stress"][0].cpu().numpy()
+        od["ele_strain"][:, :, :, 1] = out["strain"][0].cpu().numpy()
+        # step record as src/fem_solver.py:41-58,126-143 writes it
+        di = md["dof_info"]
+        free, supp = di["free_dof"] - 1, di["supp_dof"] - 1
+        react = np.zeros(di["ndof"])
+        react[supp] = sd["F_int"][supp, 0]
+        duf = sd["u_n1"][free, 0]
+        resid = sd["F_int"][free, 0] - np.asarray(md["loading"]["Pf"]).reshape(-1)
+        step = {"Pf": md["loading"]["Pf"], "Us": md["loading"]["Us"], "Uf": sd["u_n1"][free],
+                "Ps": sd["F_int"][supp, 0].copy(), "nodal_disp": u.reshape(2, nn, order="F"),
+                "nodal_react": react.reshape(2, nn, order="F"),
+                "tol_vec": np.array([abs(float(duf @ resid))]),  # energy norm, src/fem_solver.py:106-113
+                "iter_vec": np.array([[1]]), "load_ratio": np.array([[1.0]])}
+        if len(od["step"]) > 1:
+            od["step"][1] = step
+        else:
+            od["step"].append(step)
+        sd["exit_flag"] = 1

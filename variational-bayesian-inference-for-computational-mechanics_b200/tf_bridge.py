@@ -1,0 +1,80 @@
+"""TensorFlow side of the drop-in: ``tf.custom_gradient`` around the C-ABI
+library, installed over ``MeasurementData.fem_fh_fun_loop_rev`` so that
+upstream's ``main_custom_training.py`` trains through the CUDA solver.
+
+TensorFlow is not part of this image, so this module is import-guarded and is
+exercised only where TF exists; the torch ``autograd.Function`` in
+``data_generation_2sam_more_loss`` is the tested twin with identical
+semantics.  Graph mode (``tf.function``) cannot hand device pointers to
+ctypes, so the op body runs in a ``tf.py_function`` eager island and moves
+tensors by DLPack (zero-copy on the same GPU).
+"""
+from __future__ import annotations
+
+
+def _engine():
+    from .data_generation_2sam_more_loss import MeasurementData
+    return MeasurementData.engine()
+
+
+def make_fem_fh_op():
+    """Returns ``fem_fh(x) -> [y, h]`` for tf.float64 x[N,2], differentiable."""
+    import tensorflow as tf  # noqa: raises ImportError where TF is absent
+    import torch
+    from torch.utils import dlpack as tdl
+
+    def to_torch(t):
+        return tdl.from_dlpack(tf.experimental.dlpack.to_dlpack(t)).contiguous()
+
+    def to_tf(t):
+        return tf.experimental.dlpack.from_dlpack(tdl.to_dlpack(t))
+
+    def _fwd(x):
+        eng = _engine()
+        with tf.device(f"/GPU:{eng.device_index}"):
+            xt = to_torch(tf.identity(x))
+        y, h = eng.forward(xt, keep_factor=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        return to_tf(y), to_tf(h)
+
+    def _bwd(gy, gh):
+        eng = _engine()
+        with tf.device(f"/GPU:{eng.device_index}"):
+            gyt, ght = to_torch(tf.identity(gy)), to_torch(tf.identity(gh))
+        gx = eng.backward(gyt, ght)
+        torch.cuda.current_stream(eng.device).synchronize()
+        return to_tf(gx)
+
+    @tf.custom_gradient
+    def fem_fh(x):
+        y, h = tf.py_function(_fwd, [x], [tf.float64, tf.float64])
+        y.set_shape(x.shape)
+        h.set_shape(x.shape)
+
+        def grad(gy, gh):
+            gx = tf.py_function(_bwd, [gy, gh], tf.float64)
+            gx.set_shape(x.shape)
+            return gx
+
+        return [y, h], grad
+
+    return fem_fh
+
+
+def install(reference_dg_module):
+    """Monkey-patch upstream's module in place:
+    ``install(src.data_generation_2sam_more_loss)`` replaces
+    ``MeasurementData.fem_fh_fun_loop_rev`` (src/data_generation_2sam_more_loss.py:169-175)
+    and keeps the class attributes (theta_mean, theta_std, node_id, ele_id,
+    nipt_id) in sync with this package's ``MeasurementData``."""
+    from .data_generation_2sam_more_loss import MeasurementData as Mine
+    op = make_fem_fh_op()
+    Ref = reference_dg_module.MeasurementData
+
+    def fem_fh_fun_loop_rev(x):
+        for name in ("theta_mean", "theta_std", "node_id", "ele_id", "nipt_id"):
+            setattr(Mine, name, getattr(Ref, name))
+        return op(x)
+
+    Ref.fem_fh_fun_loop_rev = staticmethod(fem_fh_fun_loop_rev)
+    return op
