@@ -65,6 +65,8 @@ enum {
     VBFEM_INFO_CTAS_PER_SM = 7,
     VBFEM_INFO_NUM_SMS = 8,
     VBFEM_INFO_BLOCK_THREADS = 9,
+    VBFEM_INFO_KERNEL_VARIANT = 10, /* 0 = generic per-column kernel, 1 = twisted on-chip kernel */
+    VBFEM_INFO_TWIST_ROW = 11,      /* first middle row of the twisted factorisation */
     VBFEM_INFO_COUNT = 16
 };
 

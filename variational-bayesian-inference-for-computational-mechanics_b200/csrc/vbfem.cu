@@ -55,6 +55,16 @@ struct DevModel {
     const int *eorder;    // elements sorted by colour
     const double *pf;     // [n] load vector in band order
     const int *band2dof;  // [n] band row -> global dof (0-based)
+    // ---- twisted variant (vbfem_twist.cuh): top front [0, pT), nm middle rows, bottom front mirrored
+    int pT, nB, ndummy, num_sms, bandB_off;
+    int j0T, j0B;           // first local column with a non-zero adjoint right-hand side, per front
+    int obs_lv[2];          // local-vector index of the observed node's dofs, -1 if supported
+    int obs_lmv[8];         // local-vector index of the observed element's dofs
+    double obs_nx[2][4], obs_ny[2][4];  // dN/dx, dN/dy at the two observed Gauss points
+    const short *eoff;      // [nele][40] shared-memory band offset of each lower-triangle element entry, -1 = skip
+    const short *ulm;       // [nele][8] local-vector index of each element dof, -1 if supported
+    const double *pf_loc;   // [n + nm] load vector in local-vector order (scratch tail zero)
+    const int *lv2dof;      // [n] local-vector index -> global dof (0-based)
 };
 
 enum : int {
@@ -163,8 +173,13 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
     return h;
 }
 
+}  // namespace vbfem
+#include "vbfem_twist.cuh"
+namespace vbfem {
+
 // ------------------------------------------------------------------------------------------
-// The per-sample kernel.
+// Generic per-sample kernel (any bandwidth; band in shared memory if it fits, else in HBM).
+// Used when the twisted on-chip variant does not apply (e.g. the 80x40 mesh).
 // ------------------------------------------------------------------------------------------
 template <int NT, int EPT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ DevModel M,
@@ -684,6 +699,8 @@ struct vbfem_handle {
     double *pin = nullptr, *stage = nullptr;
     long long stage_cap = 0;
     int info_colors = 0;
+    int n_real = 0;   // order of the system without padding rows
+    int variant = 0;  // 0 = generic per-column kernel, 1 = twisted warp-synchronous kernel
 };
 
 template <typename T>
@@ -781,6 +798,30 @@ static int configure(vbfem_handle *h, size_t smem) {
     h->ctas_per_sm = nb;
     h->smem_bytes = smem;
     return 0;
+}
+
+// Host copy of shapef_q4 (vbfem_math.cuh) for the sample-independent observation geometry.
+static void host_shapef_q4(const double *x, const double *y, int gp, double *nx, double *ny) {
+    const double g = 0.577350269189626;
+    const double s0 = (gp == 1 || gp == 2) ? g : -g, s1 = (gp >= 2) ? g : -g;
+    const double sh = 0.5 * s0, th = 0.5 * s1;
+    const double sp = 0.5 + sh, tp = 0.5 + th, sm = 0.5 - sh, tm = 0.5 - th;
+    const double xo = x[0] - x[1] + x[2] - x[3];
+    double xs = -x[0] + x[1] + x[2] - x[3] + xo * s1;
+    double xt = -x[0] - x[1] + x[2] + x[3] + xo * s0;
+    const double yo = y[0] - y[1] + y[2] - y[3];
+    double ys = -y[0] + y[1] + y[2] - y[3] + yo * s1;
+    double yt = -y[0] - y[1] + y[2] + y[3] + yo * s0;
+    double xsj1 = xs * yt - xt * ys;
+    xsj1 = (xsj1 != 0.0) ? 1.0 / xsj1 : 1.0;
+    xs = (xs + xs) * xsj1;
+    xt = (xt + xt) * xsj1;
+    ys = (ys + ys) * xsj1;
+    yt = (yt + yt) * xsj1;
+    const double ytm = yt * tm, ysm = ys * sm, ytp = yt * tp, ysp = ys * sp;
+    const double xtm = xt * tm, xsm = xs * sm, xtp = xt * tp, xsp = xs * sp;
+    nx[0] = -ytm + ysm; nx[1] = ytm + ysp; nx[2] = ytp - ysp; nx[3] = -ytp - ysm;
+    ny[0] = xtm - xsm; ny[1] = -xtm - xsp; ny[2] = -xtp + xsp; ny[3] = xtp + xsm;
 }
 
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
@@ -939,10 +980,117 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         return -2;
     }
 
-    // ---- kernel configuration: band in shared memory when two CTAs fit per SM, else in HBM
+    // ---- twisted on-chip variant: band (n x 26 doubles) + vectors must fit twice per SM
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    {
+        // Twisted layout.  The band order is padded with dummy identity rows at its end so that the
+        // top front owns pT = k1*P columns, the middle has P rows and the bottom front owns nB = k2*P
+        // columns (P = 26): every front then runs whole blocks of P columns without bounds checks.
+        constexpr int TB = 25, TP = TB + 1, TNT = 128;
+        const int nblk = (std::max(n - TP, 0) + TP - 1) / TP;  // blocks shared by the two fronts
+        const int kT = (nblk + 1) / 2, kB = nblk - kT;
+        const int pT = kT * TP, nB = kB * TP, np = pT + TP + nB, ndummy = np - n, mid_end = pT + TP;
+        const size_t tw_doubles = (size_t)(np + TP) * TP + 2 * (size_t)(np + TP) + 2 * (TNT / 32) + 32;
+        const size_t tw_smem = tw_doubles * sizeof(double);
+        const bool force_generic = getenv("VBFEM_FORCE_GENERIC") != nullptr;
+        if (!force_generic && b <= TB && kB >= 2 && (np + TP) * TP < 32000 && ndummy < nB &&
+            2 * (tw_smem + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) {
+            M.n = np;
+            M.b = TB;
+            M.ldb = TP;
+            M.pT = pT;
+            M.nB = nB;
+            M.ndummy = ndummy;
+            M.num_sms = prop.multiProcessorCount;
+            M.bandB_off = mid_end * TP;
+            M.band_in_smem = 1;
+            M.vec_off = (np + TP) * TP;
+            M.red_off = M.vec_off + 2 * (np + TP);
+            // padded band index g in [0, np): real rows keep their band index, dummies follow
+            auto lvi = [&](int g) { return g < mid_end ? g : mid_end + (np - 1 - g); };
+            std::vector<short> eoff((size_t)40 * ne, (short)-1), ulm((size_t)8 * ne, (short)-1);
+            for (int e = 0; e < ne; ++e) {
+                int gb[8];
+                for (int a = 0; a < 4; ++a)
+                    for (int c = 0; c < 2; ++c) gb[2 * a + c] = dof2band[2 * (m->ien[4 * e + a] - 1) + c];
+                for (int a = 0; a < 8; ++a) {
+                    if (gb[a] >= 0) ulm[8 * e + a] = (short)lvi(gb[a]);
+                    for (int q = 0; q <= a; ++q) {
+                        if (gb[a] < 0 || gb[q] < 0) continue;
+                        const int lo = std::min(gb[a], gb[q]), hi = std::max(gb[a], gb[q]);
+                        const int off = hi < mid_end ? lo * TP + (hi - lo)
+                                                     : M.bandB_off + (np - 1 - hi) * TP + (hi - lo);
+                        eoff[40 * e + tri(a, q)] = (short)off;
+                    }
+                }
+            }
+            std::vector<double> pf_loc(np + TP, 0.0);
+            std::vector<int> lv2dof(np, -1);
+            for (int i = 0; i < n; ++i) {
+                const int g = m->free_dof[i] - 1;
+                pf_loc[lvi(dof2band[g])] = m->pf[i];
+                lv2dof[lvi(dof2band[g])] = g;
+            }
+            M.j0T = mid_end;
+            M.j0B = nB;
+            auto note_rhs = [&](int lv) {
+                if (lv < 0) return;
+                if (lv < mid_end)
+                    M.j0T = std::min(M.j0T, lv);
+                else
+                    M.j0B = std::min(M.j0B, lv - mid_end);
+            };
+            for (int k = 0; k < 2; ++k) {
+                const int g = dof2band[2 * (m->obs_node - 1) + k];
+                M.obs_lv[k] = g >= 0 ? lvi(g) : -1;
+                note_rhs(M.obs_lv[k]);
+            }
+            double ox[4], oy[4];
+            for (int a = 0; a < 4; ++a) {
+                const int nd = m->ien[4 * (m->obs_ele - 1) + a] - 1;
+                ox[a] = m->coord[2 * nd];
+                oy[a] = m->coord[2 * nd + 1];
+                for (int c = 0; c < 2; ++c) {
+                    const int g = dof2band[2 * nd + c];
+                    M.obs_lmv[2 * a + c] = g >= 0 ? lvi(g) : -1;
+                    note_rhs(M.obs_lmv[2 * a + c]);
+                }
+            }
+            for (int q = 0; q < 2; ++q) host_shapef_q4(ox, oy, m->obs_gp[q] - 1, M.obs_nx[q], M.obs_ny[q]);
+            int rc2 = 0;
+            rc2 |= upload(h, eoff, &M.eoff);
+            rc2 |= upload(h, ulm, &M.ulm);
+            rc2 |= upload(h, pf_loc, &M.pf_loc);
+            rc2 |= upload(h, lv2dof, &M.lv2dof);
+            if (rc2) {
+                vbfem_destroy(h);
+                return -2;
+            }
+            kernel_fn k = fem_twist_kernel<TB, TNT>;
+            cudaError_t e1 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tw_smem);
+            int nb = 0;
+            if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TNT, tw_smem);
+            if (e1 != cudaSuccess || nb < 1) {
+                vbfem_destroy(h);
+                return fail(-3, "twisted kernel does not fit (%zu bytes of shared memory)", tw_smem);
+            }
+            h->kern = k;
+            h->block = TNT;
+            h->ctas_per_sm = std::min(nb, 2);
+            h->smem_bytes = tw_smem;
+            h->variant = 1;
+            h->n_real = n;
+            h->ws_stride = (long long)(np + TP) * TP + np + 8;
+            h->info_colors = ncolors;
+            CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
+            *out = h;
+            return 0;
+        }
+    }
+
+    // ---- generic kernel configuration: band in shared memory when it fits, else in HBM
     const int NT = (M.nitems <= 352) ? 352 : (M.nitems <= 512 ? 256 : (M.nitems <= 4096 ? 512 : 1024));
     const int scratch = 2 * (NT / 32) + 32;
     const size_t band_doubles = ((size_t)n * ldb + 1) & ~(size_t)1;
@@ -993,7 +1141,7 @@ extern "C" void vbfem_destroy(vbfem_t *h) {
 extern "C" int vbfem_info(const vbfem_t *h, int64_t *out) {
     if (!h || !out) return fail(-1, "null argument");
     for (int i = 0; i < VBFEM_INFO_COUNT; ++i) out[i] = 0;
-    out[VBFEM_INFO_NFREE] = h->M.n;
+    out[VBFEM_INFO_NFREE] = h->variant ? h->n_real : h->M.n;
     out[VBFEM_INFO_HALF_BW] = h->M.b;
     out[VBFEM_INFO_NDOF] = h->M.ndof;
     out[VBFEM_INFO_NELE] = h->M.nele;
@@ -1003,6 +1151,8 @@ extern "C" int vbfem_info(const vbfem_t *h, int64_t *out) {
     out[VBFEM_INFO_CTAS_PER_SM] = h->ctas_per_sm;
     out[VBFEM_INFO_NUM_SMS] = h->num_sms;
     out[VBFEM_INFO_BLOCK_THREADS] = h->block;
+    out[VBFEM_INFO_KERNEL_VARIANT] = h->variant;
+    out[VBFEM_INFO_TWIST_ROW] = h->variant ? h->M.pT : 0;
     return 0;
 }
 

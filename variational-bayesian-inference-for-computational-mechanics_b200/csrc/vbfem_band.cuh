@@ -1,0 +1,299 @@
+// vbfem_band.cuh -- warp-synchronous banded LDL^T building blocks (sm_100a).
+//
+// A "front" is one warp eliminating the columns of a banded SPD matrix in LOCAL
+// coordinates (band[c*P + k] = A[c+k][c], k = 0..B, P = B+1).  Lane l owns the
+// rows congruent to l modulo 32.  The active (B+1)x(B+1) window lives in
+// registers: each lane keeps its row's band entries in P accumulator slots
+// indexed by column mod P, so that with the column loop unrolled P times every
+// register index is static.  A lane whose row has just been eliminated idles
+// for 32-P steps before its next row (r+32) becomes active; it uses those
+// steps to reload its slots from the assembled band (which also discards the
+// by-design garbage that rank-1 updates beyond the diagonal left there).  The
+// pivot column is exchanged through shared memory: it is stored exactly where
+// the factor L lives (overwriting K in place) and read back as broadcast
+// 128-bit loads.  There is no block barrier and no bounds check in the column
+// loop: the host pads the system so that every front runs whole blocks of P
+// columns (vbfem.cu, "twisted layout").
+//
+// Two fronts run concurrently on one matrix (twisted factorisation): the top
+// front on columns [0, pT) and, on the mirrored numbering, the bottom front on
+// the last nB columns; their Schur complements meet in the nm = P middle rows,
+// which the top front then finishes.  The triangular sweeps process four rows
+// per step (the 4x4 diagonal block is solved redundantly by every lane), which
+// shortens the dependency chain per row from shuffle+FMA to about a quarter.
+// tests/warp_emulator.py is a lane-level NumPy model of the index logic.
+//
+// Replaces tf.linalg.solve (src/fem_solver_tf.py:137 upstream) and its
+// gradient (the adjoint solve reuses the factor).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vbfem_math.cuh"
+
+namespace vbfem {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int B>
+struct FrontState {
+    static constexpr int P = B + 1;                   // accumulator slots = band column stride
+    static constexpr int GAP = 32 - P;                // idle steps between two rows of a lane
+    static constexpr int NPER = (P + GAP - 1) / GAP;  // slots reloaded per idle step
+    static_assert(P % 2 == 0 && GAP >= 1, "half bandwidth must be odd and <= 29");
+    double acc[P];
+    double zr;
+    int k;  // (lane - j) & 31 for the next column j
+};
+
+// Start of a front at local column 0: lane l takes row l.
+template <int B>
+__device__ __forceinline__ void front_init(FrontState<B> &st, const double *__restrict__ band,
+                                           const double *__restrict__ z, int lane) {
+    constexpr int P = B + 1;
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+        const int t = (lane - s + 2 * P) % P;  // row - column
+        const int c = lane - t;
+        st.acc[s] = (c >= 0) ? band[c * P + t] : 0.0;
+    }
+    st.zr = z[lane];
+    st.k = lane;
+}
+
+// Eliminate nblk blocks of P local columns starting at jb0 (a multiple of P): L (unit lower,
+// sub-diagonals in band[c][1..B]) and 1/d (band[c][0]) overwrite K in place; z[c] receives the
+// forward-eliminated right-hand side.  Rows >= nrows do not exist (their lanes carry harmless
+// garbage).  Returns non-zero if a pivot was non-positive or non-finite.
+template <int B>
+__device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__restrict__ band, int nrows,
+                                               double *__restrict__ z, int jb0, int nblk) {
+    constexpr int P = B + 1, NPER = FrontState<B>::NPER;
+    int flag = 0;
+    int k = st.k;
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int jb = jb0 + blk * P;
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            const int j = jb + u;
+            double *col = band + j * P;
+            const double v = (k <= B) ? st.acc[u] : 0.0;
+            const int src = j & 31;
+            const double d = __shfl_sync(kFull, v, src);
+            const double zj = __shfl_sync(kFull, st.zr, src);
+            flag |= !(d > 0.0 && d < 1.0e300);
+            const double rd = fast_rcp3(d);
+            const double w = v * rd;
+            // the next pivot depends on this one only through the k == 1 lane's own entry: keep that
+            // update off the shared-memory round trip
+            if (k == 1) st.acc[(u + 1) % P] = fma(-(v * v), rd, st.acc[(u + 1) % P]);
+            if (k <= B) col[k] = (k == 0) ? rd : w;
+            if (k == 0) z[j] = zj;
+            __syncwarp();
+            const double2 *c2 = reinterpret_cast<const double2 *>(col);
+#pragma unroll
+            for (int q = 0; q < P / 2; ++q) {
+                const double2 ww = c2[q];
+                if (q == 0) {
+                    if (k != 1) st.acc[(u + 1) % P] = fma(-v, ww.y, st.acc[(u + 1) % P]);
+                } else {
+                    st.acc[(u + 2 * q) % P] = fma(-v, ww.x, st.acc[(u + 2 * q) % P]);
+                    st.acc[(u + 2 * q + 1) % P] = fma(-v, ww.y, st.acc[(u + 2 * q + 1) % P]);
+                }
+            }
+            if (k >= 1 && k <= B) st.zr = fma(-w, zj, st.zr);
+            // idle lanes: reload NPER slots of the row R = j + k that becomes active next.
+            // (R - slot) mod P == (k - P) + C(u, t) reduced once, because jb is a multiple of P.
+            const int R = j + k;
+            const bool ld = (k > B) && (R < nrows);
+            const double *rowp = band + R * P;
+#pragma unroll
+            for (int t = 0; t < NPER; ++t) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int C = ((-(NPER - 1) * u - t) % P + P) % P;
+                int tt = (k - P) + C;
+                tt -= (tt >= P) ? P : 0;
+                if (ld) st.acc[(NPER * u + t) % P] = rowp[-tt * (P - 1)];
+            }
+            if (ld) st.zr = z[R];
+            k = (k - 1) & 31;
+        }
+    }
+    st.k = k;
+    return flag;
+}
+
+// Bottom front, after eliminating its ncols columns (a multiple of P): write the Schur
+// contributions it holds for the P middle rows into its own (zero-initialised) band extension
+// columns [ncols, ncols+P) and its right-hand-side contributions into z[ncols + a].
+template <int B>
+__device__ __forceinline__ void front_dump_middle(const FrontState<B> &st, double *__restrict__ band, int ncols,
+                                                  double *__restrict__ z) {
+    constexpr int P = B + 1;
+    const int k = st.k;
+    if (k < P) {
+        const int R = ncols + k;
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            const int t = (k - s + P) % P;
+            if (t <= k) band[(R - t) * P + t] = st.acc[s];
+        }
+        z[R] = st.zr;
+    }
+}
+
+// Top front at its first middle column pT (a multiple of P): add the bottom front's contributions
+// (mirrored: top middle row a <-> bottom local row ncolsB + P-1-a, same band offset).
+template <int B>
+__device__ __forceinline__ void front_merge_middle(FrontState<B> &st, const double *__restrict__ bandB, int ncolsB,
+                                                   const double *__restrict__ zB) {
+    constexpr int P = B + 1;
+    const int k = st.k;
+    if (k < P) {
+        const double *src = bandB + (ncolsB + P - 1 - k) * P;
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            const int t = (k - s + P) % P;
+            if (t <= k) st.acc[s] += src[t];
+        }
+        st.zr += zB[ncolsB + P - 1 - k];
+    }
+}
+
+// vec[r] *= 1/d_r for rows [0, nrows)
+template <int B>
+__device__ __forceinline__ void front_scale(const double *__restrict__ band, double *__restrict__ vec, int nrows,
+                                            int lane) {
+    for (int r = lane; r < nrows; r += 32) vec[r] *= band[r * (B + 1)];
+    __syncwarp();
+}
+
+// In-place forward substitution L z = w on local columns [lo, hi); rows up to nrows receive
+// their partial sums (rows >= hi are written back unfinished: they belong to the next stage).
+template <int B>
+__device__ __forceinline__ void front_fwd_sweep(const double *__restrict__ band, double *__restrict__ z, int lo,
+                                                int hi, int nrows, int lane) {
+    constexpr int P = B + 1;
+    if (lo >= hi) return;
+    int r = lo + ((lane - lo) & 31);
+    double acc = (r < nrows) ? z[r] : 0.0;
+    int j = lo;
+#pragma unroll 1
+    for (; j + 3 < hi; j += 4) {
+        const double a0 = __shfl_sync(kFull, acc, j & 31), a1 = __shfl_sync(kFull, acc, (j + 1) & 31);
+        const double a2 = __shfl_sync(kFull, acc, (j + 2) & 31), a3 = __shfl_sync(kFull, acc, (j + 3) & 31);
+        const double *c0 = band + j * P;
+        const double l10 = c0[1], l20 = c0[2], l30 = c0[3], l21 = c0[P + 1], l31 = c0[P + 2], l32 = c0[2 * P + 1];
+        const double z0 = a0;
+        const double z1 = fma(-l10, z0, a1);
+        const double z2 = fma(-l21, z1, fma(-l20, z0, a2));
+        const double z3 = fma(-l32, z2, fma(-l31, z1, fma(-l30, z0, a3)));
+        const int k = (lane - j) & 31;
+        if (k < 4) {
+            z[j + k] = (k == 0) ? z0 : (k == 1) ? z1 : (k == 2) ? z2 : z3;
+            r += 32;
+            acc = (r < nrows) ? z[r] : 0.0;
+        } else if (r < nrows) {
+            // row r = j + k: offsets k, k-1, k-2, k-3 into columns j .. j+3
+            const double *p = c0 + k;
+            const double m0 = (k <= B) ? p[0] : 0.0;
+            const double m1 = (k - 1 <= B) ? p[P - 1] : 0.0;
+            const double m2 = (k - 2 <= B) ? p[2 * (P - 1)] : 0.0;
+            const double m3 = (k - 3 <= B) ? p[3 * (P - 1)] : 0.0;
+            acc = fma(-m1, z1, fma(-m0, z0, acc));
+            acc = fma(-m3, z3, fma(-m2, z2, acc));
+        }
+    }
+#pragma unroll 1
+    for (; j < hi; ++j) {
+        const int k = (lane - j) & 31;
+        double lv = 0.0;
+        if (k >= 1 && k <= B && r < nrows) lv = band[j * P + k];
+        const double zj = __shfl_sync(kFull, acc, j & 31);
+        acc = fma(-lv, zj, acc);
+        if (k == 0) {
+            z[j] = zj;
+            r += 32;
+            acc = (r < nrows) ? z[r] : 0.0;
+        }
+    }
+    if (r < nrows) z[r] = acc;  // rows [hi, hi+32): unfinished partial sums
+    __syncwarp();
+}
+
+// In-place back substitution L^T x = y on local rows hi..lo (descending); rows > hi are final,
+// rows < lo receive their partial sums.
+template <int B>
+__device__ __forceinline__ void front_back_sweep(const double *__restrict__ band, double *__restrict__ x, int hi,
+                                                 int lo, int lane) {
+    constexpr int P = B + 1;
+    if (hi < lo) return;
+    int r = hi - ((hi - lane) & 31);
+    double acc = (r >= 0) ? x[r] : 0.0;
+    int j = hi;
+#pragma unroll 1
+    for (; j - 3 >= lo; j -= 4) {
+        const double a0 = __shfl_sync(kFull, acc, j & 31), a1 = __shfl_sync(kFull, acc, (j - 1) & 31);
+        const double a2 = __shfl_sync(kFull, acc, (j - 2) & 31), a3 = __shfl_sync(kFull, acc, (j - 3) & 31);
+        // L[j-p][j-q] (p < q) = band[(j-q)*P + (q-p)]
+        const double *c3 = band + (j - 3) * P;
+        const double l10 = c3[2 * P + 1], l20 = c3[P + 2], l21 = c3[P + 1], l30 = c3[3], l31 = c3[2], l32 = c3[1];
+        const double x0 = a0;
+        const double x1 = fma(-l10, x0, a1);
+        const double x2 = fma(-l21, x1, fma(-l20, x0, a2));
+        const double x3 = fma(-l32, x2, fma(-l31, x1, fma(-l30, x0, a3)));
+        const int i = (j - lane) & 31;
+        if (i < 4) {
+            x[j - i] = (i == 0) ? x0 : (i == 1) ? x1 : (i == 2) ? x2 : x3;
+            r -= 32;
+            acc = (r >= 0) ? x[r] : 0.0;
+        } else if (r >= 0) {
+            // row r = j - i: L[j-q][r] = band[r*P + (i-q)]
+            const double *p = band + r * P + i;
+            const double m0 = (i <= B) ? p[0] : 0.0;
+            const double m1 = (i - 1 <= B) ? p[-1] : 0.0;
+            const double m2 = (i - 2 <= B) ? p[-2] : 0.0;
+            const double m3 = (i - 3 <= B) ? p[-3] : 0.0;
+            acc = fma(-m1, x1, fma(-m0, x0, acc));
+            acc = fma(-m3, x3, fma(-m2, x2, acc));
+        }
+    }
+#pragma unroll 1
+    for (; j >= lo; --j) {
+        const int i = (j - lane) & 31;
+        double lv = 0.0;
+        if (i >= 1 && i <= B && r >= 0) lv = band[r * P + i];
+        const double xj = __shfl_sync(kFull, acc, j & 31);
+        acc = fma(-lv, xj, acc);
+        if (i == 0) {
+            x[j] = xj;
+            r -= 32;
+            acc = (r >= 0) ? x[r] : 0.0;
+        }
+    }
+    if (r >= 0) x[r] = acc;  // rows (lo-32, lo): unfinished partial sums
+    __syncwarp();
+}
+
+// Bottom front: rows [ncols, ncols+P) of x are final (the shared middle, copied from the top
+// front); fold them into the partial sums of rows [ncols-B, ncols).
+template <int B>
+__device__ __forceinline__ void front_apply_known(const double *__restrict__ band, double *__restrict__ x, int ncols,
+                                                  int lane) {
+    constexpr int P = B + 1;
+    const int r = ncols - 1 - lane;
+    if (lane < B && r >= 0) {
+        double a0 = x[r], a1 = 0.0;
+        const double *p = band + r * P;
+#pragma unroll
+        for (int o = 1; o <= B; o += 2) {
+            if (o > lane) a0 = fma(-p[o], x[r + o], a0);
+            if (o + 1 <= B && o + 1 > lane) a1 = fma(-p[o + 1], x[r + o + 1], a1);
+        }
+        x[r] = a0 + a1;
+    }
+    __syncwarp();
+}
+
+}  // namespace vbfem

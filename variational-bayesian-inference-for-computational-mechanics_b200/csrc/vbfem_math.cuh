@@ -26,6 +26,17 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return r;
 }
 
+// Same seed, cubically convergent correction with a three-deep dependency chain:
+// e = 1 - d r0;  r1 = r0 + r0 e (error e^2);  r2 = r1 + r1 e^2 (error e^4 < 2^-80).
+__device__ __forceinline__ double fast_rcp3(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    const double r1 = fma(r, e, r);
+    const double e2 = e * e;
+    return fma(r1, e2, r1);
+}
+
 struct ShapeQ4 {
     double nx[4];  // dN/dx   (shp[0, :])
     double ny[4];  // dN/dy   (shp[1, :])
