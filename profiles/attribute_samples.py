@@ -35,3 +35,14 @@ tot = sum(agg.values())
 print("total samples", tot)
 for loc, s in agg.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 40):
     print(f"{loc[0]}:{loc[1]:<5d} samples {s:7d} ({100*s/tot:5.1f}%)  sass {cnt[loc]:5d}  executed {ex[loc]}")
+
+# ---- phase summary: samples grouped by (file, function-ish line range) given on the command line as
+#      name=file:lo-hi ... after the count argument
+if len(sys.argv) > 5:
+    print("---- phases")
+    for spec in sys.argv[5:]:
+        name, rng = spec.split("=")
+        f, lr = rng.split(":")
+        lo, hi = (int(v) for v in lr.split("-"))
+        s = sum(v for (ff, ln), v in agg.items() if ff == f and lo <= ln <= hi)
+        print(f"{name:24s} {s:7d} samples ({100*s/tot:5.1f}%)")

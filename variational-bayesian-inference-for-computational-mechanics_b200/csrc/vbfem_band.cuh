@@ -64,6 +64,15 @@ __device__ __forceinline__ void front_init(FrontState<B> &st, const double *__re
 // sub-diagonals in band[c][1..B]) and 1/d (band[c][0]) overwrite K in place; z[c] receives the
 // forward-eliminated right-hand side.  Rows >= nrows do not exist (their lanes carry harmless
 // garbage).  Returns non-zero if a pivot was non-positive or non-finite.
+// Predicated shared-memory load straight into an accumulator register (no select / move).
+__device__ __forceinline__ void lds_if(double &dst, const double *p, bool pred) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q ld.shared.f64 %0, [%1]; }"
+                 : "+d"(dst)
+                 : "r"(a), "r"((int)pred)
+                 : "memory");
+}
+
 template <int B>
 __device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__restrict__ band, int nrows,
                                                double *__restrict__ z, int jb0, int nblk) {
@@ -73,6 +82,9 @@ __device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__rest
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
         const int jb = jb0 + blk * P;
+        // The body below is straight-line code (predication only): the warp stays converged between
+        // the shuffles, so the pivot column written by all lanes is visible to the broadcast loads
+        // that follow it in program order; the asm memory clobbers keep the compiler from reordering.
 #pragma unroll
         for (int u = 0; u < P; ++u) {
             const int j = jb + u;
@@ -81,27 +93,36 @@ __device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__rest
             const int src = j & 31;
             const double d = __shfl_sync(kFull, v, src);
             const double zj = __shfl_sync(kFull, st.zr, src);
-            flag |= !(d > 0.0 && d < 1.0e300);
+            flag |= (d > 0.0) ? 0 : 1;
             const double rd = fast_rcp3(d);
             const double w = v * rd;
             // the next pivot depends on this one only through the k == 1 lane's own entry: keep that
             // update off the shared-memory round trip
-            if (k == 1) st.acc[(u + 1) % P] = fma(-(v * v), rd, st.acc[(u + 1) % P]);
-            if (k <= B) col[k] = (k == 0) ? rd : w;
+            const double t1 = (k == 1) ? v * v : 0.0;
+            st.acc[(u + 1) % P] = fma(-t1, rd, st.acc[(u + 1) % P]);
+            const double sv = (k == 0) ? rd : w;
+            if (k <= B) col[k] = sv;
             if (k == 0) z[j] = zj;
-            __syncwarp();
-            const double2 *c2 = reinterpret_cast<const double2 *>(col);
+            asm volatile("" ::: "memory");
+            double2 ww[P / 2];
+            {
+                const unsigned ca = (unsigned)__cvta_generic_to_shared(col);
 #pragma unroll
-            for (int q = 0; q < P / 2; ++q) {
-                const double2 ww = c2[q];
-                if (q == 0) {
-                    if (k != 1) st.acc[(u + 1) % P] = fma(-v, ww.y, st.acc[(u + 1) % P]);
-                } else {
-                    st.acc[(u + 2 * q) % P] = fma(-v, ww.x, st.acc[(u + 2 * q) % P]);
-                    st.acc[(u + 2 * q + 1) % P] = fma(-v, ww.y, st.acc[(u + 2 * q + 1) % P]);
-                }
+                for (int q = 0; q < P / 2; ++q)
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                 : "=d"(ww[q].x), "=d"(ww[q].y)
+                                 : "r"(ca + 16u * q)
+                                 : "memory");
             }
-            if (k >= 1 && k <= B) st.zr = fma(-w, zj, st.zr);
+            const double vm = (k == 1) ? 0.0 : v;
+            st.acc[(u + 1) % P] = fma(-vm, ww[0].y, st.acc[(u + 1) % P]);
+#pragma unroll
+            for (int q = 1; q < P / 2; ++q) {
+                st.acc[(u + 2 * q) % P] = fma(-v, ww[q].x, st.acc[(u + 2 * q) % P]);
+                st.acc[(u + 2 * q + 1) % P] = fma(-v, ww[q].y, st.acc[(u + 2 * q + 1) % P]);
+            }
+            const double wz = (k >= 1 && k <= B) ? w : 0.0;
+            st.zr = fma(-wz, zj, st.zr);
             // idle lanes: reload NPER slots of the row R = j + k that becomes active next.
             // (R - slot) mod P == (k - P) + C(u, t) reduced once, because jb is a multiple of P.
             const int R = j + k;
@@ -109,14 +130,12 @@ __device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__rest
             const double *rowp = band + R * P;
 #pragma unroll
             for (int t = 0; t < NPER; ++t) {
-                constexpr int dummy = 0;
-                (void)dummy;
                 const int C = ((-(NPER - 1) * u - t) % P + P) % P;
                 int tt = (k - P) + C;
                 tt -= (tt >= P) ? P : 0;
-                if (ld) st.acc[(NPER * u + t) % P] = rowp[-tt * (P - 1)];
+                lds_if(st.acc[(NPER * u + t) % P], rowp - tt * (P - 1), ld);
             }
-            if (ld) st.zr = z[R];
+            lds_if(st.zr, z + R, ld);
             k = (k - 1) & 31;
         }
     }
@@ -169,8 +188,16 @@ __device__ __forceinline__ void front_scale(const double *__restrict__ band, dou
     __syncwarp();
 }
 
+// Operands of one 4-row sweep block: the strictly lower part of the 4x4 diagonal block of L
+// (uniform addresses) and this lane's four L entries coupling its row to the block.
+struct SweepBlk {
+    double l10, l20, l21, l30, l31, l32, m0, m1, m2, m3;
+};
+
 // In-place forward substitution L z = w on local columns [lo, hi); rows up to nrows receive
 // their partial sums (rows >= hi are written back unfinished: they belong to the next stage).
+// Four columns per iteration, operands of the next iteration loaded while the current one
+// resolves its shuffle -> 3 FMA chain.
 template <int B>
 __device__ __forceinline__ void front_fwd_sweep(const double *__restrict__ band, double *__restrict__ z, int lo,
                                                 int hi, int nrows, int lane) {
@@ -179,31 +206,47 @@ __device__ __forceinline__ void front_fwd_sweep(const double *__restrict__ band,
     int r = lo + ((lane - lo) & 31);
     double acc = (r < nrows) ? z[r] : 0.0;
     int j = lo;
+    const int nblk = (hi - lo) >> 2;
+    auto load_blk = [&](int jj, int rr, bool on) {
+        SweepBlk s;
+        const double *c0 = band + jj * P;
+        const int k = (lane - jj) & 31;
+        const double *p = c0 + k;
+        const bool v = on && rr < nrows;
+        s.l10 = on ? c0[1] : 0.0;
+        s.l20 = on ? c0[2] : 0.0;
+        s.l30 = on ? c0[3] : 0.0;
+        s.l21 = on ? c0[P + 1] : 0.0;
+        s.l31 = on ? c0[P + 2] : 0.0;
+        s.l32 = on ? c0[2 * P + 1] : 0.0;
+        s.m0 = (v && k >= 1 && k <= B) ? p[0] : 0.0;
+        s.m1 = (v && k >= 2 && k - 1 <= B) ? p[P - 1] : 0.0;
+        s.m2 = (v && k >= 3 && k - 2 <= B) ? p[2 * (P - 1)] : 0.0;
+        s.m3 = (v && k >= 4 && k - 3 <= B) ? p[3 * (P - 1)] : 0.0;
+        return s;
+    };
+    SweepBlk cur = load_blk(j, r, nblk > 0);
 #pragma unroll 1
-    for (; j + 3 < hi; j += 4) {
+    for (int b = 0; b < nblk; ++b, j += 4) {
         const double a0 = __shfl_sync(kFull, acc, j & 31), a1 = __shfl_sync(kFull, acc, (j + 1) & 31);
         const double a2 = __shfl_sync(kFull, acc, (j + 2) & 31), a3 = __shfl_sync(kFull, acc, (j + 3) & 31);
-        const double *c0 = band + j * P;
-        const double l10 = c0[1], l20 = c0[2], l30 = c0[3], l21 = c0[P + 1], l31 = c0[P + 2], l32 = c0[2 * P + 1];
-        const double z0 = a0;
-        const double z1 = fma(-l10, z0, a1);
-        const double z2 = fma(-l21, z1, fma(-l20, z0, a2));
-        const double z3 = fma(-l32, z2, fma(-l31, z1, fma(-l30, z0, a3)));
         const int k = (lane - j) & 31;
-        if (k < 4) {
+        const bool piv = k < 4;
+        const int rn = piv ? r + 32 : r;
+        const SweepBlk nxt = load_blk(j + 4, rn, b + 1 < nblk);
+        const double fresh = (piv && rn < nrows) ? z[rn] : 0.0;
+        const double z0 = a0;
+        const double z1 = fma(-cur.l10, z0, a1);
+        const double z2 = fma(-cur.l21, z1, fma(-cur.l20, z0, a2));
+        const double z3 = fma(-cur.l32, z2, fma(-cur.l31, z1, fma(-cur.l30, z0, a3)));
+        acc = fma(-cur.m1, z1, fma(-cur.m0, z0, acc));
+        acc = fma(-cur.m3, z3, fma(-cur.m2, z2, acc));
+        if (piv) {
             z[j + k] = (k == 0) ? z0 : (k == 1) ? z1 : (k == 2) ? z2 : z3;
-            r += 32;
-            acc = (r < nrows) ? z[r] : 0.0;
-        } else if (r < nrows) {
-            // row r = j + k: offsets k, k-1, k-2, k-3 into columns j .. j+3
-            const double *p = c0 + k;
-            const double m0 = (k <= B) ? p[0] : 0.0;
-            const double m1 = (k - 1 <= B) ? p[P - 1] : 0.0;
-            const double m2 = (k - 2 <= B) ? p[2 * (P - 1)] : 0.0;
-            const double m3 = (k - 3 <= B) ? p[3 * (P - 1)] : 0.0;
-            acc = fma(-m1, z1, fma(-m0, z0, acc));
-            acc = fma(-m3, z3, fma(-m2, z2, acc));
+            acc = fresh;
         }
+        r = rn;
+        cur = nxt;
     }
 #pragma unroll 1
     for (; j < hi; ++j) {
@@ -232,32 +275,48 @@ __device__ __forceinline__ void front_back_sweep(const double *__restrict__ band
     int r = hi - ((hi - lane) & 31);
     double acc = (r >= 0) ? x[r] : 0.0;
     int j = hi;
+    const int nblk = (hi - lo + 1) >> 2;
+    auto load_blk = [&](int jj, int rr, bool on) {
+        SweepBlk s;
+        // L[jj-p][jj-q] (p < q) = band[(jj-q)*P + (q-p)];  L[jj-q][rr] = band[rr*P + (i-q)]
+        const double *c3 = band + (jj - 3) * P;
+        const int i = (jj - lane) & 31;
+        const double *p = band + rr * P + i;
+        const bool v = on && rr >= 0;
+        s.l10 = on ? c3[2 * P + 1] : 0.0;
+        s.l20 = on ? c3[P + 2] : 0.0;
+        s.l21 = on ? c3[P + 1] : 0.0;
+        s.l30 = on ? c3[3] : 0.0;
+        s.l31 = on ? c3[2] : 0.0;
+        s.l32 = on ? c3[1] : 0.0;
+        s.m0 = (v && i >= 1 && i <= B) ? p[0] : 0.0;
+        s.m1 = (v && i >= 2 && i - 1 <= B) ? p[-1] : 0.0;
+        s.m2 = (v && i >= 3 && i - 2 <= B) ? p[-2] : 0.0;
+        s.m3 = (v && i >= 4 && i - 3 <= B) ? p[-3] : 0.0;
+        return s;
+    };
+    SweepBlk cur = load_blk(j, r, nblk > 0);
 #pragma unroll 1
-    for (; j - 3 >= lo; j -= 4) {
+    for (int b = 0; b < nblk; ++b, j -= 4) {
         const double a0 = __shfl_sync(kFull, acc, j & 31), a1 = __shfl_sync(kFull, acc, (j - 1) & 31);
         const double a2 = __shfl_sync(kFull, acc, (j - 2) & 31), a3 = __shfl_sync(kFull, acc, (j - 3) & 31);
-        // L[j-p][j-q] (p < q) = band[(j-q)*P + (q-p)]
-        const double *c3 = band + (j - 3) * P;
-        const double l10 = c3[2 * P + 1], l20 = c3[P + 2], l21 = c3[P + 1], l30 = c3[3], l31 = c3[2], l32 = c3[1];
-        const double x0 = a0;
-        const double x1 = fma(-l10, x0, a1);
-        const double x2 = fma(-l21, x1, fma(-l20, x0, a2));
-        const double x3 = fma(-l32, x2, fma(-l31, x1, fma(-l30, x0, a3)));
         const int i = (j - lane) & 31;
-        if (i < 4) {
+        const bool piv = i < 4;
+        const int rn = piv ? r - 32 : r;
+        const SweepBlk nxt = load_blk(j - 4, rn, b + 1 < nblk);
+        const double fresh = (piv && rn >= 0) ? x[rn] : 0.0;
+        const double x0 = a0;
+        const double x1 = fma(-cur.l10, x0, a1);
+        const double x2 = fma(-cur.l21, x1, fma(-cur.l20, x0, a2));
+        const double x3 = fma(-cur.l32, x2, fma(-cur.l31, x1, fma(-cur.l30, x0, a3)));
+        acc = fma(-cur.m1, x1, fma(-cur.m0, x0, acc));
+        acc = fma(-cur.m3, x3, fma(-cur.m2, x2, acc));
+        if (piv) {
             x[j - i] = (i == 0) ? x0 : (i == 1) ? x1 : (i == 2) ? x2 : x3;
-            r -= 32;
-            acc = (r >= 0) ? x[r] : 0.0;
-        } else if (r >= 0) {
-            // row r = j - i: L[j-q][r] = band[r*P + (i-q)]
-            const double *p = band + r * P + i;
-            const double m0 = (i <= B) ? p[0] : 0.0;
-            const double m1 = (i - 1 <= B) ? p[-1] : 0.0;
-            const double m2 = (i - 2 <= B) ? p[-2] : 0.0;
-            const double m3 = (i - 3 <= B) ? p[-3] : 0.0;
-            acc = fma(-m1, x1, fma(-m0, x0, acc));
-            acc = fma(-m3, x3, fma(-m2, x2, acc));
+            acc = fresh;
         }
+        r = rn;
+        cur = nxt;
     }
 #pragma unroll 1
     for (; j >= lo; --j) {
