@@ -241,10 +241,14 @@ __device__ __forceinline__ void front_fwd_sweep(const double *__restrict__ band,
         const double z3 = fma(-cur.l32, z2, fma(-cur.l31, z1, fma(-cur.l30, z0, a3)));
         acc = fma(-cur.m1, z1, fma(-cur.m0, z0, acc));
         acc = fma(-cur.m3, z3, fma(-cur.m2, z2, acc));
-        if (piv) {
-            z[j + k] = (k == 0) ? z0 : (k == 1) ? z1 : (k == 2) ? z2 : z3;
-            acc = fresh;
-        }
+        // branch-free select of this lane's resolved row (a nested ternary here compiles to a
+        // divergent jump table)
+        double zs = z3;
+        zs = (k == 2) ? z2 : zs;
+        zs = (k == 1) ? z1 : zs;
+        zs = (k == 0) ? z0 : zs;
+        if (piv) z[j + k] = zs;
+        acc = piv ? fresh : acc;
         r = rn;
         cur = nxt;
     }
@@ -311,10 +315,12 @@ __device__ __forceinline__ void front_back_sweep(const double *__restrict__ band
         const double x3 = fma(-cur.l32, x2, fma(-cur.l31, x1, fma(-cur.l30, x0, a3)));
         acc = fma(-cur.m1, x1, fma(-cur.m0, x0, acc));
         acc = fma(-cur.m3, x3, fma(-cur.m2, x2, acc));
-        if (piv) {
-            x[j - i] = (i == 0) ? x0 : (i == 1) ? x1 : (i == 2) ? x2 : x3;
-            acc = fresh;
-        }
+        double xsel = x3;
+        xsel = (i == 2) ? x2 : xsel;
+        xsel = (i == 1) ? x1 : xsel;
+        xsel = (i == 0) ? x0 : xsel;
+        if (piv) x[j - i] = xsel;
+        acc = piv ? fresh : acc;
         r = rn;
         cur = nxt;
     }
