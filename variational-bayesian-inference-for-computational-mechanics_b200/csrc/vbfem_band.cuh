@@ -43,6 +43,12 @@ struct FrontState {
     double acc[P];
     double zr;
     int k;  // (lane - j) & 31 for the next column j
+    // Look-ahead: the rank-1 update of the column eliminated last is applied one step late, in
+    // the shadow of the next column's shuffle -> reciprocal -> first-entry chain.  vp is that
+    // column's (masked) pivot-column entry of this lane, wp its scaled column entries 2..B.
+    double vp;
+    double2 wp[P / 2];  // wp[0] unused
+    int bad;            // OR of the high words of all pivots (sign bit set = non-positive pivot)
 };
 
 // Start of a front at local column 0: lane l takes row l.
@@ -58,12 +64,12 @@ __device__ __forceinline__ void front_init(FrontState<B> &st, const double *__re
     }
     st.zr = z[lane];
     st.k = lane;
+    st.vp = 0.0;
+    st.bad = 0;
+#pragma unroll
+    for (int q = 0; q < P / 2; ++q) st.wp[q] = make_double2(0.0, 0.0);
 }
 
-// Eliminate nblk blocks of P local columns starting at jb0 (a multiple of P): L (unit lower,
-// sub-diagonals in band[c][1..B]) and 1/d (band[c][0]) overwrite K in place; z[c] receives the
-// forward-eliminated right-hand side.  Rows >= nrows do not exist (their lanes carry harmless
-// garbage).  Returns non-zero if a pivot was non-positive or non-finite.
 // Predicated shared-memory load straight into an accumulator register (no select / move).
 __device__ __forceinline__ void lds_if(double &dst, const double *p, bool pred) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -73,58 +79,85 @@ __device__ __forceinline__ void lds_if(double &dst, const double *p, bool pred) 
                  : "memory");
 }
 
+// Predicated shared-memory store (a plain `if (p) *q = v;` compiles to a divergent branch).
+__device__ __forceinline__ void sts_if(double *p, double v, bool pred) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.f64 [%0], %1; }"
+                 :
+                 : "r"(a), "d"(v), "r"((int)pred)
+                 : "memory");
+}
+
+// Apply the pending rank-1 update (column j-1) to the slots of columns j+1 .. j+B-1, where u is
+// the slot of column j.
 template <int B>
-__device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__restrict__ band, int nrows,
-                                               double *__restrict__ z, int jb0, int nblk) {
+__device__ __forceinline__ void front_apply_pending(FrontState<B> &st, const int U) {
+    constexpr int P = B + 1;
+#pragma unroll
+    for (int q = 1; q < P / 2; ++q) {
+        st.acc[(U + 2 * q - 1) % P] = fma(-st.vp, st.wp[q].x, st.acc[(U + 2 * q - 1) % P]);
+        st.acc[(U + 2 * q) % P] = fma(-st.vp, st.wp[q].y, st.acc[(U + 2 * q) % P]);
+    }
+}
+
+// Flush the look-ahead state (call at a block boundary before the window is read or handed over).
+template <int B>
+__device__ __forceinline__ void front_flush(FrontState<B> &st) {
+    front_apply_pending<B>(st, 0);
+    st.vp = 0.0;
+}
+
+// Eliminate nblk blocks of P local columns starting at jb0 (a multiple of P): L (unit lower,
+// sub-diagonals in band[c][1..B]) and 1/d (band[c][0]) overwrite K in place; z[c] receives the
+// forward-eliminated right-hand side.  Rows >= nrows do not exist (their lanes carry harmless
+// garbage).  Pivot signs are collected in st.bad.
+template <int B>
+__device__ __forceinline__ void front_eliminate(FrontState<B> &st, double *__restrict__ band, int nrows,
+                                                double *__restrict__ z, int jb0, int nblk) {
     constexpr int P = B + 1, NPER = FrontState<B>::NPER;
-    int flag = 0;
     int k = st.k;
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
         const int jb = jb0 + blk * P;
         // The body below is straight-line code (predication only): the warp stays converged between
         // the shuffles, so the pivot column written by all lanes is visible to the broadcast loads
-        // that follow it in program order; the asm memory clobbers keep the compiler from reordering.
+        // that follow it in program order; the asm volatile statements keep their relative order.
 #pragma unroll
         for (int u = 0; u < P; ++u) {
             const int j = jb + u;
             double *col = band + j * P;
             const double v = (k <= B) ? st.acc[u] : 0.0;
             const int src = j & 31;
+            // critical chain: pivot d and the first sub-diagonal entry v1 -> 1/d -> the next pivot
+            // column (slot u+1) is final; everything else runs one column late
             const double d = __shfl_sync(kFull, v, src);
+            const double v1 = __shfl_sync(kFull, v, (src + 1) & 31);
             const double zj = __shfl_sync(kFull, st.zr, src);
-            flag |= (d > 0.0) ? 0 : 1;
+            front_apply_pending<B>(st, u);  // column j-1, slots u+1 .. u+B-1
+            st.bad |= __double2hiint(d);
+            const double t1 = v * v1;
             const double rd = fast_rcp3(d);
-            const double w = v * rd;
-            // the next pivot depends on this one only through the k == 1 lane's own entry: keep that
-            // update off the shared-memory round trip
-            const double t1 = (k == 1) ? v * v : 0.0;
             st.acc[(u + 1) % P] = fma(-t1, rd, st.acc[(u + 1) % P]);
+            const double w = v * rd;
             const double sv = (k == 0) ? rd : w;
-            if (k <= B) col[k] = sv;
-            if (k == 0) z[j] = zj;
-            asm volatile("" ::: "memory");
-            double2 ww[P / 2];
+            sts_if(col + k, sv, k <= B);
+            sts_if(z + j, zj, k == 0);
             {
                 const unsigned ca = (unsigned)__cvta_generic_to_shared(col);
 #pragma unroll
-                for (int q = 0; q < P / 2; ++q)
+                for (int q = 1; q < P / 2; ++q)
                     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                                 : "=d"(ww[q].x), "=d"(ww[q].y)
+                                 : "=d"(st.wp[q].x), "=d"(st.wp[q].y)
                                  : "r"(ca + 16u * q)
                                  : "memory");
             }
-            const double vm = (k == 1) ? 0.0 : v;
-            st.acc[(u + 1) % P] = fma(-vm, ww[0].y, st.acc[(u + 1) % P]);
-#pragma unroll
-            for (int q = 1; q < P / 2; ++q) {
-                st.acc[(u + 2 * q) % P] = fma(-v, ww[q].x, st.acc[(u + 2 * q) % P]);
-                st.acc[(u + 2 * q + 1) % P] = fma(-v, ww[q].y, st.acc[(u + 2 * q + 1) % P]);
-            }
+            st.vp = v;
             const double wz = (k >= 1 && k <= B) ? w : 0.0;
             st.zr = fma(-wz, zj, st.zr);
             // idle lanes: reload NPER slots of the row R = j + k that becomes active next.
             // (R - slot) mod P == (k - P) + C(u, t) reduced once, because jb is a multiple of P.
+            // Their pending entry is zero (vp = 0 for k > B) and the lane whose row was the pivot
+            // row applies its (garbage) pending update before its first reload in program order.
             const int R = j + k;
             const bool ld = (k > B) && (R < nrows);
             const double *rowp = band + R * P;
@@ -140,7 +173,6 @@ __device__ __forceinline__ int front_eliminate(FrontState<B> &st, double *__rest
         }
     }
     st.k = k;
-    return flag;
 }
 
 // Bottom front, after eliminating its ncols columns (a multiple of P): write the Schur

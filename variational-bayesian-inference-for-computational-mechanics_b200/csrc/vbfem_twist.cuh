@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(NT, 2) fem_twist_kernel(const __grid_constant_
                 FrontState<B> st;
                 double *z = fr ? vecU + mid_end : vecU;
                 front_init<B>(st, bnd, z, lane);
-                int flag = 0;
 #pragma unroll 1
                 for (int seg = 0; seg < 2; ++seg) {  // one copy of the column loop for all segments
                     if (seg == 1) {
                         if (fr == 1) {
+                            front_flush<B>(st);
                             front_dump_middle<B>(st, bnd, nB, z);
                             __syncwarp();
                         }
@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(NT, 2) fem_twist_kernel(const __grid_constant_
                         if (fr == 1) break;
                         front_merge_middle<B>(st, bandB, nB, vecU + mid_end);
                     }
-                    flag |= front_eliminate<B>(st, bnd, fr ? nB + P : mid_end, z, seg ? pT : 0,
-                                               seg ? 1 : (fr ? nB : pT) / P);
+                    front_eliminate<B>(st, bnd, fr ? nB + P : mid_end, z, seg ? pT : 0,
+                                       seg ? 1 : (fr ? nB : pT) / P);
                 }
-                if (flag && lane == 0) s_flag = 1;
+                if (st.bad < 0 && lane == 0) s_flag = 1;
                 twist_back_solve<B>(M, band, vecU, fr, lane);
             }
 
@@ -236,6 +236,8 @@ __global__ void __launch_bounds__(NT, 2) fem_twist_kernel(const __grid_constant_
                 __syncwarp();
                 f0 = (M.obs_lv[0] >= 0) ? vecU[M.obs_lv[0]] : 0.0;
                 f1 = (M.obs_lv[1] >= 0) ? vecU[M.obs_lv[1]] : 0.0;
+                // a zero or NaN pivot does not set a sign bit but poisons the solution
+                if (lane == 0 && !(fabs(f0) < 1.0e300 && fabs(f1) < 1.0e300)) s_flag = 1;
                 if (lane == 0 && !(A.mode & kLoad)) {
                     if (A.y) {
                         A.y[2 * s] = f0;
