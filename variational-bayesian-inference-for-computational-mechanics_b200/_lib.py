@@ -18,7 +18,7 @@ REPO = os.path.dirname(_HERE)
 INCLUDE = os.path.join(REPO, "include")
 LIB_PATH = os.path.join(CSRC, "libvbfem.so")
 SOURCES = ["vbfem.cu"]
-HEADERS = ["vbfem_math.cuh", "vbfem_band.cuh", os.path.join(INCLUDE, "vbfem.h")]
+HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", os.path.join(INCLUDE, "vbfem.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

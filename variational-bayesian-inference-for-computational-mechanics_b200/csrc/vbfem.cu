@@ -55,16 +55,15 @@ struct DevModel {
     const int *eorder;    // elements sorted by colour
     const double *pf;     // [n] load vector in band order
     const int *band2dof;  // [n] band row -> global dof (0-based)
-    // ---- twisted variant (vbfem_twist.cuh): top front [0, pT), nm middle rows, bottom front mirrored
-    int pT, nB, ndummy, num_sms, bandB_off;
-    int j0T, j0B;           // first local column with a non-zero adjoint right-hand side, per front
-    int obs_lv[2];          // local-vector index of the observed node's dofs, -1 if supported
-    int obs_lmv[8];         // local-vector index of the observed element's dofs
+    // ---- on-chip front kernel (vbfem_front_kernel.cuh): top front [0, pT), P middle rows, bottom
+    //      front mirrored; the internal numbering starts at the observed node
+    int pT, nB, num_sms;
+    int obs_lv[2];          // local-vector index of the observed node's dofs (top front), -1 if supported
+    int obs_lmv[8];         // local-vector index of the observed element's dofs (middle block), -1 if supported
     double obs_nx[2][4], obs_ny[2][4];  // dN/dx, dN/dy at the two observed Gauss points
     const short *eoff;      // [nele][40] shared-memory band offset of each lower-triangle element entry, -1 = skip
     const short *ulm;       // [nele][8] local-vector index of each element dof, -1 if supported
-    const double *pf_loc;   // [n + nm] load vector in local-vector order (scratch tail zero)
-    const int *lv2dof;      // [n] local-vector index -> global dof (0-based)
+    const double *pf_loc;   // [n] load vector in local-vector order
 };
 
 enum : int {
@@ -174,7 +173,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 }
 
 }  // namespace vbfem
-#include "vbfem_twist.cuh"
+#include "vbfem_front_kernel.cuh"
 namespace vbfem {
 
 // ------------------------------------------------------------------------------------------
@@ -686,6 +685,13 @@ struct vbfem_handle {
     int num_sms = 0, ctas_per_sm = 0, block = 0;
     size_t smem_bytes = 0;
     kernel_fn kern = nullptr;
+    kernel_fn kern_front[3] = {nullptr, nullptr, nullptr};  // forward / forward+adjoint / Jacobian
+    // generic kernel configuration (fields mode, meshes the front kernel does not take)
+    DevModel M_gen{};
+    int gen_block = 0, gen_ctas = 0;
+    size_t gen_smem_bytes = 0;
+    long long gen_ws_stride = 0, ws_gen_slots = 0;
+    double *ws_gen = nullptr;
     std::vector<void *> dev_allocs;
     // workspace
     double *ws = nullptr;
@@ -700,7 +706,7 @@ struct vbfem_handle {
     long long stage_cap = 0;
     int info_colors = 0;
     int n_real = 0;   // order of the system without padding rows
-    int variant = 0;  // 0 = generic per-column kernel, 1 = twisted warp-synchronous kernel
+    int variant = 0;  // 0 = generic per-column kernel, 2 = on-chip front kernel
 };
 
 template <typename T>
@@ -980,109 +986,158 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         return -2;
     }
 
-    // ---- twisted on-chip variant: band (n x 26 doubles) + vectors must fit twice per SM
+    // ---- generic kernel configuration (any bandwidth; full fields): band in shared memory when it
+    //      fits, else in HBM
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     {
-        // Twisted layout.  The band order is padded with dummy identity rows at its end so that the
-        // top front owns pT = k1*P columns, the middle has P rows and the bottom front owns nB = k2*P
-        // columns (P = 26): every front then runs whole blocks of P columns without bounds checks.
+        const int NT = (M.nitems <= 352) ? 352 : (M.nitems <= 512 ? 256 : (M.nitems <= 4096 ? 512 : 1024));
+        const int scratch = 2 * (NT / 32) + 32;
+        const size_t band_doubles = ((size_t)n * ldb + 1) & ~(size_t)1;
+        const size_t small = (2 * (size_t)n + scratch) * sizeof(double);
+        const size_t big = small + band_doubles * sizeof(double);
+        const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
+        M.band_in_smem = big <= cap ? 1 : 0;
+        M.vec_off = M.band_in_smem ? (int)band_doubles : 0;
+        M.red_off = M.vec_off + 2 * n;
+        const size_t smem = M.band_in_smem ? big : small;
+        if (M.nitems > 1024 * 16) {
+            vbfem_destroy(h);
+            return fail(-3, "half bandwidth %d too large", b);
+        }
+        if (NT == 352)
+            rc = configure<352, 1, 2>(h, smem);
+        else if (NT == 256)
+            rc = configure<256, 2, 2>(h, smem);
+        else if (NT == 512)
+            rc = configure<512, 8, 1>(h, smem);
+        else
+            rc = configure<1024, 16, 1>(h, smem);
+        if (rc) {
+            vbfem_destroy(h);
+            return rc;
+        }
+        h->ws_stride = (long long)band_doubles + 8;
+        h->gen_ws_stride = h->ws_stride;
+        h->gen_block = h->block;
+        h->gen_ctas = h->ctas_per_sm;
+        h->gen_smem_bytes = h->smem_bytes;
+        h->M_gen = h->M;
+    }
+
+    // ---- on-chip front kernel: band (n x 26 doubles) + five vectors must fit twice per SM
+    {
+        // Layout (vbfem_front_kernel.cuh): the band order is oriented so that it STARTS at the observed
+        // node (its unit vectors then ride along the top front), the observed element's dofs must fit
+        // into the P = 26 middle rows [pT, pT+P), the bottom front owns the last nB rows mirrored.
         constexpr int TB = 25, TP = TB + 1, TNT = 128;
-        const int nblk = (std::max(n - TP, 0) + TP - 1) / TP;  // blocks shared by the two fronts
-        const int kT = (nblk + 1) / 2, kB = nblk - kT;
-        const int pT = kT * TP, nB = kB * TP, np = pT + TP + nB, ndummy = np - n, mid_end = pT + TP;
-        const size_t tw_doubles = (size_t)(np + TP) * TP + 2 * (size_t)(np + TP) + 2 * (TNT / 32) + 32;
-        const size_t tw_smem = tw_doubles * sizeof(double);
-        const bool force_generic = getenv("VBFEM_FORCE_GENERIC") != nullptr;
-        if (!force_generic && b <= TB && kB >= 2 && (np + TP) * TP < 32000 && ndummy < nB &&
-            2 * (tw_smem + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) {
-            M.n = np;
+        int tip[2], er[8], elo = 1 << 30, ehi = -1, tlo = 1 << 30, thi = -1;
+        for (int k = 0; k < 2; ++k) {
+            tip[k] = dof2band[2 * (m->obs_node - 1) + k];
+            if (tip[k] >= 0) {
+                tlo = std::min(tlo, tip[k]);
+                thi = std::max(thi, tip[k]);
+            }
+        }
+        for (int a = 0; a < 4; ++a)
+            for (int c = 0; c < 2; ++c) {
+                const int g = dof2band[2 * (m->ien[4 * (m->obs_ele - 1) + a] - 1) + c];
+                er[2 * a + c] = g;
+                if (g >= 0) {
+                    elo = std::min(elo, g);
+                    ehi = std::max(ehi, g);
+                }
+            }
+        bool ok = getenv("VBFEM_FORCE_GENERIC") == nullptr && b <= TB && ehi >= 0 && ehi - elo < TP;
+        bool flip = false;
+        if (ok && thi >= 0) {
+            if (tlo > ehi)
+                flip = true;  // observed node behind the observed element: reverse the band order
+            else if (thi >= elo)
+                ok = false;   // observed node inside the element's row range: generic kernel
+        }
+        auto ori = [&](int g) { return (g < 0) ? g : (flip ? n - 1 - g : g); };
+        int pT = 0;
+        if (ok) {
+            const int lo = flip ? n - 1 - ehi : elo, hi = flip ? n - 1 - elo : ehi;
+            const int tmax = (thi < 0) ? -1 : (flip ? n - 1 - tlo : thi);
+            // pT in [hi-P+1, lo], above the observed node, both fronts at least 32 columns
+            const int pmin = std::max({hi - TP + 1, tmax + 1, 32}), pmax = std::min(lo, n - TP - 32);
+            if (pmin > pmax) ok = false;
+            // balance: the top front also eliminates the middle block
+            pT = std::min(std::max((n - 2 * TP) / 2, pmin), pmax);
+        }
+        const size_t fr_doubles = (size_t)n * TP + 5 * (size_t)n + 32 + 32 + 8 * (TNT / 32);
+        const size_t fr_smem = fr_doubles * sizeof(double);
+        if (ok && (n % 2 != 0 || (size_t)n * TP >= 32000 ||
+                   2 * (fr_smem + 1024) > (size_t)prop.sharedMemPerMultiprocessor))
+            ok = false;
+        if (ok) {
+            const int me = pT + TP, nB = n - me;
             M.b = TB;
             M.ldb = TP;
             M.pT = pT;
             M.nB = nB;
-            M.ndummy = ndummy;
             M.num_sms = prop.multiProcessorCount;
-            M.bandB_off = mid_end * TP;
             M.band_in_smem = 1;
-            M.vec_off = (np + TP) * TP;
-            M.red_off = M.vec_off + 2 * (np + TP);
-            // padded band index g in [0, np): real rows keep their band index, dummies follow
-            auto lvi = [&](int g) { return g < mid_end ? g : mid_end + (np - 1 - g); };
+            // oriented band row g -> local vector index / band storage
+            auto lvi = [&](int g) { return g < me ? g : me + (n - 1 - g); };
             std::vector<short> eoff((size_t)40 * ne, (short)-1), ulm((size_t)8 * ne, (short)-1);
             for (int e = 0; e < ne; ++e) {
                 int gb[8];
                 for (int a = 0; a < 4; ++a)
-                    for (int c = 0; c < 2; ++c) gb[2 * a + c] = dof2band[2 * (m->ien[4 * e + a] - 1) + c];
+                    for (int c = 0; c < 2; ++c) gb[2 * a + c] = ori(dof2band[2 * (m->ien[4 * e + a] - 1) + c]);
                 for (int a = 0; a < 8; ++a) {
                     if (gb[a] >= 0) ulm[8 * e + a] = (short)lvi(gb[a]);
                     for (int q = 0; q <= a; ++q) {
                         if (gb[a] < 0 || gb[q] < 0) continue;
                         const int lo = std::min(gb[a], gb[q]), hi = std::max(gb[a], gb[q]);
-                        const int off = hi < mid_end ? lo * TP + (hi - lo)
-                                                     : M.bandB_off + (np - 1 - hi) * TP + (hi - lo);
+                        // top + middle rows: column lo of the top band; bottom rows: mirrored column of hi
+                        const int off = hi < me ? lo * TP + (hi - lo) : me * TP + (n - 1 - hi) * TP + (hi - lo);
                         eoff[40 * e + tri(a, q)] = (short)off;
                     }
                 }
             }
-            std::vector<double> pf_loc(np + TP, 0.0);
-            std::vector<int> lv2dof(np, -1);
-            for (int i = 0; i < n; ++i) {
-                const int g = m->free_dof[i] - 1;
-                pf_loc[lvi(dof2band[g])] = m->pf[i];
-                lv2dof[lvi(dof2band[g])] = g;
-            }
-            M.j0T = mid_end;
-            M.j0B = nB;
-            auto note_rhs = [&](int lv) {
-                if (lv < 0) return;
-                if (lv < mid_end)
-                    M.j0T = std::min(M.j0T, lv);
-                else
-                    M.j0B = std::min(M.j0B, lv - mid_end);
-            };
-            for (int k = 0; k < 2; ++k) {
-                const int g = dof2band[2 * (m->obs_node - 1) + k];
-                M.obs_lv[k] = g >= 0 ? lvi(g) : -1;
-                note_rhs(M.obs_lv[k]);
-            }
+            std::vector<double> pf_loc(n, 0.0);
+            for (int i = 0; i < n; ++i) pf_loc[lvi(ori(dof2band[m->free_dof[i] - 1]))] = m->pf[i];
+            for (int k = 0; k < 2; ++k) M.obs_lv[k] = tip[k] >= 0 ? lvi(ori(tip[k])) : -1;
             double ox[4], oy[4];
             for (int a = 0; a < 4; ++a) {
                 const int nd = m->ien[4 * (m->obs_ele - 1) + a] - 1;
                 ox[a] = m->coord[2 * nd];
                 oy[a] = m->coord[2 * nd + 1];
-                for (int c = 0; c < 2; ++c) {
-                    const int g = dof2band[2 * nd + c];
-                    M.obs_lmv[2 * a + c] = g >= 0 ? lvi(g) : -1;
-                    note_rhs(M.obs_lmv[2 * a + c]);
-                }
+                for (int c = 0; c < 2; ++c) M.obs_lmv[2 * a + c] = er[2 * a + c] >= 0 ? lvi(ori(er[2 * a + c])) : -1;
             }
             for (int q = 0; q < 2; ++q) host_shapef_q4(ox, oy, m->obs_gp[q] - 1, M.obs_nx[q], M.obs_ny[q]);
             int rc2 = 0;
             rc2 |= upload(h, eoff, &M.eoff);
             rc2 |= upload(h, ulm, &M.ulm);
             rc2 |= upload(h, pf_loc, &M.pf_loc);
-            rc2 |= upload(h, lv2dof, &M.lv2dof);
             if (rc2) {
                 vbfem_destroy(h);
                 return -2;
             }
-            kernel_fn k = fem_twist_kernel<TB, TNT>;
-            cudaError_t e1 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tw_smem);
-            int nb = 0;
-            if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TNT, tw_smem);
-            if (e1 != cudaSuccess || nb < 1) {
-                vbfem_destroy(h);
-                return fail(-3, "twisted kernel does not fit (%zu bytes of shared memory)", tw_smem);
+            kernel_fn ks[3] = {fem_front_kernel<TB, TNT, 0>, fem_front_kernel<TB, TNT, 1>,
+                               fem_front_kernel<TB, TNT, 2>};
+            int nbmin = 1 << 30;
+            for (int q = 0; q < 3; ++q) {
+                cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr_smem);
+                int nb = 0;
+                if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], TNT, fr_smem);
+                if (e1 != cudaSuccess || nb < 1) {
+                    vbfem_destroy(h);
+                    return fail(-3, "front kernel does not fit (%zu bytes of shared memory)", fr_smem);
+                }
+                nbmin = std::min(nbmin, nb);
+                h->kern_front[q] = ks[q];
             }
-            h->kern = k;
             h->block = TNT;
-            h->ctas_per_sm = std::min(nb, 2);
-            h->smem_bytes = tw_smem;
-            h->variant = 1;
+            h->ctas_per_sm = std::min(nbmin, 2);
+            h->smem_bytes = fr_smem;
+            h->variant = 2;
             h->n_real = n;
-            h->ws_stride = (long long)(np + TP) * TP + np + 8;
+            h->ws_stride = 8;  // the 4x2 Jacobian d(y, h)/dx per sample
             h->info_colors = ncolors;
             CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
             *out = h;
@@ -1090,34 +1145,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         }
     }
 
-    // ---- generic kernel configuration: band in shared memory when it fits, else in HBM
-    const int NT = (M.nitems <= 352) ? 352 : (M.nitems <= 512 ? 256 : (M.nitems <= 4096 ? 512 : 1024));
-    const int scratch = 2 * (NT / 32) + 32;
-    const size_t band_doubles = ((size_t)n * ldb + 1) & ~(size_t)1;
-    const size_t small = (2 * (size_t)n + scratch) * sizeof(double);
-    const size_t big = small + band_doubles * sizeof(double);
-    const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
-    M.band_in_smem = big <= cap ? 1 : 0;
-    M.vec_off = M.band_in_smem ? (int)band_doubles : 0;
-    M.red_off = M.vec_off + 2 * n;
-    const size_t smem = M.band_in_smem ? big : small;
-    if (M.nitems > 1024 * 16) {
-        vbfem_destroy(h);
-        return fail(-3, "half bandwidth %d too large", b);
-    }
-    if (NT == 352)
-        rc = configure<352, 1, 2>(h, smem);
-    else if (NT == 256)
-        rc = configure<256, 2, 2>(h, smem);
-    else if (NT == 512)
-        rc = configure<512, 8, 1>(h, smem);
-    else
-        rc = configure<1024, 16, 1>(h, smem);
-    if (rc) {
-        vbfem_destroy(h);
-        return rc;
-    }
-    h->ws_stride = (long long)band_doubles + 8;
+    // ---- no front kernel for this mesh / observation set-up: the generic kernel serves every mode
     h->info_colors = ncolors;
     CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
     *out = h;
@@ -1129,6 +1157,7 @@ extern "C" void vbfem_destroy(vbfem_t *h) {
     cudaSetDevice(h->device);
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->ws);
+    cudaFree(h->ws_gen);
     cudaFree(h->status);
     cudaFree(h->elbo_f);
     cudaFree(h->elbo_g);
@@ -1156,14 +1185,15 @@ extern "C" int vbfem_info(const vbfem_t *h, int64_t *out) {
     return 0;
 }
 
-static int ensure_ws(vbfem_handle *h, long long slots) {
-    if (slots <= h->ws_slots) return 0;
+static int ensure_ws(vbfem_handle *h, double **ws, long long *have, long long stride, long long slots) {
+    if (slots <= *have) return 0;
     CU(cudaDeviceSynchronize());
-    cudaFree(h->ws);
-    h->ws = nullptr;
-    h->ws_slots = 0;
-    CU(cudaMalloc(&h->ws, (size_t)slots * h->ws_stride * sizeof(double)));
-    h->ws_slots = slots;
+    cudaFree(*ws);
+    *ws = nullptr;
+    *have = 0;
+    CU(cudaMalloc(ws, (size_t)slots * stride * sizeof(double)));
+    *have = slots;
+    (void)h;
     return 0;
 }
 static int ensure_status(vbfem_handle *h, long long n) {
@@ -1180,22 +1210,41 @@ static int ensure_status(vbfem_handle *h, long long n) {
 static int launch(vbfem_handle *h, Args &a, void *stream) {
     if (a.N <= 0) return 0;
     CU(cudaSetDevice(h->device));
-    const long long resident = (long long)h->num_sms * h->ctas_per_sm;
-    const long long grid = std::min<long long>(a.N, resident);
-    const bool per_sample_ws = (a.mode & (kKeep | kLoad)) != 0;
-    if (per_sample_ws || !h->M.band_in_smem) {
-        int rc = ensure_ws(h, per_sample_ws ? std::max(a.N, h->ws_slots) : std::max(grid, h->ws_slots));
-        if (rc) return rc;
-        a.ws = h->ws;
-        a.ws_stride = h->ws_stride;
-    }
+    const bool front = h->variant == 2 && !(a.mode & kFields);
     if (!(a.mode & kLoad)) {
         int rc = ensure_status(h, a.N);
         if (rc) return rc;
         a.status = h->status;
         h->last_n = a.N;
     }
-    h->kern<<<(unsigned)grid, h->block, h->smem_bytes, (cudaStream_t)stream>>>(h->M, a);
+    if (front) {
+        const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);
+        if (a.mode & (kKeep | kLoad)) {
+            int rc = ensure_ws(h, &h->ws, &h->ws_slots, h->ws_stride, std::max(a.N, h->ws_slots));
+            if (rc) return rc;
+            a.ws = h->ws;
+            a.ws_stride = h->ws_stride;
+        }
+        if (a.mode & kLoad) {  // backward: gx = J^T (gy, gh) with the Jacobians a forward(keep) left behind
+            const int nt = 256;
+            jac_apply_kernel<<<(unsigned)((a.N + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+                a.N, h->ws, h->ws_stride, a.gy, a.gh, a.gx);
+        } else {
+            const int mode = (a.mode & kKeep) ? 2 : ((a.mode & kAdjoint) ? 1 : 0);
+            h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, (cudaStream_t)stream>>>(h->M, a);
+        }
+    } else {
+        const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->gen_ctas);
+        const bool per_sample_ws = (a.mode & (kKeep | kLoad)) != 0;
+        if (per_sample_ws || !h->M_gen.band_in_smem) {
+            int rc = ensure_ws(h, &h->ws_gen, &h->ws_gen_slots, h->gen_ws_stride,
+                               per_sample_ws ? std::max(a.N, h->ws_gen_slots) : std::max(grid, h->ws_gen_slots));
+            if (rc) return rc;
+            a.ws = h->ws_gen;
+            a.ws_stride = h->gen_ws_stride;
+        }
+        h->kern<<<(unsigned)grid, h->gen_block, h->gen_smem_bytes, (cudaStream_t)stream>>>(h->M_gen, a);
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1213,7 +1262,7 @@ extern "C" int vbfem_forward(vbfem_t *h, int64_t N, const double *x, double *y, 
 
 extern "C" int vbfem_backward(vbfem_t *h, int64_t N, const double *gy, const double *gh, double *gx, void *stream) {
     if (!h || (N > 0 && (!gy || !gh || !gx))) return fail(-1, "null argument");
-    if (N > h->ws_slots || N > h->last_n)
+    if (N > (h->variant == 2 ? h->ws_slots : h->ws_gen_slots) || N > h->last_n)
         return fail(-5, "vbfem_backward: no stored factor for %lld samples (call vbfem_forward with keep_factor=1)",
                     (long long)N);
     Args a{};
