@@ -64,6 +64,7 @@ struct DevModel {
     const short *eoff;      // [nele][40] shared-memory band offset of each lower-triangle element entry, -1 = skip
     const short *ulm;       // [nele][8] local-vector index of each element dof, -1 if supported
     const double *pf_loc;   // [n] load vector in local-vector order
+    int *sm_ticket;         // [num_sms] running CTA tickets per SM
 };
 
 enum : int {
@@ -1114,6 +1115,12 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             rc2 |= upload(h, eoff, &M.eoff);
             rc2 |= upload(h, ulm, &M.ulm);
             rc2 |= upload(h, pf_loc, &M.pf_loc);
+            {
+                std::vector<int> zero(prop.multiProcessorCount, 0);
+                const int *p = nullptr;
+                rc2 |= upload(h, zero, &p);
+                M.sm_ticket = const_cast<int *>(p);
+            }
             if (rc2) {
                 vbfem_destroy(h);
                 return -2;

@@ -109,38 +109,48 @@ __device__ __forceinline__ void front_flush(FrontState<B> &st) {
 
 // Eliminate local columns [j0, j1): L (unit lower, sub-diagonals in band[c][1..B]) and 1/d
 // (band[c][0]) overwrite K in place; z_r[c] receives the forward-eliminated right-hand sides.
-// Rows >= nrows do not exist.  Loads of columns beyond the stored band must hit zeroed memory.
+// Rows beyond the end of the matrix are not masked: their lanes read whatever lies behind the band
+// (the kernel keeps zeros or finite data there) and only ever touch their own registers and the
+// unused tail slots of the last columns.  Loads of columns beyond the stored band that belong to
+// existing rows must hit zeroed memory.
+// The loop is rotated: the broadcasts of column j+1 are issued as soon as its entries are final,
+// so their latency overlaps the stores / loads that finish column j.
 template <int B, int NRA>
-__device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band, int nrows, unsigned zs,
-                                                unsigned vs, int j0, int j1) {
+__device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band, unsigned zs, unsigned vs, int j0,
+                                                int j1) {
     constexpr int P = B + 1;
     int k = st.k, R = st.R;
     unsigned pk = st.pk;
-    bool rowok = R < nrows;
     unsigned colp = band + 8u * (unsigned)(j0 * P);
     unsigned zp = zs + 8u * (unsigned)j0;
+    double v = st.cur[0];
+    double d = __shfl_sync(kFull, v, j0 & 31);
+    double v1 = __shfl_sync(kFull, v, (j0 + 1) & 31);
+    double zj[NRA];
+#pragma unroll
+    for (int r = 0; r < NRA; ++r) zj[r] = __shfl_sync(kFull, st.zr[r], j0 & 31);
 #pragma unroll 1
     for (int j = j0; j < j1; ++j) {
-        const bool act = (k <= B) && rowok;
-        const double v = act ? st.cur[0] : 0.0;
-        const int src = j & 31;
-        // critical chain: pivot d and first sub-diagonal entry v1 -> 1/d -> next pivot column
-        const double d = __shfl_sync(kFull, v, src);
-        const double v1 = __shfl_sync(kFull, v, (src + 1) & 31);
-        double zj[NRA];
-#pragma unroll
-        for (int r = 0; r < NRA; ++r) zj[r] = __shfl_sync(kFull, st.zr[r], src);
+        const bool sub = (unsigned)(k - 1) < (unsigned)B;  // 1 <= k <= B: a sub-diagonal row of column j
+        const double vm = sub ? v : 0.0;
+        const double t1 = vm * v1;
+        const double rd = fast_rcp3(d);
+        st.bad |= __double2hiint(d);
         // late update of column j-1, written one slot down: the window slides with the pivot
 #pragma unroll
         for (int t = 1; t < B; ++t) st.cur[t - 1] = fma(-st.vp, wp_at<B>(st, t + 1), st.cur[t]);
         st.cur[B - 1] = st.cur[B];
         st.cur[B] = st.cur[B + 1];
-        st.bad |= __double2hiint(d);
-        const double t1 = v * v1;
-        const double rd = fast_rcp3(d);
+        // first entry of column j's update: the next pivot column is final -> broadcast it now
         st.cur[0] = fma(-t1, rd, st.cur[0]);
-        const double w = v * rd;
-        sts_if(pk, (k == 0) ? rd : w, k <= B);
+        const int srcn = (j + 1) & 31;
+        const double vn = st.cur[0];
+        const double dn = __shfl_sync(kFull, vn, srcn);
+        const double v1n = __shfl_sync(kFull, vn, (srcn + 1) & 31);
+        // column j: L entries and 1/d to the band, eliminated right-hand sides to z
+        const double w = vm * rd;
+        sts_if(pk, w, sub);
+        sts_if(colp, rd, k == 0);
 #pragma unroll
         for (int r = 0; r < NRA; ++r) sts_if(zp + r * vs, zj[r], k == 0);
 #pragma unroll
@@ -149,12 +159,9 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
                          : "=d"(st.wp[q].x), "=d"(st.wp[q].y)
                          : "r"(colp + 16u * q)
                          : "memory");
-        // the pivot lane starts reloading its next row at the end of this step: its own (dead)
-        // row must not receive the late update
-        st.vp = (k >= 1) ? v : 0.0;
-        const double wz = (k >= 1) ? w : 0.0;
+        st.vp = vm;  // the pivot lane and the lanes between two rows take no part in the late update
 #pragma unroll
-        for (int r = 0; r < NRA; ++r) st.zr[r] = fma(-wz, zj[r], st.zr[r]);
+        for (int r = 0; r < NRA; ++r) st.zr[r] = fma(-w, zj[r], st.zr[r]);
         if (NRA == 3) {
             const double c = zj[0] * rd;
             st.ydot[0] = fma(c, zj[NRA > 1 ? 1 : 0], st.ydot[0]);
@@ -164,19 +171,22 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
         const bool wrap = (k == 0);
         k = (k - 1) & 31;
         R += wrap ? 32 : 0;
-        rowok = R < nrows;
         pk += 8u * (P - 1) + (wrap ? 256u : 0u);
         colp += 8u * P;
         zp += 8u;
         // lanes between two rows: one entry per static slot and step (distance e = k - slot)
-        const bool pa = (k >= B) && rowok;
+        const bool pa = (k >= B);
         lds_if(st.cur[B - 20], pk + 8u * (B - 20) * (P - 1), pa && k <= B + 5);
         lds_if(st.cur[B - 13], pk + 8u * (B - 13) * (P - 1), pa);
         lds_if(st.cur[B - 6], pk + 8u * (B - 6) * (P - 1), pa);
-        lds_if(st.cur[B + 1], pk + 8u * (B + 1) * (P - 1), pa && k >= B + 1);
-        const bool pz = wrap && rowok;
+        lds_if(st.cur[B + 1], pk + 8u * (B + 1) * (P - 1), k >= B + 1);
 #pragma unroll
-        for (int r = 0; r < NRA; ++r) lds_if(st.zr[r], zs + r * vs + 8u * (unsigned)R, pz);
+        for (int r = 0; r < NRA; ++r) lds_if(st.zr[r], zs + r * vs + 8u * (unsigned)R, wrap);
+#pragma unroll
+        for (int r = 0; r < NRA; ++r) zj[r] = __shfl_sync(kFull, st.zr[r], srcn);
+        v = vn;
+        d = dn;
+        v1 = v1n;
     }
     st.k = k;
     st.R = R;

@@ -81,9 +81,26 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
     double *zpad = X + 5 * n;  // 32 zeros
     double *obs_s = zpad + 32;  // 2 x 12 observation slots, then gy0, gy1, gh0, gh1
     double *red = obs_s + 32;   // 2 * NADJ * NW reduction slots
-    // the two resident CTAs of an SM put their fronts on different scheduler partitions
-    const int fw = (NW >= 4) ? 2 * ((blockIdx.x / M.num_sms) & 1) : 0;
-    const int fr = warp - fw;  // 0: top front, 1: bottom front, else helper
+    // The two resident CTAs of an SM put their fronts on different scheduler partitions.  A warp's
+    // partition is its hardware slot modulo 4 (measured, profiles/micro/warpid.cu: the second CTA of
+    // an SM gets slots 5, 6, 7, 4); each CTA draws a ticket from its SM's counter (consecutive
+    // tickets differ in parity) and takes partitions {0, 1} or {2, 3} for its two fronts.
+    __shared__ int s_parts;
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_flag = atomicAdd(M.sm_ticket + smid, 1);
+        s_parts = 0;
+    }
+    __syncthreads();
+    unsigned hw_slot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_slot));
+    if (lane == 0) atomicOr(&s_parts, 1 << (hw_slot & 3));
+    __syncthreads();
+    const int half = 2 * (s_flag & 1);
+    // fall back to the warp index if the four warps do not sit on four different partitions
+    const int fr = (NW == 4 && s_parts == 15) ? (int)(hw_slot & 3) - half : warp - half;  // 0 top, 1 bottom front
+    __syncthreads();
 
     for (long long s = blockIdx.x; s < A.N; s += gridDim.x) {
         // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu)
@@ -170,11 +187,11 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                 //                  vector and the observed node's unit vectors are eliminated on the fly
                 const unsigned bT = smem_addr(bandT), zsT = smem_addr(X2);
                 front_init<B, 3>(st, bT, zsT, vsb, lane);
-                front_eliminate<B, 3>(st, bT, me, zsT, vsb, 0, pT);
+                front_eliminate<B, 3>(st, bT, zsT, vsb, 0, pT);
                 front_flush<B>(st);
                 asm volatile("bar.sync 1, 64;" ::: "memory");
                 front_merge_middle<B>(st, S_sa, rs_sa);
-                front_eliminate<B, 3>(st, bT, me, zsT, vsb, pT, me);
+                front_eliminate<B, 3>(st, bT, zsT, vsb, pT, me);
                 // y = e_node^T K^-1 f = sum_j z_f z_e / d over the top front and the middle
                 const double f0 = (M.obs_lv[0] >= 0) ? st.ydot[0] : 0.0;
                 const double f1 = (M.obs_lv[1] >= 0) ? st.ydot[1] : 0.0;
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                 // ---------------- (c) bottom front: mirrored columns, load vector only
                 const unsigned bBs = smem_addr(bandB), zsB = smem_addr(X2 + me);
                 front_init<B, 1>(st, bBs, zsB, vsb, lane);
-                front_eliminate<B, 1>(st, bBs, nB + P, zsB, vsb, 0, nB);
+                front_eliminate<B, 1>(st, bBs, zsB, vsb, 0, nB);
                 front_flush<B>(st);
                 front_dump_middle<B>(st, S_sa, rs_sa);
                 if (lane == 0 && st.bad < 0) s_flag = 1;
