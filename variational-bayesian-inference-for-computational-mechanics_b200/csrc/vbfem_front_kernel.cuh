@@ -170,9 +170,14 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                     short off[40];
 #pragma unroll
                     for (int q = 0; q < 5; ++q) *reinterpret_cast<uint4 *>(off + 8 * q) = o4[q];
+                    // the 36 targets of one element are distinct and no other element of this colour
+                    // shares them: load all, then store all (no read-after-write serialisation)
+                    double cur[36];
+#pragma unroll
+                    for (int q = 0; q < 36; ++q) cur[q] = smem[off[q] >= 0 ? off[q] : 0];
 #pragma unroll
                     for (int q = 0; q < 36; ++q)
-                        if (off[q] >= 0) smem[off[q]] += ke[q];
+                        if (off[q] >= 0) smem[off[q]] = cur[q] + ke[q];
                 }
                 __syncthreads();
             }
