@@ -58,7 +58,7 @@ struct DevModel {
     // ---- on-chip front kernel (vbfem_front_kernel.cuh): top front [0, pT), P middle rows, bottom
     //      front mirrored; the internal numbering starts at the observed node
     int pT, nB, num_sms;
-    int obs_lv[2];          // local-vector index of the observed node's dofs (top front), -1 if supported
+    int obs_lv[2];          // local-vector index of the observed node's dofs (bottom front), -1 if supported
     int obs_lmv[8];         // local-vector index of the observed element's dofs (middle block), -1 if supported
     double obs_nx[2][4], obs_ny[2][4];  // dN/dx, dN/dy at the two observed Gauss points
     const short *eoff;      // [nele][40] shared-memory band offset of each lower-triangle element entry, -1 = skip
@@ -1029,8 +1029,8 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
 
     // ---- on-chip front kernel: band (n x 26 doubles) + five vectors must fit twice per SM
     {
-        // Layout (vbfem_front_kernel.cuh): the band order is oriented so that it STARTS at the observed
-        // node (its unit vectors then ride along the top front), the observed element's dofs must fit
+        // Layout (vbfem_front_kernel.cuh): the band order is oriented so that it ENDS at the observed
+        // node (its unit vectors then ride along the bottom front), the observed element's dofs must fit
         // into the P = 26 middle rows [pT, pT+P), the bottom front owns the last nB rows mirrored.
         constexpr int TB = 25, TP = TB + 1, TNT = 128;
         int tip[2], er[8], elo = 1 << 30, ehi = -1, tlo = 1 << 30, thi = -1;
@@ -1053,21 +1053,21 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         bool ok = getenv("VBFEM_FORCE_GENERIC") == nullptr && b <= TB && ehi >= 0 && ehi - elo < TP;
         bool flip = false;
         if (ok && thi >= 0) {
-            if (tlo > ehi)
-                flip = true;  // observed node behind the observed element: reverse the band order
-            else if (thi >= elo)
+            if (thi < elo)
+                flip = true;  // observed node ahead of the observed element: reverse the band order
+            else if (tlo <= ehi)
                 ok = false;   // observed node inside the element's row range: generic kernel
         }
         auto ori = [&](int g) { return (g < 0) ? g : (flip ? n - 1 - g : g); };
         int pT = 0;
         if (ok) {
             const int lo = flip ? n - 1 - ehi : elo, hi = flip ? n - 1 - elo : ehi;
-            const int tmax = (thi < 0) ? -1 : (flip ? n - 1 - tlo : thi);
-            // pT in [hi-P+1, lo], above the observed node, both fronts at least 32 columns
-            const int pmin = std::max({hi - TP + 1, tmax + 1, 32}), pmax = std::min(lo, n - TP - 32);
+            const int tmin = (thi < 0) ? n : (flip ? n - 1 - thi : tlo);
+            // pT in [hi-P+1, lo], the observed node inside the bottom front, both fronts at least 32 columns
+            const int pmin = std::max(hi - TP + 1, 32), pmax = std::min({lo, n - TP - 32, tmin - TP});
             if (pmin > pmax) ok = false;
             // balance: the top front also eliminates the middle block
-            pT = std::min(std::max((n - 2 * TP) / 2, pmin), pmax);
+            pT = std::min(std::max((int)((n - 2 * TP) * 0.565), pmin), pmax);  // a 3-rhs column costs about 1.3 x a 1-rhs column
         }
         const size_t fr_doubles = (size_t)n * TP + 5 * (size_t)n + 32 + 32 + 8 * (TNT / 32);
         const size_t fr_smem = fr_doubles * sizeof(double);

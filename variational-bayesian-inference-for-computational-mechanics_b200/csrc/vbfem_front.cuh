@@ -65,7 +65,6 @@ struct FrontState {
     int k;               // (row - j) & 31 for the next column j
     int R;               // this lane's current row
     unsigned pk;         // shared address of band[j*P + k]
-    int bad;             // OR of the high words of all pivots (sign bit set = negative pivot)
 };
 
 template <int B>
@@ -96,7 +95,6 @@ __device__ __forceinline__ void front_init(FrontState<B> &st, unsigned band, uns
     st.k = lane;
     st.R = lane;
     st.pk = band + 8u * lane;
-    st.bad = 0;
 }
 
 // Apply the late update in place (no shift): call before the window is read or handed over.
@@ -126,16 +124,20 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
     double v = st.cur[0];
     double d = __shfl_sync(kFull, v, j0 & 31);
     double v1 = __shfl_sync(kFull, v, (j0 + 1) & 31);
+    // eliminated right-hand sides travel through their final place in shared memory: the pivot
+    // lane stores, everybody reads the broadcast back
     double zj[NRA];
 #pragma unroll
-    for (int r = 0; r < NRA; ++r) zj[r] = __shfl_sync(kFull, st.zr[r], j0 & 31);
+    for (int r = 0; r < NRA; ++r) {
+        sts_if(zp + r * vs, st.zr[r], k == 0);
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(zj[r]) : "r"(zp + r * vs) : "memory");
+    }
 #pragma unroll 1
     for (int j = j0; j < j1; ++j) {
         const bool sub = (unsigned)(k - 1) < (unsigned)B;  // 1 <= k <= B: a sub-diagonal row of column j
         const double vm = sub ? v : 0.0;
         const double t1 = vm * v1;
         const double rd = fast_rcp3(d);
-        st.bad |= __double2hiint(d);
         // late update of column j-1, written one slot down: the window slides with the pivot
 #pragma unroll
         for (int t = 1; t < B; ++t) st.cur[t - 1] = fma(-st.vp, wp_at<B>(st, t + 1), st.cur[t]);
@@ -151,8 +153,6 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
         const double w = vm * rd;
         sts_if(pk, w, sub);
         sts_if(colp, rd, k == 0);
-#pragma unroll
-        for (int r = 0; r < NRA; ++r) sts_if(zp + r * vs, zj[r], k == 0);
 #pragma unroll
         for (int q = 1; q < P / 2; ++q)
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
@@ -182,8 +182,12 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
         lds_if(st.cur[B + 1], pk + 8u * (B + 1) * (P - 1), k >= B + 1);
 #pragma unroll
         for (int r = 0; r < NRA; ++r) lds_if(st.zr[r], zs + r * vs + 8u * (unsigned)R, wrap);
+        const bool pst = (k == 0) && (j + 1 < j1);  // nothing to publish behind the last column
 #pragma unroll
-        for (int r = 0; r < NRA; ++r) zj[r] = __shfl_sync(kFull, st.zr[r], srcn);
+        for (int r = 0; r < NRA; ++r) {
+            sts_if(zp + r * vs, st.zr[r], pst);
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(zj[r]) : "r"(zp + r * vs) : "memory");
+        }
         v = vn;
         d = dn;
         v1 = v1n;
@@ -227,16 +231,21 @@ __device__ __forceinline__ void front_merge_middle(FrontState<B> &st, unsigned S
     }
 }
 
-// x_v[r] *= 1/d_r for rows [0, nrows) of NV vectors (stride vs doubles)
+// x_v[r] *= 1/d_r for rows [lo, hi) of NV vectors (stride vs doubles; NV = 0: check only).  Returns
+// non-zero if a pivot of these rows was non-positive or not finite (the elimination loop itself
+// does not test them).
 template <int B, int NV>
-__device__ __forceinline__ void front_scale(const double *__restrict__ band, double *__restrict__ x, int vs,
-                                            int lo, int hi, int lane) {
+__device__ __forceinline__ int front_scale(const double *__restrict__ band, double *__restrict__ x, int vs,
+                                           int lo, int hi, int lane) {
+    int bad = 0;
     for (int r = lo + lane; r < hi; r += 32) {
         const double rd = band[r * (B + 1)];
+        bad |= !(rd > 0.0 && rd < 1.0e300);
 #pragma unroll
         for (int v = 0; v < NV; ++v) x[v * vs + r] *= rd;
     }
     __syncwarp();
+    return bad;
 }
 
 // Operands of one 4-row sweep block: the strictly lower part of the 4x4 diagonal block of L

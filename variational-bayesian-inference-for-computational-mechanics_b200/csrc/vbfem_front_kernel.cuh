@@ -71,13 +71,15 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
     double *bandT = smem;
     double *bandB = smem + me * P;
     // five vectors of length n, local order [top | middle | bottom mirrored]; the internal numbering
-    // starts at the observed node, so its two unit vectors live in the top front:
-    //   X0 psi / adjoint of h0, X1 adjoint of h1, X4 / X3 unit vectors of the observed node -> their
-    //   adjoints, X2 load -> u (followed by the zero pad: right-hand-side reloads of the bottom
-    //   front's middle rows).  X0 and X1 are zero during the elimination: they back the bottom
-    //   front's band (columns >= nB read as zero) and then carry the Schur hand-over.
+    // ENDS at the observed node, so its two unit vectors live in the bottom front (three
+    // right-hand sides there, one on the top front, which in turn finishes the middle block):
+    //   X0 psi / adjoint of h0, X1 adjoint of h1, X2 load -> u, X3 / X4 unit vectors of the observed
+    //   node -> their adjoints.  X0 and X1 are zero during the elimination: they back the bottom
+    //   front's band (columns >= nB read as zero) and then carry the Schur hand-over.  The bottom
+    //   front's right-hand-side reloads for its middle rows hit the (zero) top part of the next
+    //   vector, resp. the zero pad behind X4.
     double *X = smem + n * P;
-    double *X0 = X, *X1 = X + n, *X4 = X + 2 * n, *X3 = X + 3 * n, *X2 = X + 4 * n;
+    double *X0 = X, *X1 = X + n, *X2 = X + 2 * n, *X3 = X + 3 * n, *X4 = X + 4 * n;
     double *zpad = X + 5 * n;  // 32 zeros
     double *obs_s = zpad + 32;  // 2 x 12 observation slots, then gy0, gy1, gh0, gh1
     double *red = obs_s + 32;   // 2 * NADJ * NW reduction slots
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
         }
         __syncthreads();
         for (int i = tid; i < n; i += NT) X2[i] = M.pf_loc[i];
-        if (tid < 2 && M.obs_lv[tid] >= 0) X[(3 - tid) * n + M.obs_lv[tid]] = 1.0;
+        if (tid < 2 && M.obs_lv[tid] >= 0) X[(3 + tid) * n + M.obs_lv[tid]] = 1.0;
 
         // ---------------- (a) element kernels + (b) colour-ordered scatter assembly
         for (int base = 0; base < M.nele; base += NT) {
@@ -184,26 +186,28 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
         }
 
         if (fr == 0 || fr == 1) {
-            const unsigned vsb = (unsigned)(-8 * n);  // right-hand sides X2, X3, X4 lie n doubles apart, descending
+            const unsigned vsb = 8u * (unsigned)n;  // right-hand sides X2, X3, X4 lie n doubles apart
             const unsigned S_sa = smem_addr(X0), rs_sa = S_sa + 8u * (P * P);
+            double *yd = X0 + P * P + 3 * P + 2;  // bottom front's dot products (hand-over scratch)
             FrontState<B> st;
             if (fr == 0) {
-                // ---------------- (c) top front: columns [0, pT), then the merged middle block; the load
-                //                  vector and the observed node's unit vectors are eliminated on the fly
+                // ---------------- (c) top front: columns [0, pT) with the load vector, then the merged
+                //                  middle block with all three right-hand sides
                 const unsigned bT = smem_addr(bandT), zsT = smem_addr(X2);
-                front_init<B, 3>(st, bT, zsT, vsb, lane);
-                front_eliminate<B, 3>(st, bT, zsT, vsb, 0, pT);
+                front_init<B, 1>(st, bT, zsT, vsb, lane);
+                front_eliminate<B, 1>(st, bT, zsT, vsb, 0, pT);
                 front_flush<B>(st);
                 asm volatile("bar.sync 1, 64;" ::: "memory");
                 front_merge_middle<B>(st, S_sa, rs_sa);
+                const double ydB0 = yd[0], ydB1 = yd[1];
                 front_eliminate<B, 3>(st, bT, zsT, vsb, pT, me);
-                // y = e_node^T K^-1 f = sum_j z_f z_e / d over the top front and the middle
-                const double f0 = (M.obs_lv[0] >= 0) ? st.ydot[0] : 0.0;
-                const double f1 = (M.obs_lv[1] >= 0) ? st.ydot[1] : 0.0;
-                if (lane == 0 && (st.bad < 0 || !(fabs(f0) < 1.0e300 && fabs(f1) < 1.0e300))) s_flag = 1;
+                // y = e_node^T K^-1 f = sum_j z_f z_e / d over the bottom front and the middle
+                const double f0 = (M.obs_lv[0] >= 0) ? st.ydot[0] + ydB0 : 0.0;
+                const double f1 = (M.obs_lv[1] >= 0) ? st.ydot[1] + ydB1 : 0.0;
                 __syncwarp();
                 // middle block of u: D^-1, then L_M^T
-                front_scale<B, 1>(bandT, X2, 0, 0, me, lane);
+                const int bad = front_scale<B, 1>(bandT, X2, 0, 0, me, lane);
+                if (bad || (lane == 0 && !(fabs(f0) < 1.0e300 && fabs(f1) < 1.0e300))) s_flag = 1;
                 front_back_sweep<B, 1>(bandT, X2, 0, me - 1, pT, lane);
                 // ---------------- (d) observations: y, h = von Mises at (obs ele, obs gps)
                 if (lane < 2) {
@@ -238,10 +242,10 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                         gh0 = A.gh[2 * s];
                         gh1 = A.gh[2 * s + 1];
                     }
-                    // forward-eliminated adjoint right-hand side on the top front: gy . (eliminated unit vectors)
-                    for (int r = lane; r < pT; r += 32) X0[r] = (gy0 * X3[r] + gy1 * X4[r]) * bandT[r * P];
-                    for (int r = pT + lane; r < me; r += 32) X0[r] = 0.0;
+                    for (int r = lane; r < me; r += 32) X0[r] = 0.0;  // also clears the hand-over scratch
                     if (lane == 0) {
+                        obs_s[24] = gy0;
+                        obs_s[25] = gy1;
                         obs_s[26] = gh0;
                         obs_s[27] = gh1;
                     }
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                     __syncwarp();
                     front_back_sweep<B, 1>(bandT, X0, 0, me - 1, pT, lane);
                     asm volatile("bar.sync 1, 64;" ::: "memory");
-                    front_back_sweep<B, 2>(bandT, X0, 4 * n, pT - 1, 0, lane);  // psi and u together
+                    front_back_sweep<B, 2>(bandT, X0, 2 * n, pT - 1, 0, lane);  // psi and u together
                 } else if (MODE == 2) {
                     for (int r = lane; r < me; r += 32) X0[r] = X1[r] = 0.0;
                     __syncwarp();
@@ -273,31 +277,37 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                     __syncwarp();
                     front_fwd_sweep<B, 2>(bandT, X0, n, pT, me, me, lane);
                     front_scale<B, 2>(bandT, X0, n, pT, me, lane);
-                    front_scale<B, 2>(bandT, X4, n, 0, me, lane);  // eliminated unit vectors, top and middle
+                    front_scale<B, 2>(bandT, X3, n, pT, me, lane);
                     front_back_sweep<B, 2>(bandT, X0, n, me - 1, pT, lane);
-                    front_back_sweep<B, 2>(bandT, X4, n, me - 1, pT, lane);
+                    front_back_sweep<B, 2>(bandT, X3, n, me - 1, pT, lane);
                     asm volatile("bar.sync 1, 64;" ::: "memory");
                     front_back_sweep<B, 5>(bandT, X0, n, pT - 1, 0, lane);
                 }
             } else {
-                // ---------------- (c) bottom front: mirrored columns, load vector only
+                // ---------------- (c) bottom front: mirrored columns, the load vector and the observed
+                //                  node's two unit vectors are eliminated on the fly
                 const unsigned bBs = smem_addr(bandB), zsB = smem_addr(X2 + me);
-                front_init<B, 1>(st, bBs, zsB, vsb, lane);
-                front_eliminate<B, 1>(st, bBs, zsB, vsb, 0, nB);
+                front_init<B, 3>(st, bBs, zsB, vsb, lane);
+                front_eliminate<B, 3>(st, bBs, zsB, vsb, 0, nB);
                 front_flush<B>(st);
                 front_dump_middle<B>(st, S_sa, rs_sa);
-                if (lane == 0 && st.bad < 0) s_flag = 1;
+                if (lane == 0) {
+                    yd[0] = st.ydot[0];
+                    yd[1] = st.ydot[1];
+                }
                 __syncwarp();
                 asm volatile("bar.sync 1, 64;" ::: "memory");
+                // D^-1 on the bottom parts of u and of the eliminated unit vectors (and the pivot check)
+                if (front_scale<B, (MODE > 0 ? 3 : 0)>(bandB, X2 + me, n, 0, nB, lane)) s_flag = 1;
                 if (MODE > 0) {
-                    front_scale<B, 1>(bandB, X2 + me, 0, 0, nB, lane);
                     asm volatile("bar.sync 1, 64;" ::: "memory");
-                    // the adjoint right-hand sides vanish on the bottom front
                     if (MODE == 1) {
-                        for (int c = lane; c < nB; c += 32) X0[me + c] = 0.0;
+                        // forward-eliminated adjoint right-hand side on the bottom front: gy . (unit vectors)
+                        const double gy0 = obs_s[24], gy1 = obs_s[25];
+                        for (int c = lane; c < nB; c += 32) X0[me + c] = gy0 * X3[me + c] + gy1 * X4[me + c];
                         __syncwarp();
-                        front_apply_known<B, 2>(bandB, X0 + me, X0 + pT, 4 * n, nB, lane);
-                        front_back_sweep<B, 2>(bandB, X0 + me, 4 * n, nB - 1, 0, lane);
+                        front_apply_known<B, 2>(bandB, X0 + me, X0 + pT, 2 * n, nB, lane);
+                        front_back_sweep<B, 2>(bandB, X0 + me, 2 * n, nB - 1, 0, lane);
                     } else {
                         for (int c = lane; c < nB; c += 32) X0[me + c] = X1[me + c] = 0.0;
                         __syncwarp();
