@@ -138,27 +138,43 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
         const double vm = sub ? v : 0.0;
         const double t1 = vm * v1;
         const double rd = fast_rcp3(d);
-        // late update of column j-1, written one slot down: the window slides with the pivot
+        // late update of column j-1, written one slot down: the window slides with the pivot.  The
+        // first QS slot pairs run in the shadow of the reciprocal chain ...
+        constexpr int QS = 4;
 #pragma unroll
-        for (int t = 1; t < B; ++t) st.cur[t - 1] = fma(-st.vp, wp_at<B>(st, t + 1), st.cur[t]);
-        st.cur[B - 1] = st.cur[B];
-        st.cur[B] = st.cur[B + 1];
+        for (int t = 1; t <= 2 * QS; ++t) st.cur[t - 1] = fma(-st.vp, wp_at<B>(st, t + 1), st.cur[t]);
         // first entry of column j's update: the next pivot column is final -> broadcast it now
         st.cur[0] = fma(-t1, rd, st.cur[0]);
         const int srcn = (j + 1) & 31;
         const double vn = st.cur[0];
         const double dn = __shfl_sync(kFull, vn, srcn);
         const double v1n = __shfl_sync(kFull, vn, (srcn + 1) & 31);
-        // column j: L entries and 1/d to the band, eliminated right-hand sides to z
+        // column j: L entries and 1/d to the band
         const double w = vm * rd;
         sts_if(pk, w, sub);
         sts_if(colp, rd, k == 0);
+        // ... the rest is interleaved with the broadcast loads of column j's scaled entries (each
+        // load overwrites a pair the late update has just consumed), so that the FP64 pipe and
+        // the shared-memory pipe work at the same time
 #pragma unroll
-        for (int q = 1; q < P / 2; ++q)
+        for (int q = 1; q <= QS; ++q)
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
                          : "=d"(st.wp[q].x), "=d"(st.wp[q].y)
                          : "r"(colp + 16u * q)
                          : "memory");
+        const double vpo = st.vp;
+#pragma unroll
+        for (int q = QS + 1; q < P / 2; ++q) {
+            const double wx = st.wp[q].x, wy = st.wp[q].y;
+            st.cur[2 * q - 2] = fma(-vpo, wx, st.cur[2 * q - 1]);
+            if (2 * q < B) st.cur[2 * q - 1] = fma(-vpo, wy, st.cur[2 * q]);
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                         : "=d"(st.wp[q].x), "=d"(st.wp[q].y)
+                         : "r"(colp + 16u * q)
+                         : "memory");
+        }
+        st.cur[B - 1] = st.cur[B];
+        st.cur[B] = st.cur[B + 1];
         st.vp = vm;  // the pivot lane and the lanes between two rows take no part in the late update
 #pragma unroll
         for (int r = 0; r < NRA; ++r) st.zr[r] = fma(-w, zj[r], st.zr[r]);
