@@ -247,3 +247,40 @@ def test_refined_mesh_80x40(pkg):
         fd = (((yp - ym) * gy).sum(1) + ((hp - hm) * gh).sum(1)) / (2 * eps)
         assert np.max(np.abs(fd - gx.cpu().numpy()[:, k])) < 1e-6 * max(1.0, np.abs(fd).max())
     eng.close()
+
+
+@pytest.mark.parametrize("node_id,ele_id,nipt_id,variant", [
+    (231, 12, (1, 3), 2),     # the reference's set-up: node behind the element in band order
+    (21, 12, (2, 4), 2),      # tip of the bottom edge, other Gauss points
+    (23, 150, (1, 2), 2),     # node AHEAD of the element: the band order is flipped internally
+    (1, 50, (3, 4), 2),       # supported node: y == 0, gradient through h only
+    (116, 110, (1, 3), 0),    # node of the observed element itself: generic kernel
+    (1, 60, (3, 4), 0),       # element too close to the end of the band for two fronts: generic kernel
+])
+def test_other_observation_setups(pkg, golden_model, oracle_mesh, node_id, ele_id, nipt_id, variant):
+    """The front kernel's layout (orientation, middle block, unit vectors) is derived from the
+    observation set-up; every choice must agree with the oracle."""
+    import fem_oracle as fo
+    eng = pkg.CookFemEngine(golden_model, device=0, node_id=node_id, ele_id=ele_id, nipt_id=nipt_id)
+    assert eng.info["kernel_variant"] == variant
+    to = fo.TorchOracle(*oracle_mesh, node_id=node_id, ele_id=ele_id, nipt_id=nipt_id)
+    n = 64
+    x = np.random.default_rng(7).standard_normal((n, 2))
+    gy = np.random.default_rng(8).standard_normal((n, 2))
+    gh = np.random.default_rng(9).standard_normal((n, 2))
+    yo, ho, gxo = to.vjp(x, gy, gh)
+    y, h, gx = eng.forward_backward(_t(x, eng), _t(gy, eng), _t(gh, eng))
+    scale = max(float(np.abs(yo).max()), 1e-30)
+    assert float(np.abs(y.cpu().numpy() - yo).max()) < TOL * max(scale, 1.0)
+    assert relerr(h.cpu().numpy(), ho) < TOL
+    assert relerr(gx.cpu().numpy(), gxo) < TOL
+    y2, h2 = eng.forward(_t(x, eng), keep_factor=True)       # Jacobian mode + J^T g
+    gx2 = eng.backward(_t(gy, eng), _t(gh, eng))
+    assert float(np.abs(y2.cpu().numpy() - yo).max()) < TOL * max(scale, 1.0)
+    assert relerr(h2.cpu().numpy(), ho) < TOL
+    assert relerr(gx2.cpu().numpy(), gxo) < TOL
+    y3, h3 = eng.forward(_t(x, eng))                          # forward only
+    assert float(np.abs(y3.cpu().numpy() - yo).max()) < TOL * max(scale, 1.0)
+    assert relerr(h3.cpu().numpy(), ho) < TOL
+    assert eng.status(n)[0] == 0
+    eng.close()
