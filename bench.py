@@ -251,13 +251,29 @@ def run_cuda(args):
     for i in range(elbo_steps):
         last_loss = elbo_step(3 + i)
     barrier()
+    elbo_eager_s = time.perf_counter() - t0
+
+    # the same step captured once in a CUDA graph (nets + fused FEM op + Adam) and replayed
+    gmodel = pkg.elbo.make_step1_model(device=dev)
+    gstep = pkg.elbo.GraphedStep1(gmodel, pkg.elbo.make_step1_optimizer_capturable(gmodel), loss_fn, B, dev)
+
+    def elbo_graph_step(i):
+        return float(gstep.step(yd[(i * B) % 9984:(i * B) % 9984 + B]))  # H2D of the batch, D2H of the loss
+
+    for i in range(3):
+        elbo_graph_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(elbo_steps):
+        last_loss_g = elbo_graph_step(3 + i)
+    barrier()
     elbo_s = time.perf_counter() - t0
 
     # ---------------- max over ranks
-    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s = t.tolist()
+    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s = t.tolist()
 
     if rank == 0:
         import ctypes
@@ -316,8 +332,10 @@ def run_cuda(args):
                       "forward_only_solves_per_s": world * BATCH * args.steps / (fwd_ms * 1e-3),
                       "step_ms_min": min(step_ms), "step_ms_max": max(step_ms),
                       "elbo": {"steps_per_s": elbo_steps / elbo_s, "B": B, "S": S, "samples_per_step": B * S,
-                               "fem_solves_per_s": B * S * elbo_steps / elbo_s, "last_loss": last_loss,
-                               "what": "NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd -> Adam, "
+                               "fem_solves_per_s": B * S * elbo_steps / elbo_s, "last_loss": last_loss_g,
+                               "cuda_graph": bool(gstep.graphed),
+                               "eager_steps_per_s": elbo_steps / elbo_eager_s, "eager_last_loss": last_loss,
+                               "what": "NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd -> Adam (one CUDA graph replay per step), "
                                        "batch H2D and loss D2H inside; one NCCL all-reduce per step when N>1"}},
         }
         print(json.dumps(line))

@@ -140,3 +140,76 @@ def make_step1_optimizer(model, lr=1e-3):
     import torch
 
     return torch.optim.Adam(model.parameters(), lr=lr, betas=(0.99, 0.999), eps=1e-10)
+
+
+def make_step1_optimizer_capturable(model, lr=1e-3):
+    """Same Adam (main_custom_training.py:243) with its step counter on the device, so that
+    the whole training step can be captured in a CUDA graph."""
+    import torch
+
+    return torch.optim.Adam(model.parameters(), lr=lr, betas=(0.99, 0.999), eps=1e-10, capturable=True)
+
+
+class GraphedStep1:
+    """One step-1 training step (main_custom_training.py:252-258: forward, loss, tape.gradient,
+    Adam) captured ONCE in a CUDA graph and replayed per batch:
+
+        pinned host batch --H2D--> nets --> reparameterisation + FEM + adjoint (libvbfem) --> loss
+        --> backward through the nets --> Adam
+
+    The ~100 small launches of the two MLPs and of Adam otherwise cost about as much as the
+    6400 finite-element solves of a step.  ``step(y_batch_host)`` copies the batch into the
+    pinned staging buffer, replays the graph and returns the loss tensor (device); reading
+    it (``float``) is the step's only synchronisation.  Falls back to eager execution when
+    capture is not possible (``self.graphed`` tells which)."""
+
+    def __init__(self, model, optimizer, loss_fn, batch_size, device, use_graph=True, warmup=3):
+        import torch
+
+        self.torch, self.model, self.opt, self.loss_fn = torch, model, optimizer, loss_fn
+        self.pin = torch.empty(batch_size, 2, dtype=torch.float64).pin_memory()
+        self.yb = torch.empty(batch_size, 2, dtype=torch.float64, device=device)
+        self.loss = torch.zeros((), dtype=torch.float64, device=device)
+        self.graph, self.graphed = None, False
+        self._warm = warmup
+        self._use_graph = use_graph
+        self._device = device
+
+    def _body(self):
+        self.yb.copy_(self.pin, non_blocking=True)
+        self.opt.zero_grad(set_to_none=True)
+        mu, sig, ls = self.model(self.yb)
+        loss = self.loss_fn(self.yb, mu, sig, ls)
+        loss.backward()
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def _capture(self):
+        torch = self.torch
+        side = torch.cuda.Stream(device=self._device)
+        side.wait_stream(torch.cuda.current_stream(self._device))
+        with torch.cuda.stream(side):
+            for _ in range(self._warm):   # also sizes the library's scratch buffers before capture
+                self._body()
+        torch.cuda.current_stream(self._device).wait_stream(side)
+        torch.cuda.synchronize(self._device)
+        try:
+            g = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph, self.graphed = g, True
+        except Exception as exc:  # capture unsupported (e.g. an uncapturable collective): run eagerly
+            self.graph, self.graphed = None, False
+            self.capture_error = repr(exc)
+            torch.cuda.synchronize(self._device)
+
+    def step(self, y_batch_host):
+        self.pin.copy_(self.torch.as_tensor(y_batch_host, dtype=self.torch.float64))
+        if self._use_graph and self.graph is None and not hasattr(self, "capture_error"):
+            self._capture()
+        if self.graphed:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss
