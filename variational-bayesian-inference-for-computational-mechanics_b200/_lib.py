@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 REPO = os.path.dirname(_HERE)
 INCLUDE = os.path.join(REPO, "include")
-LIB_PATH = os.path.join(CSRC, "libvbfem.so")
+LIB_PATH = os.environ.get("VBFEM_LIB", os.path.join(CSRC, "libvbfem.so"))  # VBFEM_LIB: profiling builds
 SOURCES = ["vbfem.cu"]
 HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", os.path.join(INCLUDE, "vbfem.h")]
 

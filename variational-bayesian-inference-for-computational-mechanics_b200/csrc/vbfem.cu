@@ -92,6 +92,7 @@ struct Args {
     long long j_begin;
     double gcoef;  // 1 / (sig_e * B * (B*S))
     double *f_out;
+    long long *timeline;  // profiling builds (-DVBFEM_TIMELINE): clock64 marks per CTA and warp
 };
 
 // ------------------------------------------------------------------------------------------
@@ -173,6 +174,15 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
     return h;
 }
 
+#ifdef VBFEM_TIMELINE
+#define VBFEM_TL(i)                                                                              \
+    do {                                                                                        \
+        if (A.timeline && (threadIdx.x & 31) == 0)                                              \
+            A.timeline[(blockIdx.x * 4 + (threadIdx.x >> 5)) * 16 + (i)] = clock64();          \
+    } while (0)
+#else
+#define VBFEM_TL(i) ((void)0)
+#endif
 }  // namespace vbfem
 #include "vbfem_front_kernel.cuh"
 namespace vbfem {
@@ -708,6 +718,7 @@ struct vbfem_handle {
     int info_colors = 0;
     int n_real = 0;   // order of the system without padding rows
     int variant = 0;  // 0 = generic per-column kernel, 2 = on-chip front kernel
+    long long *timeline = nullptr;
 };
 
 template <typename T>
@@ -1238,6 +1249,14 @@ static int launch(vbfem_handle *h, Args &a, void *stream) {
                 a.N, h->ws, h->ws_stride, a.gy, a.gh, a.gx);
         } else {
             const int mode = (a.mode & kKeep) ? 2 : ((a.mode & kAdjoint) ? 1 : 0);
+#ifdef VBFEM_TIMELINE
+            if (!h->timeline) {
+                CU(cudaMalloc(&h->timeline, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long)));
+            }
+            CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long),
+                               (cudaStream_t)stream));
+            a.timeline = h->timeline;
+#endif
             h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, (cudaStream_t)stream>>>(h->M, a);
         }
     } else {
@@ -1472,3 +1491,14 @@ extern "C" int vbfem_measure_peaks(int device, double *fp64_tflops, double *copy
     cudaEventDestroy(e1);
     return 0;
 }
+
+#ifdef VBFEM_TIMELINE
+// Profiling builds only: clock64 marks of the last sample each CTA processed, [cta][warp][16].
+extern "C" int vbfem_debug_timeline(vbfem_t *h, long long *out_host, int64_t max_entries) {
+    if (!h || !h->timeline) return fail(-1, "no timeline recorded");
+    CU(cudaDeviceSynchronize());
+    const int64_t n = std::min<int64_t>(max_entries, (int64_t)h->num_sms * h->ctas_per_sm * 4 * 16);
+    CU(cudaMemcpy(out_host, h->timeline, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    return (int)(h->num_sms * h->ctas_per_sm);
+}
+#endif

@@ -301,13 +301,11 @@ __device__ __forceinline__ void front_fwd_sweep(const double *__restrict__ band,
         s.m3 = (ok && k >= 4 && k - 3 <= B) ? p[3 * (P - 1)] : 0.0;
         return s;
     };
-    SweepBlk cur = load_blk(j, r, nblk > 0);
-#pragma unroll 1
-    for (int b = 0; b < nblk; ++b, j += 4) {
+    auto step = [&](const SweepBlk &cur, SweepBlk &nxt, bool more) {
         const int k = (lane - j) & 31;
         const bool piv = k < 4;
         const int rn = piv ? r + 32 : r;
-        const SweepBlk nxt = load_blk(j + 4, rn, b + 1 < nblk);
+        nxt = load_blk(j + 4, rn, more);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const double a0 = __shfl_sync(kFull, acc[v], j & 31), a1 = __shfl_sync(kFull, acc[v], (j + 1) & 31);
@@ -327,8 +325,16 @@ __device__ __forceinline__ void front_fwd_sweep(const double *__restrict__ band,
             acc[v] = piv ? fresh : a;
         }
         r = rn;
-        cur = nxt;
+        j += 4;
+    };
+    SweepBlk blkA = load_blk(j, r, nblk > 0), blkB;
+    int b = 0;
+#pragma unroll 1
+    for (; b + 1 < nblk; b += 2) {
+        step(blkA, blkB, true);
+        step(blkB, blkA, b + 2 < nblk);
     }
+    if (b < nblk) step(blkA, blkB, false);
 #pragma unroll 1
     for (; j < hi; ++j) {
         const int k = (lane - j) & 31;
@@ -383,13 +389,13 @@ __device__ __forceinline__ void front_back_sweep(const double *__restrict__ band
         s.m3 = (ok && i >= 4 && i - 3 <= B) ? p[-3] : 0.0;
         return s;
     };
-    SweepBlk cur = load_blk(j, r, nblk > 0);
-#pragma unroll 1
-    for (int b = 0; b < nblk; ++b, j -= 4) {
+    // one 4-row block: shuffle the four unresolved values, solve the 4x4 block redundantly, update
+    // this lane's row; `nxt` is loaded for the following block while this one resolves
+    auto step = [&](const SweepBlk &cur, SweepBlk &nxt, bool more) {
         const int i = (j - lane) & 31;
         const bool piv = i < 4;
         const int rn = piv ? r - 32 : r;
-        const SweepBlk nxt = load_blk(j - 4, rn, b + 1 < nblk);
+        nxt = load_blk(j - 4, rn, more);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const double a0 = __shfl_sync(kFull, acc[v], j & 31), a1 = __shfl_sync(kFull, acc[v], (j - 1) & 31);
@@ -409,8 +415,16 @@ __device__ __forceinline__ void front_back_sweep(const double *__restrict__ band
             acc[v] = piv ? fresh : a;
         }
         r = rn;
-        cur = nxt;
+        j -= 4;
+    };
+    SweepBlk blkA = load_blk(j, r, nblk > 0), blkB;
+    int b = 0;
+#pragma unroll 1
+    for (; b + 1 < nblk; b += 2) {  // two blocks per trip: the operand sets alternate, no register copies
+        step(blkA, blkB, true);
+        step(blkB, blkA, b + 2 < nblk);
     }
+    if (b < nblk) step(blkA, blkB, false);
 #pragma unroll 1
     for (; j >= lo; --j) {
         const int i = (j - lane) & 31;

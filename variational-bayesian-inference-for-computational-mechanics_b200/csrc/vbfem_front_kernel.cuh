@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
         const double nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
         const Lame mat = lame_from_E_nu(E, nu);
         if (tid == 0) s_flag = 0;
+        VBFEM_TL(0);
 
         // ---------------- zero the band and the vectors, load the right-hand sides
         {
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
             for (int i = tid; i < nz; i += NT) b2[i] = z2;
         }
         __syncthreads();
+        VBFEM_TL(1);
         for (int i = tid; i < n; i += NT) X2[i] = M.pf_loc[i];
         if (tid < 2 && M.obs_lv[tid] >= 0) X[(3 + tid) * n + M.obs_lv[tid]] = 1.0;
 
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
             }
         }
 
+        VBFEM_TL(2);
         if (fr == 0 || fr == 1) {
             const unsigned vsb = 8u * (unsigned)n;  // right-hand sides X2, X3, X4 lie n doubles apart
             const unsigned S_sa = smem_addr(X0), rs_sa = S_sa + 8u * (P * P);
@@ -197,10 +200,13 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                 front_init<B, 1>(st, bT, zsT, vsb, lane);
                 front_eliminate<B, 1>(st, bT, zsT, vsb, 0, pT);
                 front_flush<B>(st);
+                VBFEM_TL(3);
                 asm volatile("bar.sync 1, 64;" ::: "memory");
+                VBFEM_TL(4);
                 front_merge_middle<B>(st, S_sa, rs_sa);
                 const double ydB0 = yd[0], ydB1 = yd[1];
                 front_eliminate<B, 3>(st, bT, zsT, vsb, pT, me);
+                VBFEM_TL(5);
                 // y = e_node^T K^-1 f = sum_j z_f z_e / d over the bottom front and the middle
                 const double f0 = (M.obs_lv[0] >= 0) ? st.ydot[0] + ydB0 : 0.0;
                 const double f1 = (M.obs_lv[1] >= 0) ? st.ydot[1] + ydB1 : 0.0;
@@ -229,6 +235,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                     }
                 }
                 __syncwarp();
+                VBFEM_TL(6);
                 if (MODE == 1) {
                     // ---------------- adjoint right-hand side w = d(gy.y + gh.h)/du
                     double gy0, gy1, gh0 = 0.0, gh1 = 0.0;
@@ -264,8 +271,11 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                     }
                     __syncwarp();
                     front_back_sweep<B, 1>(bandT, X0, 0, me - 1, pT, lane);
+                    VBFEM_TL(7);
                     asm volatile("bar.sync 1, 64;" ::: "memory");
+                    VBFEM_TL(8);
                     front_back_sweep<B, 2>(bandT, X0, 2 * n, pT - 1, 0, lane);  // psi and u together
+                    VBFEM_TL(9);
                 } else if (MODE == 2) {
                     for (int r = lane; r < me; r += 32) X0[r] = X1[r] = 0.0;
                     __syncwarp();
@@ -290,6 +300,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                 front_init<B, 3>(st, bBs, zsB, vsb, lane);
                 front_eliminate<B, 3>(st, bBs, zsB, vsb, 0, nB);
                 front_flush<B>(st);
+                VBFEM_TL(3);
                 front_dump_middle<B>(st, S_sa, rs_sa);
                 if (lane == 0) {
                     yd[0] = st.ydot[0];
@@ -297,10 +308,13 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                 }
                 __syncwarp();
                 asm volatile("bar.sync 1, 64;" ::: "memory");
+                VBFEM_TL(4);
                 // D^-1 on the bottom parts of u and of the eliminated unit vectors (and the pivot check)
                 if (front_scale<B, (MODE > 0 ? 3 : 0)>(bandB, X2 + me, n, 0, nB, lane)) s_flag = 1;
                 if (MODE > 0) {
+                    VBFEM_TL(7);
                     asm volatile("bar.sync 1, 64;" ::: "memory");
+                    VBFEM_TL(8);
                     if (MODE == 1) {
                         // forward-eliminated adjoint right-hand side on the bottom front: gy . (unit vectors)
                         const double gy0 = obs_s[24], gy1 = obs_s[25];
@@ -308,6 +322,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
                         __syncwarp();
                         front_apply_known<B, 2>(bandB, X0 + me, X0 + pT, 2 * n, nB, lane);
                         front_back_sweep<B, 2>(bandB, X0 + me, 2 * n, nB - 1, 0, lane);
+                        VBFEM_TL(9);
                     } else {
                         for (int c = lane; c < nB; c += 32) X0[me + c] = X1[me + c] = 0.0;
                         __syncwarp();
@@ -318,6 +333,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
             }
         }
         __syncthreads();
+        VBFEM_TL(10);
 
         // ---------------- (e) element-wise contraction -psi^T (dK/dp) u + explicit dh/dp, chained to x
         if (MODE > 0) {
@@ -410,6 +426,7 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
         }
         if (tid == 0 && A.status) A.status[s] = s_flag;
         __syncthreads();
+        VBFEM_TL(11);
     }
 }
 
