@@ -61,7 +61,8 @@ struct DevModel {
     int obs_lv[2];          // local-vector index of the observed node's dofs (bottom front), -1 if supported
     int obs_lmv[8];         // local-vector index of the observed element's dofs (middle block), -1 if supported
     double obs_nx[2][4], obs_ny[2][4];  // dN/dx, dN/dy at the two observed Gauss points
-    const short *eoff;      // [nele][40] shared-memory band offset of each lower-triangle element entry, -1 = skip
+    const unsigned *eoff;   // [nele][36] shared-memory BYTE offset of each lower-triangle element entry (supported
+                            //            dofs: a scratch slot)
     const short *ulm;       // [nele][8] local-vector index of each element dof, -1 if supported
     const double *pf_loc;   // [n] load vector in local-vector order
     int *sm_ticket;         // [num_sms] running CTA tickets per SM
@@ -1095,7 +1096,10 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             M.band_in_smem = 1;
             // oriented band row g -> local vector index / band storage
             auto lvi = [&](int g) { return g < me ? g : me + (n - 1 - g); };
-            std::vector<short> eoff((size_t)40 * ne, (short)-1), ulm((size_t)8 * ne, (short)-1);
+            // scratch slot for entries of supported dofs: the last observation slot (vbfem_front_kernel.cuh)
+            const unsigned dummy = (unsigned)(((size_t)n * TP + 5 * (size_t)n + 32 + 31) * sizeof(double));
+            std::vector<unsigned> eoff((size_t)36 * ne, dummy);
+            std::vector<short> ulm((size_t)8 * ne, (short)-1);
             for (int e = 0; e < ne; ++e) {
                 int gb[8];
                 for (int a = 0; a < 4; ++a)
@@ -1107,7 +1111,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                         const int lo = std::min(gb[a], gb[q]), hi = std::max(gb[a], gb[q]);
                         // top + middle rows: column lo of the top band; bottom rows: mirrored column of hi
                         const int off = hi < me ? lo * TP + (hi - lo) : me * TP + (n - 1 - hi) * TP + (hi - lo);
-                        eoff[40 * e + tri(a, q)] = (short)off;
+                        eoff[36 * e + tri(a, q)] = (unsigned)(off * sizeof(double));
                     }
                 }
             }

@@ -169,19 +169,21 @@ __global__ void __launch_bounds__(NT, 2) fem_front_kernel(const __grid_constant_
             }
             for (int c = 0; c < M.ncolors; ++c) {
                 if (color == c) {
-                    // 36 offsets (16-bit, padded to 40) as five 128-bit loads
-                    const uint4 *o4 = reinterpret_cast<const uint4 *>(M.eoff + 40 * e);
-                    short off[40];
+                    // 36 byte offsets into shared memory as nine 128-bit loads (entries of supported
+                    // dofs point at a scratch slot); the 36 targets of one element are distinct and
+                    // no other element of this colour shares them: load all, then store all
+                    const uint4 *o4 = reinterpret_cast<const uint4 *>(M.eoff + 36 * e);
+                    unsigned off[36];
 #pragma unroll
-                    for (int q = 0; q < 5; ++q) *reinterpret_cast<uint4 *>(off + 8 * q) = o4[q];
-                    // the 36 targets of one element are distinct and no other element of this colour
-                    // shares them: load all, then store all (no read-after-write serialisation)
+                    for (int q = 0; q < 9; ++q) *reinterpret_cast<uint4 *>(off + 4 * q) = o4[q];
+                    const unsigned sb = smem_addr(smem);
                     double cur[36];
 #pragma unroll
-                    for (int q = 0; q < 36; ++q) cur[q] = smem[off[q] >= 0 ? off[q] : 0];
+                    for (int q = 0; q < 36; ++q)
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cur[q]) : "r"(sb + off[q]));
 #pragma unroll
                     for (int q = 0; q < 36; ++q)
-                        if (off[q] >= 0) smem[off[q]] = cur[q] + ke[q];
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + off[q]), "d"(cur[q] + ke[q]) : "memory");
                 }
                 __syncthreads();
             }
