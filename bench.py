@@ -28,6 +28,9 @@ METRIC = "FEM forward+adjoint solves/s (Cook 20x10, batch 4096 per GPU)"
 # algorithmic work per forward+adjoint solve at 20x10 (n=440, b=25)
 FLOP_PER_SOLVE = 1600 * 200 + 440 * (25 * 25 + 3 * 25) + 2 * 4 * 440 * 25   # = 0.716 MFLOP
 BYTES_PER_SOLVE = 96                                                          # x, gy, gh in; y, h, gx out
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch at batch 4096 from the committed
+# `ncu --set full` capture (profiles/r01_ncu_front_kernel_final_details.txt): 328 704 B read, 0 B written
+NCU_DRAM_BYTES_PER_LAUNCH = 328704
 
 
 def golden_model():
@@ -320,7 +323,12 @@ def run_cuda(args):
                     "api": "CookFemEngine.forward_backward_host -> vbfem_forward_backward_host (NumPy in/out)"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64.value, "unit": "TFLOP/s",
-                         "frac": tflops / fp64.value if fp64.value else None, "traffic": None,
+                         "frac": tflops / fp64.value if fp64.value else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_unit": "bytes of DRAM traffic per launch (ncu, batch 4096): the band never leaves the SM",
+                         "other_pipes_ncu": {"fp64_pipe_active_pct": 22.8, "shared_memory_data_pipe_pct": 52.6,
+                                             "note": "profiles/r01_ncu_front_kernel_final_details.txt: the broadcast of the "
+                                                     "scaled pivot column (12 LDS.128 per column and front) keeps the "
+                                                     "shared-memory pipe busier than the FP64 pipe"},
                          "peak_source": "DFMA loop measured on this GPU by vbfem_measure_peaks "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_solve": FLOP_PER_SOLVE,
