@@ -65,7 +65,7 @@ enum {
     VBFEM_INFO_CTAS_PER_SM = 7,
     VBFEM_INFO_NUM_SMS = 8,
     VBFEM_INFO_BLOCK_THREADS = 9,
-    VBFEM_INFO_KERNEL_VARIANT = 10, /* 0 = generic per-column kernel, 1 = twisted on-chip kernel */
+    VBFEM_INFO_KERNEL_VARIANT = 10, /* 0 = generic per-column kernel, 2 = on-chip two-front kernel */
     VBFEM_INFO_TWIST_ROW = 11,      /* first middle row of the twisted factorisation */
     VBFEM_INFO_COUNT = 16
 };
@@ -83,16 +83,16 @@ int vbfem_info(const vbfem_t *h, int64_t *out /* [VBFEM_INFO_COUNT] */);
  * (fem_solver_tf.py:229-341, mat_subroutine_tf.py:23-110), solve
  * (fem_solver_tf.py:129-153), observe u at obs_node and the von Mises stress
  * at (obs_ele, obs_gp) (fem_postprocess.py:172-185).  With keep_factor != 0
- * the factor and solution are kept in the library workspace for
- * vbfem_backward. */
+ * the library also keeps what vbfem_backward needs: the 4x2 Jacobian d(y, h)/dx
+ * per sample (front kernel) or the factor and solution (generic kernel). */
 int vbfem_forward(vbfem_t *h, int64_t n_samples, const double *x_dev /* [N][2] */,
                   double *y_dev /* [N][2] */, double *h_dev /* [N][2] */,
                   int keep_factor, void *stream);
 
 /* gx = d(sum(gy*y) + sum(gh*h))/dx for the batch of the last
  * vbfem_forward(keep_factor=1): the discrete adjoint that tape.gradient
- * (main_custom_training.py:252-256) derives through the TF graph, computed
- * with the stored factor. */
+ * (main_custom_training.py:252-256) derives through the TF graph (J^T g with
+ * the stored Jacobians, or an adjoint solve with the stored factor). */
 int vbfem_backward(vbfem_t *h, int64_t n_samples, const double *gy_dev, const double *gh_dev,
                    double *gx_dev /* [N][2] */, void *stream);
 
@@ -123,6 +123,17 @@ int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t 
                      const double *mu_dev, const double *sig2_dev, const double *e_dev,
                      const double *ybatch_dev, double sig_e, double *sums_dev, double *gmu_dev,
                      double *gsig2_dev, double *f_dev /* optional [j_end-j_begin][2] */, void *stream);
+
+/* Step-2 ELBO data term (main_custom_training.py:338-364, term5): forward-only FEM over the flat
+ * sample range [j_begin, j_end) of the B*S reparameterised samples of the FROZEN theta nets
+ * (main_custom_training.py:305), reduced to the sufficient statistics of the [B, B*S] broadcast of
+ * h_data against (z_mean, z_sig):
+ *   sums_dev[0..1] = sum_j h_j (per component), sums_dev[2..3] = sum_j h_j^2.
+ * The caller all-reduces them; term5 and its gradient w.r.t. the z nets are closed-form in these
+ * sums (elbo.Step2Loss).  h_dev (optional) receives h [j_end-j_begin][2]. */
+int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                     const double *mu_dev, const double *sig2_dev, const double *e_dev,
+                     double *sums_dev, double *h_dev /* optional */, void *stream);
 
 /* Per-sample status words of the last launch (0 = ok, bit0 = non-positive or
  * non-finite pivot).  Synchronises.  Returns the number of flagged samples,

@@ -422,6 +422,28 @@ def elbo_step1_torch(torch_oracle, y_batch, mu, sig2, e_data, sig_e):
     return term1 - term2 - term3, term1, term2, term3
 
 
+def elbo_step2_torch(torch_oracle, mu, sig2, z_mean, z_sig, log_z_sig, logz_mean_post, logz_sig_post, e_data,
+                     sig_eta, alpha=1.0):
+    """main_custom_training.py:338-384 statement by statement: term4, term5 (with the [B, B*S]
+    broadcast of h_data against z_mean_point[B, 1, .] at main_custom_training.py:347-364), add_loss;
+    loss = (term4 - term5) * alpha + add_loss.  The theta nets are frozen (main_custom_training.py:305):
+    mu, sig2 carry no gradient."""
+    t = torch_oracle.torch
+    zd = z_mean.shape[-1]
+    term4 = t.mean(-0.5 * t.sum(log_z_sig, dim=-1) - t.sum(z_mean, dim=-1)) - 0.5 * zd * math.log(2.0 * math.pi) \
+        - 0.5 * zd
+    std = t.sqrt(sig2).unsqueeze(1)
+    theta = (e_data * std + mu.unsqueeze(1)).reshape(-1, mu.shape[-1])
+    _, h = torch_oracle.fem_fh(theta.detach())           # [B*S, 2]
+    zm, zs = z_mean.unsqueeze(1), z_sig.unsqueeze(1)      # [B, 1, 2]
+    l1 = -0.5 / sig_eta * t.sum(t.exp(2.0 * zm + 2.0 * zs), dim=-1)                       # [B, 1]
+    l2 = -0.5 / sig_eta * t.sum(-2.0 * (h * t.exp(zm + 0.5 * zs)) + h ** 2, dim=-1)       # [B, B*S]
+    l3 = -0.5 * zd * math.log(2.0 * math.pi * sig_eta)
+    term5 = t.mean(l1 + l2) + l3
+    add = t.mean((z_mean - logz_mean_post) ** 2) + t.mean((z_sig - logz_sig_post) ** 2)
+    return (term4 - term5) * alpha + add, term4, term5, add
+
+
 # ------------------------------------------------------ sparse form (large meshes)
 class SparseOracle:
     """The reference NumPy twin's own solver route -- CSR assembly by

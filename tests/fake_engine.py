@@ -34,3 +34,12 @@ class OracleEngine:
         else:
             gmu, gsig2 = torch.zeros_like(mu), torch.zeros_like(sig2)
         return sums, gmu, gsig2, (fd if want_f else None)
+
+    def elbo_step2_partials(self, mu, sig2, e_data, j_begin=0, j_end=None, want_h=False):
+        B, S = mu.shape[0], e_data.shape[0]
+        j_end = B * S if j_end is None else j_end
+        theta = (e_data * sig2.sqrt().unsqueeze(1) + mu.unsqueeze(1)).reshape(-1, 2)[j_begin:j_end]
+        with torch.no_grad():
+            _, h = self.oracle.fem_fh(theta)
+        sums = torch.cat([h.sum(0), (h ** 2).sum(0)]) if j_end > j_begin else torch.zeros(4, dtype=torch.float64)
+        return sums, (h if want_h else None)

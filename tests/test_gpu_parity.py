@@ -308,3 +308,38 @@ def test_graphed_elbo_step_equals_eager(pkg, engine):
         assert step.graphed == graph
         losses[graph] = np.array(seq)
     assert np.max(np.abs(losses[True] - losses[False])) < 1e-10 * np.max(np.abs(losses[False]))
+
+
+def test_elbo_step2_fused_vs_oracle(pkg, engine, torch_oracle):
+    """Step 2 (main_custom_training.py:304-384) on the fused forward-only op: the logz pre-pass and
+    the loss (term4 - term5) * alpha + add_loss with gradients w.r.t. the z nets."""
+    import torch
+    import fem_oracle as fo
+    rng = np.random.default_rng(41)
+    B, S = 8, 25
+    mu = rng.standard_normal((B, 2)) * 0.3
+    sig2 = np.exp(rng.standard_normal((B, 2)) * 0.2)
+    e = rng.standard_normal((S, 2))
+    eta = math.sqrt(3e-3) * rng.standard_normal((S, 2))
+    # pre-pass: moments of log z over the reparameterised samples (main_custom_training.py:311-328)
+    pm, ps = pkg.elbo.logz_posterior_moments(engine, _t(mu, engine), _t(sig2, engine), _t(e, engine), _t(eta, engine))
+    theta = (e[None] * np.sqrt(sig2)[:, None] + mu[:, None]).reshape(-1, 2)
+    _, ho = torch_oracle.fem_fh(torch.tensor(theta))
+    logz = np.log(ho.numpy().reshape(B, S, 2) + eta[None])
+    assert relerr(pm.cpu().numpy(), logz.mean(1)) < TOL and relerr(ps.cpu().numpy(), logz.var(1)) < 1e-8
+    res = []
+    for impl in range(2):
+        dev = engine.device if impl == 0 else torch.device("cpu")
+        zm = torch.tensor(logz.mean(1) + 0.02, device=dev, requires_grad=True)
+        lzs = torch.tensor(np.log(logz.var(1)) + 0.1, device=dev, requires_grad=True)
+        T = lambda a: torch.tensor(a, device=dev)
+        if impl == 0:
+            loss = pkg.elbo.Step2Loss(engine, T(e), 3e-3, alpha=0.5)(T(mu), T(sig2), zm, torch.exp(lzs), lzs,
+                                                                       T(logz.mean(1)), T(logz.var(1)))
+        else:
+            loss, *_ = fo.elbo_step2_torch(torch_oracle, T(mu), T(sig2), zm, torch.exp(lzs), lzs, T(logz.mean(1)),
+                                           T(logz.var(1)), T(e), 3e-3, alpha=0.5)
+        loss.backward()
+        res.append((float(loss), zm.grad.cpu().numpy(), lzs.grad.cpu().numpy()))
+    assert abs(res[0][0] - res[1][0]) < TOL * abs(res[1][0])
+    assert relerr(res[0][1], res[1][1]) < TOL and relerr(res[0][2], res[1][2]) < TOL

@@ -170,3 +170,78 @@ def test_step1_loss_sharded_over_gloo_ranks(tmp_path, world):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ERR" in o
+
+
+def test_step2_loss_equals_oracle_broadcast(pkg):
+    """Step2Loss (sufficient statistics of h) against the statement-by-statement restatement of
+    main_custom_training.py:338-384 with its [B, B*S] broadcast: value and gradients w.r.t. the z nets."""
+    import torch
+    import fem_oracle as fo
+    from fake_engine import OracleEngine
+    rng = np.random.default_rng(21)
+    B, S = 3, 4
+    eng = OracleEngine()
+    mu = torch.tensor(rng.standard_normal((B, 2)) * 0.3)
+    sig2 = torch.tensor(np.exp(rng.standard_normal((B, 2)) * 0.2))
+    e = torch.tensor(rng.standard_normal((S, 2)))
+    post_m = torch.tensor(rng.standard_normal((B, 2)) * 0.1 - 1.3)
+    post_s = torch.tensor(np.abs(rng.standard_normal((B, 2))) * 0.05)
+    vals = []
+    for impl in range(2):
+        zm = torch.tensor(np.full((B, 2), -1.3) + 0.05 * np.arange(B)[:, None], requires_grad=True)
+        lzs = torch.tensor(np.full((B, 2), -3.0) + 0.1 * np.arange(2)[None, :], requires_grad=True)
+        zs = torch.exp(lzs)
+        if impl == 0:
+            loss = pkg.elbo.Step2Loss(eng, e, 3e-3, alpha=0.7)(mu, sig2, zm, zs, lzs, post_m, post_s)
+        else:
+            loss, *_ = fo.elbo_step2_torch(eng.oracle, mu, sig2, zm, zs, lzs, post_m, post_s, e, 3e-3, alpha=0.7)
+        loss.backward()
+        vals.append((float(loss), zm.grad.clone(), lzs.grad.clone()))
+    assert abs(vals[0][0] - vals[1][0]) < 1e-12 * abs(vals[1][0])
+    assert float((vals[0][1] - vals[1][1]).abs().max()) < 1e-11 * float(vals[1][1].abs().max())
+    assert float((vals[0][2] - vals[1][2]).abs().max()) < 1e-11 * float(vals[1][2].abs().max())
+
+
+_WORKER2 = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import importlib
+pkg = importlib.import_module("variational-bayesian-inference-for-computational-mechanics_b200")
+import fem_oracle as fo
+from fake_engine import OracleEngine
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rng = np.random.default_rng(31)
+B, S = 3, 5
+mu = torch.tensor(rng.standard_normal((B, 2)) * 0.3); sig2 = torch.tensor(np.exp(rng.standard_normal((B, 2)) * 0.2))
+e = torch.tensor(rng.standard_normal((S, 2)))
+zm = torch.tensor(rng.standard_normal((B, 2)) * 0.1 - 1.3, requires_grad=True)
+lzs = torch.tensor(rng.standard_normal((B, 2)) * 0.1 - 3.0, requires_grad=True)
+pm = torch.tensor(rng.standard_normal((B, 2)) * 0.1 - 1.3); ps = torch.tensor(np.abs(rng.standard_normal((B, 2))) * 0.05)
+eng = OracleEngine()
+loss = pkg.elbo.Step2Loss(eng, e, 3e-3, alpha=1.0, rank=rank, world=world)(mu, sig2, zm, torch.exp(lzs), lzs, pm, ps)
+loss.backward()
+zm2 = zm.detach().clone().requires_grad_(True); lzs2 = lzs.detach().clone().requires_grad_(True)
+ref, *_ = fo.elbo_step2_torch(eng.oracle, mu, sig2, zm2, torch.exp(lzs2), lzs2, pm, ps, e, 3e-3)
+ref.backward()
+err = max(abs(float(loss - ref)) / abs(float(ref)),
+          float((zm.grad - zm2.grad).abs().max() / zm2.grad.abs().max()),
+          float((lzs.grad - lzs2.grad).abs().max() / lzs2.grad.abs().max()))
+print("RANK", rank, "ERR", err, flush=True)
+assert err < 1e-10, err
+dist.destroy_process_group()
+'''
+
+
+def test_step2_loss_sharded_over_gloo_ranks(tmp_path):
+    script = tmp_path / "worker2.py"
+    script.write_text(_WORKER2.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29612", OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), WORLD_SIZE="2"),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ERR" in o

@@ -32,7 +32,7 @@ INFO_NAMES = ["nfree", "half_bw", "ndof", "nele", "ncolors", "band_in_smem", "sm
 # every symbol include/vbfem.h declares
 SYMBOLS = [
     "vbfem_create", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_forward", "vbfem_backward",
-    "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_status", "vbfem_forward_host",
+    "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
     "vbfem_forward_backward_host", "vbfem_measure_peaks",
 ]
 
@@ -121,6 +121,9 @@ def load():
     lib.vbfem_elbo_step1.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp, c_dp,
                                      c_dp, ctypes.c_double, c_dp, c_dp, c_dp, c_dp, c_dp]
     lib.vbfem_elbo_step1.restype = ctypes.c_int
+    lib.vbfem_elbo_step2.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp, c_dp,
+                                     c_dp, c_dp, c_dp]
+    lib.vbfem_elbo_step2.restype = ctypes.c_int
     lib.vbfem_status.argtypes = [ctypes.c_void_p, c_dp, i64]
     lib.vbfem_status.restype = i64
     lib.vbfem_forward_host.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp]

@@ -634,6 +634,32 @@ __global__ void elbo_reduce_kernel(int B, int S, long long j_begin, long long j_
     }
 }
 
+// Step-2 sufficient statistics over the local sample range (fixed order):
+//   sums[0..1] = sum_j h_j (per component), sums[2..3] = sum_j h_j^2
+__global__ void hsum_kernel(long long nloc, const double *h, double *sums) {
+    __shared__ double sh[4][256];
+    const int tid = threadIdx.x;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (long long j = tid; j < nloc; j += blockDim.x) {
+        const double h0 = h[2 * j], h1 = h[2 * j + 1];
+        a0 += h0;
+        a1 += h1;
+        a2 += h0 * h0;
+        a3 += h1 * h1;
+    }
+    sh[0][tid] = a0;
+    sh[1][tid] = a1;
+    sh[2][tid] = a2;
+    sh[3][tid] = a3;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int q = 0; q < 4; ++q) sh[q][tid] += sh[q][tid + o];
+        __syncthreads();
+    }
+    if (tid < 4) sums[tid] = sh[tid][0];
+}
+
 __global__ void ysum_kernel(int B, const double *y, double *out) {
     if (threadIdx.x < 2) {
         double a = 0.0;
@@ -1371,6 +1397,40 @@ extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
     if (rc) return rc;
     const int nblk = 1 + (2 * B + 255) / 256;
     elbo_reduce_kernel<<<nblk, 256, 0, st>>>(B, S, j_begin, j_end, a.f_out, h->elbo_g, e, sig2, sums, gmu, gsig2);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
+                                const double *sig2, const double *e, double *sums, double *h_out, void *stream) {
+    if (!h || !mu || !sig2 || !e || !sums) return fail(-1, "null argument");
+    if (B <= 0 || S <= 0 || j_begin < 0 || j_end < j_begin || j_end > (int64_t)B * S)
+        return fail(-1, "bad ELBO sample range");
+    CU(cudaSetDevice(h->device));
+    const long long nloc = j_end - j_begin;
+    if (nloc > h->elbo_cap) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(h->elbo_f);
+        cudaFree(h->elbo_g);
+        h->elbo_f = h->elbo_g = nullptr;
+        h->elbo_cap = 0;
+        CU(cudaMalloc(&h->elbo_f, (size_t)std::max<long long>(nloc, 1) * 2 * sizeof(double)));
+        CU(cudaMalloc(&h->elbo_g, (size_t)std::max<long long>(nloc, 1) * 2 * sizeof(double)));
+        h->elbo_cap = nloc;
+    }
+    Args a{};
+    a.N = nloc;
+    a.mode = kElbo;  // forward only: the theta nets are frozen in step 2 (main_custom_training.py:305)
+    a.mu = mu;
+    a.sig2 = sig2;
+    a.e = e;
+    a.B = B;
+    a.S = S;
+    a.j_begin = j_begin;
+    a.h = h_out ? h_out : h->elbo_g;
+    int rc = launch(h, a, stream);
+    if (rc) return rc;
+    hsum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(nloc, a.h, sums);
     CU(cudaGetLastError());
     return 0;
 }

@@ -213,3 +213,73 @@ class GraphedStep1:
         else:
             self._body()
         return self.loss
+
+
+# ------------------------------------------------------------------------------------- step 2
+def term4(z_mean, log_z_sig, z_dim=2):
+    """main_custom_training.py:338-340."""
+    return ((-0.5 * log_z_sig.sum(dim=-1) - z_mean.sum(dim=-1)).mean()
+            - 0.5 * z_dim * math.log(2.0 * math.pi) - 0.5 * z_dim)
+
+
+def term5_from_sums(sums, z_mean, z_sig, n_samples, sig_eta, z_dim=2):
+    """term5 (main_custom_training.py:347-364) from sum_j h_j (sums[0:2]) and sum_j h_j^2
+    (sums[2:4]) over all ``n_samples`` = B*S samples.  Upstream broadcasts h_data[B*S, 2] against
+    z_mean_point[B, 1, 2], so l2 averages over ALL B x (B*S) pairs:
+        mean_{b,j} l2 = -0.5/sig_eta * sum_k( -2 mean_j(h_jk) mean_b exp(zm_bk + zs_bk/2) + mean_j(h_jk^2) )."""
+    l1 = -0.5 / sig_eta * torch_exp(2.0 * z_mean + 2.0 * z_sig).sum(dim=-1)
+    hm, h2m = sums[0:2] / n_samples, sums[2:4] / n_samples
+    em = torch_exp(z_mean + 0.5 * z_sig).mean(dim=0)
+    l2 = -0.5 / sig_eta * (-2.0 * hm * em + h2m).sum()
+    l3 = -0.5 * z_dim * math.log(2.0 * math.pi * sig_eta)
+    return l1.mean() + l2 + l3
+
+
+def torch_exp(t):
+    import torch
+
+    return torch.exp(t)
+
+
+def add_loss(z_mean, z_sig, logz_mean_post, logz_sig_post):
+    """main_custom_training.py:373-375."""
+    return ((z_mean - logz_mean_post) ** 2).mean() + ((z_sig - logz_sig_post) ** 2).mean()
+
+
+class Step2Loss:
+    """vi_pred_loss_step2 (main_custom_training.py:381-384) on the fused forward-only op:
+    (term4 - term5) * alpha + add_loss.  The theta nets are frozen in step 2
+    (main_custom_training.py:305), so the FEM needs no adjoint here: the library returns the
+    sufficient statistics of h over this rank's sample shard, the ranks all-reduce 4 doubles."""
+
+    def __init__(self, engine, e_data, sig_eta, alpha=1.0, group=None, rank=0, world=1):
+        self.engine, self.e_data, self.sig_eta, self.alpha = engine, e_data.contiguous(), float(sig_eta), float(alpha)
+        self.group, self.rank, self.world = group, int(rank), int(world)
+
+    def __call__(self, theta_mean, theta_sig, z_mean, z_sig, log_z_sig, logz_mean_post, logz_sig_post):
+        B, S = theta_mean.shape[0], self.e_data.shape[0]
+        lo, hi = shard_range(B * S, self.rank, self.world)
+        sums, _ = self.engine.elbo_step2_partials(theta_mean.detach().contiguous(), theta_sig.detach().contiguous(),
+                                                  self.e_data, lo, hi)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        t5 = term5_from_sums(sums, z_mean, z_sig, B * S, self.sig_eta)
+        return (term4(z_mean, log_z_sig) - t5) * self.alpha + add_loss(z_mean, z_sig, logz_mean_post, logz_sig_post)
+
+
+def logz_posterior_moments(engine, theta_mean, theta_sig, e_data, eta_err, chunk=1 << 18):
+    """The pre-pass of step 2 (main_custom_training.py:311-328): forward FEM over all
+    num_data * ne_sam reparameterised samples, z = h + eta_err, moments of log z over the samples.
+    theta_mean/theta_sig [D, 2], e_data [S, 2], eta_err [S, 2] (device tensors) ->
+    (logz_mean_post [D, 2], logz_sig_post [D, 2])."""
+    import torch
+
+    D, S = theta_mean.shape[0], e_data.shape[0]
+    theta = (e_data[None, :, :] * torch.sqrt(theta_sig)[:, None, :] + theta_mean[:, None, :]).reshape(-1, 2)
+    hs = []
+    for i in range(0, theta.shape[0], chunk):
+        hs.append(engine.forward(theta[i:i + chunk].contiguous())[1])
+    h = torch.cat(hs).reshape(D, S, 2)
+    logz = torch.log(h + eta_err[None, :, :])
+    return logz.mean(dim=1), logz.var(dim=1, unbiased=False)

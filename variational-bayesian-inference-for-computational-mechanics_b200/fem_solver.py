@@ -170,6 +170,21 @@ class CookFemEngine:
         self.launches += 3
         return sums, gmu, gsig2, f
 
+    def elbo_step2_partials(self, mu, sig2, e_data, j_begin=0, j_end=None, want_h=False):
+        """Forward-only FEM over the flat sample range [j_begin, j_end) of the B*S samples of the
+        frozen theta nets, reduced to (sum_j h_j, sum_j h_j^2) for term5
+        (main_custom_training.py:338-364).  Returns (sums[4], h|None)."""
+        B, S = int(mu.shape[0]), int(e_data.shape[0])
+        j_end = B * S if j_end is None else int(j_end)
+        sums = self._new(4)
+        h = self._new(max(j_end - j_begin, 0), 2) if want_h else None
+        _lib.check(self.lib.vbfem_elbo_step2(
+            self._h, B, S, int(j_begin), j_end, self._chk(mu, B, "mu"), self._chk(sig2, B, "sig2"),
+            self._chk(e_data, S, "e_data"), ctypes.c_void_p(sums.data_ptr()),
+            ctypes.c_void_p(h.data_ptr()) if want_h else ctypes.c_void_p(0), self._stream()), "vbfem_elbo_step2")
+        self.launches += 2
+        return sums, h
+
     def status(self, n):
         """Per-sample status words of the last launch; returns (n_bad, flags)."""
         flags = np.zeros(int(n), dtype=np.int32)
