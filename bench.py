@@ -346,9 +346,24 @@ def run_cuda(args):
                                "what": "NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd -> Adam (one CUDA graph replay per step), "
                                        "batch H2D and loss D2H inside; one NCCL all-reduce per step when N>1"}},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down in a safe order: the captured graph (it holds an NCCL all-reduce node) goes first,
+        # then the process group; a watchdog ends the process if the NCCL teardown does not return
+        # (seen once at 8 GPUs: the line above was printed, the interpreter never exited).
+        import gc
+        import threading
+        sys.stdout.flush()
+        dog = threading.Timer(45.0, lambda: os._exit(0))
+        dog.daemon = True
+        dog.start()
+        gstep.graph = None
+        del gstep
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        dog.cancel()
 
 
 def main():
