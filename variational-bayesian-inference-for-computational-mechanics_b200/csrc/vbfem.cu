@@ -41,6 +41,7 @@ struct DevModel {
     int ncolors, nitems;    // nitems = b(b+1)/2 trailing-update entries + b rhs entries per column step
     int band_in_smem;
     int vec_off, red_off;   // offsets (in doubles) of the two work vectors / reduction scratch in smem
+    int ring_off, ring_w;   // band in HBM: shared-memory ring of ring_w band columns (factor window / sweep staging)
     int obs_ele, obs_gp[2]; // 0-based
     int obs_dof[2];         // band rows of the observed node's (x, y) dofs, -1 if supported
     int obs_lmb[8];         // band rows of the observed element's dofs
@@ -189,10 +190,137 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 namespace vbfem {
 
 // ------------------------------------------------------------------------------------------
+// Band-in-HBM helpers of the generic kernel (wide bands, e.g. Cook 80x40: n = 6560, b = 85).
+// ------------------------------------------------------------------------------------------
+constexpr int kRingDepth = 8;  // band columns fetched ahead of the factorisation window (cp.async groups in flight)
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Triangular sweeps with the factor in HBM: the band columns pass through the shared-memory ring in
+// two halves of `ch` columns; warps 1.. stage the next half while warp 0 sweeps the current one.
+//   DIR = -1: back substitution L^T x = y, column oriented: x_j = y_j - sum_i L[j+i][j] x_{j+i}
+//   DIR = +1: forward substitution L z = w from column j0: z[j+i] -= L[j+i][j] z_j
+template <int NT, int DIR>
+__device__ __forceinline__ void staged_sweep(const double *__restrict__ band, double *__restrict__ ring, int ch,
+                                             int n, int b, int ldb, double *__restrict__ x, int j0, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int first = (DIR > 0) ? j0 : n - 1;
+    const int ncol = (DIR > 0) ? n - j0 : n;
+    const int nchunk = (ncol + ch - 1) / ch;
+    auto chunk_lo = [&](int q) { return (DIR > 0) ? first + q * ch : max(first - (q + 1) * ch + 1, 0); };
+    auto chunk_cnt = [&](int q) { return (DIR > 0) ? min(ch, n - (first + q * ch)) : (first - q * ch) - chunk_lo(q) + 1; };
+    auto stage = [&](int q, int t0, int nthr) {
+        const int lo = chunk_lo(q), cnt = chunk_cnt(q);
+        double *dst = ring + (q & 1) * ch * ldb;
+        const double *src = band + (size_t)lo * ldb;
+        for (int i = t0; i < cnt * ldb; i += nthr) dst[i] = src[i];
+    };
+    if (nchunk <= 0) return;
+    stage(0, tid, NT);
+    __syncthreads();
+    for (int q = 0; q < nchunk; ++q) {
+        if (warp > 0) {
+            if (q + 1 < nchunk) stage(q + 1, tid - 32, NT - 32);
+        } else {
+            const int lo = chunk_lo(q), cnt = chunk_cnt(q);
+            const double *cols = ring + (q & 1) * ch * ldb;
+            if (DIR < 0) {
+                int j = lo + cnt - 1;
+                // four columns per trip: four independent partial dot products over the already final
+                // entries (their shuffle reductions overlap), then the 4x4 coupling inside the block
+                for (; j - 3 >= lo; j -= 4) {
+                    double acc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double *c = cols + (j - k - lo) * ldb;
+                        acc[k] = 0.0;
+                        for (int i = k + 1 + lane; i <= b; i += 32)
+                            if (j - k + i < n) acc[k] = fma(c[i], x[j - k + i], acc[k]);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                    const double *c1 = cols + (j - 1 - lo) * ldb, *c2 = cols + (j - 2 - lo) * ldb,
+                                 *c3 = cols + (j - 3 - lo) * ldb;
+                    const double x0 = x[j] - acc[0];
+                    const double x1 = fma(-c1[1], x0, x[j - 1] - acc[1]);
+                    const double x2 = fma(-c2[1], x1, fma(-c2[2], x0, x[j - 2] - acc[2]));
+                    const double x3 = fma(-c3[1], x2, fma(-c3[2], x1, fma(-c3[3], x0, x[j - 3] - acc[3])));
+                    __syncwarp();
+                    if (lane == 0) {
+                        x[j] = x0;
+                        x[j - 1] = x1;
+                        x[j - 2] = x2;
+                        x[j - 3] = x3;
+                    }
+                    __syncwarp();
+                }
+                for (; j >= lo; --j) {
+                    const double *c = cols + (j - lo) * ldb;
+                    double acc = 0.0;
+                    for (int i = 1 + lane; i <= b; i += 32)
+                        if (j + i < n) acc = fma(c[i], x[j + i], acc);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) x[j] -= acc;
+                    __syncwarp();
+                }
+            } else {
+                int j = lo;
+                // four columns per trip: resolve the block's four unknowns (every lane redundantly),
+                // then one pass over the rows below applies all four columns
+                for (; j + 3 < lo + cnt; j += 4) {
+                    const double *c0 = cols + (j - lo) * ldb, *c1 = c0 + ldb, *c2 = c1 + ldb, *c3 = c2 + ldb;
+                    const double z0 = x[j];
+                    const double z1 = fma(-c0[1], z0, x[j + 1]);
+                    const double z2 = fma(-c1[1], z1, fma(-c0[2], z0, x[j + 2]));
+                    const double z3 = fma(-c2[1], z2, fma(-c1[2], z1, fma(-c0[3], z0, x[j + 3])));
+                    __syncwarp();
+                    if (lane == 0) {
+                        x[j + 1] = z1;
+                        x[j + 2] = z2;
+                        x[j + 3] = z3;
+                    }
+                    // rows r = j+4 .. j+3+b: entry of column j+k at offset r - (j+k), valid while <= b
+                    for (int r = j + 4 + lane; r <= j + 3 + b && r < n; r += 32) {
+                        const int o = r - j;
+                        double a = x[r];
+                        if (o <= b) a = fma(-c0[o], z0, a);
+                        if (o - 1 <= b) a = fma(-c1[o - 1], z1, a);
+                        if (o - 2 <= b) a = fma(-c2[o - 2], z2, a);
+                        a = fma(-c3[o - 3], z3, a);
+                        x[r] = a;
+                    }
+                    __syncwarp();
+                }
+                for (; j < lo + cnt; ++j) {
+                    const double *c = cols + (j - lo) * ldb;
+                    const double zj = x[j];
+                    for (int i = 1 + lane; i <= b; i += 32)
+                        if (j + i < n) x[j + i] = fma(-c[i], zj, x[j + i]);
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic per-sample kernel (any bandwidth; band in shared memory if it fits, else in HBM).
 // Used when the twisted on-chip variant does not apply (e.g. the 80x40 mesh).
 // ------------------------------------------------------------------------------------------
-template <int NT, int EPT, int MINB>
+template <int NT, int EPT, int MINB, bool HBM>
 __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ DevModel M,
                                                  const __grid_constant__ Args A) {
     extern __shared__ __align__(16) double smem[];
@@ -211,7 +339,7 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
     {
         const int ntri = b * (b + 1) / 2;
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
+        for (int k = 0; k < (HBM ? 0 : EPT); ++k) {
             int idx = tid + k * NT;
             it_tgt[k] = -1;
             it_s1[k] = it_s2[k] = it_row[k] = 0;
@@ -234,6 +362,10 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
             }
         }
     }
+
+    // band in HBM: the factorisation window lives in a shared-memory ring
+    double *ring = smem + M.ring_off;
+    const int ring_w = M.ring_w, ring_ch = M.ring_w / 2;
 
     for (long long s = blockIdx.x; s < A.N; s += gridDim.x) {
         // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu)
@@ -323,34 +455,102 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
             }
 
             // ---------------- (c) banded LDL^T, forward substitution fused (rhs slot b+1)
-            for (int j = 0; j < n; ++j) {
-                double *colj = band + j * ldb;
-                const double d = colj[0];
-                if (tid == 0 && !(d > 0.0 && d < 1.0e300)) s_flag = 1;
-                const double rd = fast_rcp(d);
+            if (!HBM) {
+                for (int j = 0; j < n; ++j) {
+                    double *colj = band + j * ldb;
+                    const double d = colj[0];
+                    if (tid == 0 && !(d > 0.0 && d < 1.0e300)) s_flag = 1;
+                    const double rd = fast_rcp(d);
 #pragma unroll
-                for (int k = 0; k < EPT; ++k) {
-                    if (it_tgt[k] >= 0 && j + it_row[k] < n) {
-                        const double v = colj[it_s1[k]];
-                        const double w = colj[it_s2[k]] * rd;
-                        colj[it_tgt[k]] = fma(-v, w, colj[it_tgt[k]]);
+                    for (int k = 0; k < EPT; ++k) {
+                        if (it_tgt[k] >= 0 && j + it_row[k] < n) {
+                            const double v = colj[it_s1[k]];
+                            const double w = colj[it_s2[k]] * rd;
+                            colj[it_tgt[k]] = fma(-v, w, colj[it_tgt[k]]);
+                        }
                     }
+                    __syncthreads();
+                }
+                // L = V D^-1 (unit lower), diagonal slot <- 1/d, rhs slot <- D^-1 z
+                for (int c = tid; c < n; c += NT) band[c * ldb] = fast_rcp(band[c * ldb]);
+                __syncthreads();
+                for (int c = warp; c < n; c += NW) {
+                    const double rdc = band[c * ldb];
+                    for (int i = 1 + lane; i <= b + 1; i += 32) band[c * ldb + i] *= rdc;
                 }
                 __syncthreads();
+            } else {
+                // Band in HBM: the b+1 columns under the trailing update live in a shared-memory ring
+                // (column c <-> slot c mod ring_w).  While the block updates the window of column j, the
+                // first ldb threads write the finished column j-1 back (already scaled: L = V D^-1, 1/d,
+                // D^-1 z) and fetch column j-1+ring_w into its slot with cp.async, kRingDepth columns
+                // ahead of its first use.
+                __syncthreads();  // assembly complete in HBM
+                for (int i = tid; i < min(ring_w, n) * ldb; i += NT) ring[i] = band[i];
+                __syncthreads();
+                int js = 0;
+                double rd_prev = 0.0;
+                for (int j = 0; j < n; ++j) {
+                    const double *colj = ring + js * ldb;
+                    const double d = colj[0];
+                    if (tid == 0 && !(d > 0.0 && d < 1.0e300)) s_flag = 1;
+                    const double rd = fast_rcp(d);
+                    // trailing update, one warp per target column j+m, lanes over its entries (no index
+                    // tables: the item arrays of the shared-memory path would live in local memory here)
+                    const double zjs = colj[b + 1];
+                    // trailing update, one warp per target column j+m, lanes over its entries
+                    for (int m = 1 + warp; m <= b && j + m < n; m += NW) {
+                        int slot = js + m;
+                        slot -= (slot >= ring_w) ? ring_w : 0;
+                        double *tc = ring + slot * ldb + lane;
+                        const double *cs = colj + m + lane;
+                        const double wm = colj[m] * rd;    // L[j+m][j]
+                        const int cnt = b - m + 1 - lane;  // this lane's entries t = lane, lane+32, ... below cnt
+                        if (b <= 127) {
+                            // all loads first, then the FMAs, then the stores: source and target live in the
+                            // same ring, a load-FMA-store loop would serialise on the assumed aliasing
+                            double a[4], c[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                a[q] = (32 * q < cnt) ? tc[32 * q] : 0.0;
+                                c[q] = (32 * q < cnt) ? cs[32 * q] : 0.0;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (32 * q < cnt) tc[32 * q] = fma(-c[q], wm, a[q]);
+                        } else {
+                            for (int t = 0; t < cnt; t += 32) tc[t] = fma(-cs[t], wm, tc[t]);
+                        }
+                        if (lane == 31) tc[b + 1 - lane] = fma(-zjs, wm, tc[b + 1 - lane]);  // rhs[j+m] -= L[j+m][j] z_j
+                    }
+                    if (tid < ldb && j >= 1) {
+                        int sp = js - 1;
+                        sp += (sp < 0) ? ring_w : 0;
+                        const double v = ring[sp * ldb + tid];
+                        band[(size_t)(j - 1) * ldb + tid] = (tid == 0) ? rd_prev : v * rd_prev;
+                        const int jn = j - 1 + ring_w;
+                        if (jn < n) cp_async8(ring + sp * ldb + tid, band + (size_t)jn * ldb + tid);
+                    }
+                    cp_async_commit();
+                    cp_async_wait<kRingDepth - 1>();
+                    __syncthreads();
+                    rd_prev = rd;
+                    js = (js + 1 == ring_w) ? 0 : js + 1;
+                }
+                if (tid < ldb) {
+                    int sp = js - 1;
+                    sp += (sp < 0) ? ring_w : 0;
+                    const double v = ring[sp * ldb + tid];
+                    band[(size_t)(n - 1) * ldb + tid] = (tid == 0) ? rd_prev : v * rd_prev;
+                }
+                cp_async_wait<0>();
+                __syncthreads();
             }
-            // L = V D^-1 (unit lower), diagonal slot <- 1/d, rhs slot <- D^-1 z
-            for (int c = tid; c < n; c += NT) band[c * ldb] = fast_rcp(band[c * ldb]);
-            __syncthreads();
-            for (int c = warp; c < n; c += NW) {
-                const double rdc = band[c * ldb];
-                for (int i = 1 + lane; i <= b + 1; i += 32) band[c * ldb + i] *= rdc;
-            }
-            __syncthreads();
 
             // ---------------- back substitution  L^T u = D^-1 z
             if (b <= 31) {
                 if (warp == 0) warp_back_sweep(band, n, b, ldb, band + (b + 1), ldb, nullptr, vec_u, lane);
-            } else {
+            } else if (!HBM) {
                 for (int r = tid; r < n; r += NT) vec_u[r] = band[r * ldb + (b + 1)];
                 __syncthreads();
                 for (int j = n - 1; j >= 0; --j) {
@@ -359,6 +559,10 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                         if (j - i >= 0) vec_u[j - i] = fma(-band[(j - i) * ldb + i], xj, vec_u[j - i]);
                     __syncthreads();
                 }
+            } else {
+                for (int r = tid; r < n; r += NT) vec_u[r] = band[(size_t)r * ldb + (b + 1)];
+                __syncthreads();
+                staged_sweep<NT, -1>(band, ring, ring_ch, n, b, ldb, vec_u, 0, tid);
             }
             __syncthreads();
             if (A.mode & kKeep) {  // solution travels in the rhs slot of the stored factor
@@ -510,6 +714,11 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                     __syncwarp();
                     warp_back_sweep(band, n, b, ldb, vec_p, 1, band, vec_p, lane);
                 }
+            } else if (HBM) {
+                staged_sweep<NT, +1>(band, ring, ring_ch, n, b, ldb, vec_p, M.w_first, tid);
+                for (int r = tid; r < n; r += NT) vec_p[r] *= band[(size_t)r * ldb];
+                __syncthreads();
+                staged_sweep<NT, -1>(band, ring, ring_ch, n, b, ldb, vec_p, 0, tid);
             } else {
                 for (int j = M.w_first; j < n; ++j) {
                     const double zj = vec_p[j];
@@ -831,9 +1040,9 @@ static std::vector<int> rcm_order(const vbfem_mesh *m) {
     return order;
 }
 
-template <int NT, int EPT, int MINB>
+template <int NT, int EPT, int MINB, bool HBM>
 static int configure(vbfem_handle *h, size_t smem) {
-    kernel_fn k = fem_kernel<NT, EPT, MINB>;
+    kernel_fn k = fem_kernel<NT, EPT, MINB, HBM>;
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NT, smem));
@@ -1031,7 +1240,12 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     {
-        const int NT = (M.nitems <= 352) ? 352 : (M.nitems <= 512 ? 256 : (M.nitems <= 4096 ? 512 : 1024));
+        int NT = (M.nitems <= 352) ? 352 : (M.nitems <= 512 ? 256 : (M.nitems <= 4096 ? 512 : 1024));
+        {   // band in HBM: 256 threads (255 registers, no spills: the per-column loop must not touch local memory)
+            const size_t need = (((size_t)n * ldb + 1) & ~(size_t)1) * sizeof(double) +
+                                (2 * (size_t)n + 2 * (NT / 32) + 32) * sizeof(double);
+            if (need > (size_t)prop.sharedMemPerBlockOptin) NT = 256;
+        }
         const int scratch = 2 * (NT / 32) + 32;
         const size_t band_doubles = ((size_t)n * ldb + 1) & ~(size_t)1;
         const size_t small = (2 * (size_t)n + scratch) * sizeof(double);
@@ -1040,19 +1254,30 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         M.band_in_smem = big <= cap ? 1 : 0;
         M.vec_off = M.band_in_smem ? (int)band_doubles : 0;
         M.red_off = M.vec_off + 2 * n;
-        const size_t smem = M.band_in_smem ? big : small;
+        // band in HBM: ring of b + 1 + kRingDepth columns behind the vectors (factor window, sweep staging)
+        M.ring_w = (b + 1 + kRingDepth + 1) & ~1;
+        M.ring_off = (M.red_off + scratch + 1) & ~1;
+        const size_t ring_bytes = M.band_in_smem ? 0 : (size_t)M.ring_w * ldb * sizeof(double);
+        if (!M.band_in_smem && small + 16 + ring_bytes > cap) {
+            vbfem_destroy(h);
+            return fail(-3, "mesh too large: %zu bytes of shared memory for the work vectors and the band window",
+                        small + ring_bytes);
+        }
+        const size_t smem = M.band_in_smem ? big : small + 16 + ring_bytes;
         if (M.nitems > 1024 * 16) {
             vbfem_destroy(h);
             return fail(-3, "half bandwidth %d too large", b);
         }
-        if (NT == 352)
-            rc = configure<352, 1, 2>(h, smem);
+        if (!M.band_in_smem)
+            rc = configure<256, 1, 1, true>(h, smem);
+        else if (NT == 352)
+            rc = configure<352, 1, 2, false>(h, smem);
         else if (NT == 256)
-            rc = configure<256, 2, 2>(h, smem);
+            rc = configure<256, 2, 2, false>(h, smem);
         else if (NT == 512)
-            rc = configure<512, 8, 1>(h, smem);
+            rc = configure<512, 8, 1, false>(h, smem);
         else
-            rc = configure<1024, 16, 1>(h, smem);
+            rc = configure<1024, 16, 1, false>(h, smem);
         if (rc) {
             vbfem_destroy(h);
             return rc;
