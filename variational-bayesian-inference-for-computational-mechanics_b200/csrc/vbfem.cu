@@ -438,14 +438,37 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                 }
                 for (int c = 0; c < M.ncolors; ++c) {
                     if (color == c) {
+                        if (HBM) {
+                            // band in HBM: the 36 targets of an element are distinct and no other element of
+                            // this colour shares them -- issue all loads, then all stores (a `+=` loop would
+                            // serialise 36 HBM round trips on the assumed aliasing)
+                            double cur[36];
 #pragma unroll
-                        for (int a = 0; a < 8; ++a) {
+                            for (int a = 0; a < 8; ++a)
 #pragma unroll
-                            for (int q = 0; q <= a; ++q) {
-                                const int pa = lm[a], pq = lm[q];
-                                if (pa >= 0 && pq >= 0) {
+                                for (int q = 0; q <= a; ++q) {
+                                    const int pa = lm[a], pq = lm[q];
                                     const int lo = min(pa, pq), hi = max(pa, pq);
-                                    band[lo * ldb + (hi - lo)] += ke[tri(a, q)];
+                                    cur[tri(a, q)] = (lo >= 0) ? band[(size_t)lo * ldb + (hi - lo)] : 0.0;
+                                }
+#pragma unroll
+                            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                                for (int q = 0; q <= a; ++q) {
+                                    const int pa = lm[a], pq = lm[q];
+                                    const int lo = min(pa, pq), hi = max(pa, pq);
+                                    if (lo >= 0) band[(size_t)lo * ldb + (hi - lo)] = cur[tri(a, q)] + ke[tri(a, q)];
+                                }
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < 8; ++a) {
+#pragma unroll
+                                for (int q = 0; q <= a; ++q) {
+                                    const int pa = lm[a], pq = lm[q];
+                                    if (pa >= 0 && pq >= 0) {
+                                        const int lo = min(pa, pq), hi = max(pa, pq);
+                                        band[lo * ldb + (hi - lo)] += ke[tri(a, q)];
+                                    }
                                 }
                             }
                         }
@@ -521,7 +544,16 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                         } else {
                             for (int t = 0; t < cnt; t += 32) tc[t] = fma(-cs[t], wm, tc[t]);
                         }
-                        if (lane == 31) tc[b + 1 - lane] = fma(-zjs, wm, tc[b + 1 - lane]);  // rhs[j+m] -= L[j+m][j] z_j
+                    }
+                    // right-hand side slots of the b columns below: rhs[j+m] -= L[j+m][j] z_j, lanes over m
+                    // (one dependent read-modify-write per target column inside the loop above would stall it)
+                    if (warp == NW - 1) {
+                        for (int m = 1 + lane; m <= b && j + m < n; m += 32) {
+                            int slot = js + m;
+                            slot -= (slot >= ring_w) ? ring_w : 0;
+                            double *tr = ring + slot * ldb + (b + 1);
+                            *tr = fma(-zjs, colj[m] * rd, *tr);
+                        }
                     }
                     if (tid < ldb && j >= 1) {
                         int sp = js - 1;
