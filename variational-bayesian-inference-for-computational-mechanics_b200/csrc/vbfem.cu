@@ -4,14 +4,17 @@
 //   (a) per-element Q4 Gauss-point kernel: shape functions, material subroutine
 //       (stress + consistent tangent), element stiffness in registers
 //       [src/mat_subroutine_tf.py:23-110, src/fem_preprocess.py:1223-1285]
-//   (b) atomics-free scatter assembly, colour by colour, into a banded SPD matrix held
-//       in shared memory under an internal bandwidth-minimising numbering
+//   (b) atomics-free scatter assembly, colour by colour, into a banded SPD matrix under an
+//       internal bandwidth-minimising numbering
 //       [replaces tf.scatter_nd into dense Kg, src/fem_solver_tf.py:336-341]
-//   (c) banded LDL^T, forward substitution fused into the column loop, warp-level
-//       back substitution [replaces tf.linalg.solve, src/fem_solver_tf.py:137]
+//   (c) banded LDL^T with the forward substitution fused into the column loop, back
+//       substitution [replaces tf.linalg.solve, src/fem_solver_tf.py:137]
 //   (d) fused displacement / von Mises observation [src/fem_postprocess.py:172-185]
 //   (e) adjoint: reuse the factor for K psi = dJ/du, contract -psi^T (dK/dp) u element
 //       by element, chain to x [what tape.gradient derives, main_custom_training.py:252-256]
+// Two kernels: fem_front_kernel (vbfem_front_kernel.cuh; band on chip, two warp-synchronous
+// elimination fronts -- the production path for Cook 20x10) and fem_kernel below (any
+// bandwidth, band in shared memory or HBM, full fields).
 // Paths are relative to nfeng2022/Variational-Bayesian-Inference-for-Computational-Mechanics.
 #include <cuda_runtime.h>
 
@@ -318,7 +321,7 @@ __device__ __forceinline__ void staged_sweep(const double *__restrict__ band, do
 
 // ------------------------------------------------------------------------------------------
 // Generic per-sample kernel (any bandwidth; band in shared memory if it fits, else in HBM).
-// Used when the twisted on-chip variant does not apply (e.g. the 80x40 mesh).
+// Used when the on-chip two-front kernel does not apply (e.g. the 80x40 mesh) and for full fields.
 // ------------------------------------------------------------------------------------------
 template <int NT, int EPT, int MINB, bool HBM>
 __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ DevModel M,
@@ -518,10 +521,9 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                     const double d = colj[0];
                     if (tid == 0 && !(d > 0.0 && d < 1.0e300)) s_flag = 1;
                     const double rd = fast_rcp(d);
-                    // trailing update, one warp per target column j+m, lanes over its entries (no index
-                    // tables: the item arrays of the shared-memory path would live in local memory here)
                     const double zjs = colj[b + 1];
-                    // trailing update, one warp per target column j+m, lanes over its entries
+                    // trailing update, one warp per target column j+m, lanes over its entries (no index
+                    // tables here: the item arrays of the shared-memory path cost registers)
                     for (int m = 1 + warp; m <= b && j + m < n; m += NW) {
                         int slot = js + m;
                         slot -= (slot >= ring_w) ? ring_w : 0;
