@@ -1187,6 +1187,27 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         color[e] = c;
         ncolors = std::max(ncolors, c + 1);
     }
+    // Structured quad grids numbered along the short side (Cook nx x ny: b = 2(ny+2)+1) also admit the
+    // colouring (i + 2j) mod 4.  It is preferred when valid: elements of one colour then spread over four
+    // shared-memory bank classes instead of two (same-colour band targets lie 4 or 44 rows apart, a row
+    // is 26 doubles), which halves the bank conflicts of the scatter.
+    if (ncolors == 4 && b >= 9 && (b - 1) % 2 == 0) {
+        const int per = 2 * ((b - 1) / 2 - 1);  // dofs per node column
+        std::vector<int> alt(ne, -1);
+        bool valid = per > 0;
+        for (int e = 0; e < ne && valid; ++e) {
+            int rmax = -1;
+            for (int a = 0; a < 4; ++a)
+                for (int c = 0; c < 2; ++c) rmax = std::max(rmax, dof2band[2 * (m->ien[4 * e + a] - 1) + c]);
+            if (rmax < 0) valid = false;
+            else alt[e] = ((rmax / per) + 2 * ((rmax % per) / 2)) & 3;
+        }
+        for (int e = 0; e < ne && valid; ++e)
+            for (int a = 0; a < 4 && valid; ++a)
+                for (int o : node_elems[m->ien[4 * e + a] - 1])
+                    if (o != e && alt[o] == alt[e]) valid = false;
+        if (valid) color = alt;
+    }
     std::vector<int> eorder(ne);
     std::iota(eorder.begin(), eorder.end(), 0);
     std::stable_sort(eorder.begin(), eorder.end(), [&](int a, int c) { return color[a] < color[c]; });
