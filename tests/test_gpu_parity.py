@@ -343,3 +343,37 @@ def test_elbo_step2_fused_vs_oracle(pkg, engine, torch_oracle):
         res.append((float(loss), zm.grad.cpu().numpy(), lzs.grad.cpu().numpy()))
     assert abs(res[0][0] - res[1][0]) < TOL * abs(res[1][0])
     assert relerr(res[0][1], res[1][1]) < TOL and relerr(res[0][2], res[1][2]) < TOL
+
+
+@pytest.mark.parametrize("nx,ny,variant", [
+    (24, 8, 2),    # n = 432, narrower band (b = 21 < 25): front kernel with a zero-padded band
+    (20, 9, 2),    # n = 400, b = 23: other front lengths
+    (16, 8, 0),    # n = 288: too small for the front kernel's shared-memory layout -> generic kernel
+    (30, 10, 0),   # n = 660: the band no longer fits twice per SM -> generic kernel, band in shared memory
+])
+def test_other_mesh_sizes(pkg, nx, ny, variant):
+    """Cook membranes of other sizes through the same entry points (mesh text -> preprocessor ->
+    engine), against the oracle built from the same text: forward, fused adjoint, Jacobian mode."""
+    import torch
+    import fem_oracle as fo
+    md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(nx, ny))
+    node_id, ele_id = (nx + 1) * (ny + 1), nx // 2 + 2
+    eng = pkg.CookFemEngine(md, device=0, node_id=node_id, ele_id=ele_id)
+    assert eng.info["kernel_variant"] == variant, eng.info
+    m = fo.read_mesh_text(fo.cook_mesh_text(nx, ny))
+    dof = fo.assign_dof(m)
+    to = fo.TorchOracle(m, dof, node_id=node_id, ele_id=ele_id)
+    n = 40
+    x = np.random.default_rng(nx).standard_normal((n, 2))
+    gy = np.random.default_rng(ny).standard_normal((n, 2))
+    gh = np.random.default_rng(nx + ny).standard_normal((n, 2))
+    yo, ho, gxo = to.vjp(x, gy, gh)
+    y, h, gx = eng.forward_backward(_t(x, eng), _t(gy, eng), _t(gh, eng))
+    assert relerr(y.cpu().numpy(), yo) < TOL and relerr(h.cpu().numpy(), ho) < TOL
+    assert relerr(gx.cpu().numpy(), gxo) < TOL
+    y2, h2 = eng.forward(_t(x, eng), keep_factor=True)
+    gx2 = eng.backward(_t(gy, eng), _t(gh, eng))
+    assert relerr(y2.cpu().numpy(), yo) < TOL and relerr(h2.cpu().numpy(), ho) < TOL
+    assert relerr(gx2.cpu().numpy(), gxo) < TOL
+    assert eng.status(n)[0] == 0
+    eng.close()

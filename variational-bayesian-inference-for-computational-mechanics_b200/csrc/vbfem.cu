@@ -1389,6 +1389,9 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         }
         const size_t fr_doubles = (size_t)n * TP + 5 * (size_t)n + 32 + 32 + 8 * (TNT / 32);
         const size_t fr_smem = fr_doubles * sizeof(double);
+        // the first two vectors double as the zero extension behind the bottom front's band
+        // ((TP-1)*TP + 1 doubles) and as the Schur hand-over scratch (TP*TP + 3*TP + 4 doubles)
+        if (ok && 2 * n < TP * TP + 3 * TP + 4) ok = false;
         if (ok && (n % 2 != 0 || (size_t)n * TP >= 32000 ||
                    2 * (fr_smem + 1024) > (size_t)prop.sharedMemPerMultiprocessor))
             ok = false;
