@@ -246,6 +246,11 @@ def test_refined_mesh_80x40(pkg):
         ym, hm = so.fem_fh(xm, 3321, 12)
         fd = (((yp - ym) * gy).sum(1) + ((hp - hm) * gh).sum(1)) / (2 * eps)
         assert np.max(np.abs(fd - gx.cpu().numpy()[:, k])) < 1e-6 * max(1.0, np.abs(fd).max())
+    # forward(keep) + backward (the autograd / tf.custom_gradient route: factor kept in HBM) == fused
+    y2, h2 = eng.forward(_t(x, eng), keep_factor=True)
+    gx2 = eng.backward(_t(gy, eng), _t(gh, eng))
+    assert relerr(y2.cpu().numpy(), yo) < TOL and relerr(h2.cpu().numpy(), ho) < TOL
+    assert relerr(gx2.cpu().numpy(), gx.cpu().numpy()) < TOL
     eng.close()
 
 
