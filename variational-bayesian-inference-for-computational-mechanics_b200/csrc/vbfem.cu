@@ -1213,6 +1213,12 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     std::stable_sort(eorder.begin(), eorder.end(), [&](int a, int c) { return color[a] < color[c]; });
 
     vbfem_handle *h = new vbfem_handle();
+    struct Guard {  // every failing return below releases the half-built handle
+        vbfem_handle *p;
+        ~Guard() {
+            if (p) vbfem_destroy(p);
+        }
+    } guard{h};
     h->device = device;
     DevModel &M = h->M;
     M.n = n;
@@ -1285,7 +1291,6 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     rc |= upload(h, pf, &M.pf);
     rc |= upload(h, band2dof, &M.band2dof);
     if (rc) {
-        vbfem_destroy(h);
         return -2;
     }
 
@@ -1314,13 +1319,11 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         M.ring_off = (M.red_off + scratch + 1) & ~1;
         const size_t ring_bytes = M.band_in_smem ? 0 : (size_t)M.ring_w * ldb * sizeof(double);
         if (!M.band_in_smem && small + 16 + ring_bytes > cap) {
-            vbfem_destroy(h);
             return fail(-3, "mesh too large: %zu bytes of shared memory for the work vectors and the band window",
                         small + ring_bytes);
         }
         const size_t smem = M.band_in_smem ? big : small + 16 + ring_bytes;
         if (M.nitems > 1024 * 16) {
-            vbfem_destroy(h);
             return fail(-3, "half bandwidth %d too large", b);
         }
         if (!M.band_in_smem)
@@ -1334,7 +1337,6 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         else
             rc = configure<1024, 16, 1, false>(h, smem);
         if (rc) {
-            vbfem_destroy(h);
             return rc;
         }
         h->ws_stride = (long long)band_doubles + 8;
@@ -1446,7 +1448,6 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                 M.sm_ticket = const_cast<int *>(p);
             }
             if (rc2) {
-                vbfem_destroy(h);
                 return -2;
             }
             kernel_fn ks[3] = {fem_front_kernel<TB, TNT, 0>, fem_front_kernel<TB, TNT, 1>,
@@ -1457,7 +1458,6 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                 int nb = 0;
                 if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], TNT, fr_smem);
                 if (e1 != cudaSuccess || nb < 1) {
-                    vbfem_destroy(h);
                     return fail(-3, "front kernel does not fit (%zu bytes of shared memory)", fr_smem);
                 }
                 nbmin = std::min(nbmin, nb);
@@ -1471,6 +1471,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             h->ws_stride = 8;  // the 4x2 Jacobian d(y, h)/dx per sample
             h->info_colors = ncolors;
             CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
+            guard.p = nullptr;
             *out = h;
             return 0;
         }
@@ -1479,6 +1480,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     // ---- no front kernel for this mesh / observation set-up: the generic kernel serves every mode
     h->info_colors = ncolors;
     CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
+    guard.p = nullptr;
     *out = h;
     return 0;
 }
