@@ -74,6 +74,14 @@ enum {
  * colouring, device tables, workspace.  Replaces the setup the reference does
  * in fem_preprocess.py:291-443 + fem_solver_tf.py:378-396 (host side). */
 int vbfem_create(vbfem_t **out, const vbfem_mesh *mesh, int device);
+
+/* The host-side plan vbfem_create would make for this mesh and observation set-up, WITHOUT touching
+ * a GPU (unit tests of the numbering / orientation / front split): out[0] = kernel variant (2 = on-chip
+ * two-front kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
+ * middle row pT, out[4] = bottom-front columns nB, out[5] = 1 if the band order was reversed so that
+ * it ends at the observed node, out[6] = shared memory per CTA in bytes, out[7] reserved.
+ * smem_per_sm: shared memory per SM assumed for the fit test (<= 0: 233472, B200). */
+int vbfem_plan(const vbfem_mesh *mesh, int64_t smem_per_sm, int64_t *out /* [8] */);
 void vbfem_destroy(vbfem_t *h);
 const char *vbfem_last_error(void);
 int vbfem_info(const vbfem_t *h, int64_t *out /* [VBFEM_INFO_COUNT] */);

@@ -19,11 +19,20 @@ def _t(a, eng):
     return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=eng.device)
 
 
+def golden_model_of(engine):
+    import conftest
+    return conftest.model_from_golden(np.load(conftest.os.path.join(conftest.ROOT, "tests", "golden", "ref_numpy_twin.npz")))
+
+
 def test_native_library_is_loaded(engine, pkg):
     maps = open("/proc/self/maps").read()
     assert "libvbfem.so" in maps
     assert engine.info["nfree"] == 440 and engine.info["half_bw"] == 25  # short-side numbering
     assert engine.info["band_in_smem"] == 1
+    # the host-only plan (vbfem_plan, unit-tested without a GPU) is what vbfem_create built
+    plan = pkg.fem_solver.plan_layout(golden_model_of(engine))
+    for k in ("kernel_variant", "nfree", "half_bw", "twist_row", "smem_bytes"):
+        assert plan[k] == engine.info[k], (k, plan, engine.info)
 
 
 def test_forward_matches_reference_golden(engine, golden):

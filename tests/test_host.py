@@ -245,3 +245,32 @@ def test_step2_loss_sharded_over_gloo_ranks(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ERR" in o
+
+
+def test_plan_layout_on_host(pkg, golden_model):
+    """vbfem_plan: the numbering / orientation / front split vbfem_create would choose, computed
+    without a GPU.  Cook 20x10 with the reference's observation set-up: short-side numbering
+    (b = 25 instead of 43), middle block on the observed element, observed node in the bottom front."""
+    plan = pkg.fem_solver.plan_layout(golden_model)
+    assert plan == {"kernel_variant": 2, "nfree": 440, "half_bw": 25, "twist_row": 220, "bottom_cols": 194,
+                    "flipped": 0, "smem_bytes": 109888}
+    # observed node ahead of the observed element: the band order is reversed
+    p2 = pkg.fem_solver.plan_layout(golden_model, node_id=23, ele_id=150)
+    assert p2["kernel_variant"] == 2 and p2["flipped"] == 1
+    assert p2["twist_row"] + 26 + p2["bottom_cols"] == 440 and p2["twist_row"] >= 32 and p2["bottom_cols"] >= 32
+    # observed node inside the observed element's rows / element too close to the end of the band
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=116, ele_id=110)["kernel_variant"] == 0
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 0
+    # supported observed node: no unit vectors, still the front kernel
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=50)["kernel_variant"] == 2
+    # a smaller shared memory does not fit two samples per SM
+    assert pkg.fem_solver.plan_layout(golden_model, smem_per_sm=200000)["kernel_variant"] == 0
+
+
+@pytest.mark.parametrize("nx,ny,variant,b", [(24, 8, 2, 21), (20, 9, 2, 23), (16, 8, 0, 21), (30, 10, 0, 25),
+                                             (80, 40, 0, 85)])
+def test_plan_layout_other_meshes(pkg, nx, ny, variant, b):
+    md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(nx, ny))
+    plan = pkg.fem_solver.plan_layout(md, node_id=(nx + 1) * (ny + 1), ele_id=nx // 2 + 2)
+    assert plan["kernel_variant"] == variant and plan["half_bw"] == b
+    assert plan["nfree"] == 2 * nx * (ny + 1)

@@ -31,7 +31,7 @@ INFO_NAMES = ["nfree", "half_bw", "ndof", "nele", "ncolors", "band_in_smem", "sm
 
 # every symbol include/vbfem.h declares
 SYMBOLS = [
-    "vbfem_create", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_forward", "vbfem_backward",
+    "vbfem_create", "vbfem_plan", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_forward", "vbfem_backward",
     "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
     "vbfem_forward_backward_host", "vbfem_measure_peaks",
 ]
@@ -104,6 +104,8 @@ def load():
     i64 = ctypes.c_int64
     lib.vbfem_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(VbfemMesh), ctypes.c_int]
     lib.vbfem_create.restype = ctypes.c_int
+    lib.vbfem_plan.argtypes = [ctypes.POINTER(VbfemMesh), i64, ctypes.POINTER(i64)]
+    lib.vbfem_plan.restype = ctypes.c_int
     lib.vbfem_destroy.argtypes = [ctypes.c_void_p]
     lib.vbfem_destroy.restype = None
     lib.vbfem_last_error.argtypes = []

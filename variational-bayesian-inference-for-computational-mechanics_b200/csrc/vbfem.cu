@@ -1112,6 +1112,101 @@ static void host_shapef_q4(const double *x, const double *y, int gp, double *nx,
     ny[0] = xtm - xsm; ny[1] = -xtm - xsp; ny[2] = -xtp + xsp; ny[3] = xtp + xsm;
 }
 
+// Internal numbering: try natural / coordinate-sorted / RCM node orders, keep the narrowest band.
+// Returns the half bandwidth over the free dofs; dof2band[global dof] = band row or -1.
+static int choose_numbering(const vbfem_mesh *m, const std::vector<char> &is_free, std::vector<int> &dof2band) {
+    const int nn = m->nnodes;
+    std::vector<std::vector<int>> cands;
+    std::vector<int> nat(nn);
+    std::iota(nat.begin(), nat.end(), 0);
+    cands.push_back(nat);
+    double ext = 0;
+    for (int i = 0; i < 2 * nn; ++i) ext = std::max(ext, std::fabs(m->coord[i]));
+    const double tol = std::max(ext, 1.0) * 1e-9;
+    for (int major = 0; major < 2; ++major) {
+        std::vector<int> o = nat;
+        std::stable_sort(o.begin(), o.end(), [&](int a, int c) {
+            const double pa = m->coord[2 * a + major], pc = m->coord[2 * c + major];
+            if (std::fabs(pa - pc) > tol) return pa < pc;
+            return m->coord[2 * a + 1 - major] < m->coord[2 * c + 1 - major];
+        });
+        cands.push_back(o);
+    }
+    cands.push_back(rcm_order(m));
+    int best_bw = 1 << 30;
+    std::vector<int> tmp;
+    for (size_t c = 0; c < cands.size(); ++c) {
+        const int bw = band_for_order(m, cands[c], is_free, tmp);
+        if (bw < best_bw) {
+            best_bw = bw;
+            dof2band = tmp;
+        }
+    }
+    return best_bw;
+}
+
+// Layout of the on-chip two-front kernel (vbfem_front_kernel.cuh) for a numbering: the band order is
+// oriented so that it ENDS at the observed node (its unit vectors then ride along the bottom front), the
+// observed element's dofs must fit into the P = 26 middle rows [pT, pT+P), the bottom front owns the
+// last nB rows mirrored.  ok == false: the generic kernel serves this mesh / observation set-up.
+struct FrontPlan {
+    bool ok, flip;
+    int pT;
+    int tip[2], er[8];  // band rows (before orientation) of the observed node's / element's dofs
+};
+constexpr int kFrontB = 25, kFrontP = kFrontB + 1, kFrontNT = 128;
+static size_t front_smem_bytes(int n) {
+    return ((size_t)n * kFrontP + 5 * (size_t)n + 32 + 32 + 8 * (kFrontNT / 32)) * sizeof(double);
+}
+static FrontPlan plan_front(const vbfem_mesh *m, const std::vector<int> &dof2band, int n, int b,
+                            size_t smem_per_sm) {
+    constexpr int TB = kFrontB, TP = kFrontP;
+    FrontPlan P{};
+    int elo = 1 << 30, ehi = -1, tlo = 1 << 30, thi = -1;
+    for (int k = 0; k < 2; ++k) {
+        P.tip[k] = dof2band[2 * (m->obs_node - 1) + k];
+        if (P.tip[k] >= 0) {
+            tlo = std::min(tlo, P.tip[k]);
+            thi = std::max(thi, P.tip[k]);
+        }
+    }
+    for (int a = 0; a < 4; ++a)
+        for (int c = 0; c < 2; ++c) {
+            const int g = dof2band[2 * (m->ien[4 * (m->obs_ele - 1) + a] - 1) + c];
+            P.er[2 * a + c] = g;
+            if (g >= 0) {
+                elo = std::min(elo, g);
+                ehi = std::max(ehi, g);
+            }
+        }
+    bool ok = getenv("VBFEM_FORCE_GENERIC") == nullptr && b <= TB && ehi >= 0 && ehi - elo < TP;
+    bool flip = false;
+    if (ok && thi >= 0) {
+        if (thi < elo)
+            flip = true;  // observed node ahead of the observed element: reverse the band order
+        else if (tlo <= ehi)
+            ok = false;   // observed node inside the element's row range: generic kernel
+    }
+    int pT = 0;
+    if (ok) {
+        const int lo = flip ? n - 1 - ehi : elo, hi = flip ? n - 1 - elo : ehi;
+        const int tmin = (thi < 0) ? n : (flip ? n - 1 - thi : tlo);
+        // pT in [hi-P+1, lo], the observed node inside the bottom front, both fronts at least 32 columns
+        const int pmin = std::max(hi - TP + 1, 32), pmax = std::min({lo, n - TP - 32, tmin - TP});
+        if (pmin > pmax) ok = false;
+        // balance: the top front also eliminates the middle block
+        pT = std::min(std::max((int)((n - 2 * TP) * 0.565), pmin), pmax);
+    }
+    // the first two vectors double as the zero extension behind the bottom front's band
+    // ((TP-1)*TP + 1 doubles) and as the Schur hand-over scratch (TP*TP + 3*TP + 4 doubles)
+    if (ok && 2 * n < TP * TP + 3 * TP + 4) ok = false;
+    if (ok && (n % 2 != 0 || (size_t)n * TP >= 32000 || 2 * (front_smem_bytes(n) + 1024) > smem_per_sm)) ok = false;
+    P.ok = ok;
+    P.flip = flip;
+    P.pT = pT;
+    return P;
+}
+
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
@@ -1139,35 +1234,9 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         is_free[g - 1] = 1;
     }
 
-    // ---- internal numbering: try natural / coordinate-sorted / RCM node orders, keep the narrowest band
-    std::vector<std::vector<int>> cands;
-    std::vector<int> nat(nn);
-    std::iota(nat.begin(), nat.end(), 0);
-    cands.push_back(nat);
-    double ext = 0;
-    for (int i = 0; i < 2 * nn; ++i) ext = std::max(ext, std::fabs(m->coord[i]));
-    const double tol = std::max(ext, 1.0) * 1e-9;
-    for (int major = 0; major < 2; ++major) {
-        std::vector<int> o = nat;
-        std::stable_sort(o.begin(), o.end(), [&](int a, int c) {
-            const double pa = m->coord[2 * a + major], pc = m->coord[2 * c + major];
-            if (std::fabs(pa - pc) > tol) return pa < pc;
-            return m->coord[2 * a + 1 - major] < m->coord[2 * c + 1 - major];
-        });
-        cands.push_back(o);
-    }
-    cands.push_back(rcm_order(m));
-    int best = -1, best_bw = 1 << 30;
-    std::vector<int> dof2band, tmp;
-    for (size_t c = 0; c < cands.size(); ++c) {
-        const int bw = band_for_order(m, cands[c], is_free, tmp);
-        if (bw < best_bw) {
-            best_bw = bw;
-            best = (int)c;
-            dof2band = tmp;
-        }
-    }
-    (void)best;
+    // ---- internal numbering (narrowest band over natural / coordinate-sorted / RCM node orders)
+    std::vector<int> dof2band;
+    const int best_bw = choose_numbering(m, is_free, dof2band);
     const int n = m->nfree, b = std::max(best_bw, 1), ldb = b + 2;
 
     // ---- element colouring (no two elements of a colour share a node) and colour-sorted order
@@ -1349,54 +1418,13 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
 
     // ---- on-chip front kernel: band (n x 26 doubles) + five vectors must fit twice per SM
     {
-        // Layout (vbfem_front_kernel.cuh): the band order is oriented so that it ENDS at the observed
-        // node (its unit vectors then ride along the bottom front), the observed element's dofs must fit
-        // into the P = 26 middle rows [pT, pT+P), the bottom front owns the last nB rows mirrored.
-        constexpr int TB = 25, TP = TB + 1, TNT = 128;
-        int tip[2], er[8], elo = 1 << 30, ehi = -1, tlo = 1 << 30, thi = -1;
-        for (int k = 0; k < 2; ++k) {
-            tip[k] = dof2band[2 * (m->obs_node - 1) + k];
-            if (tip[k] >= 0) {
-                tlo = std::min(tlo, tip[k]);
-                thi = std::max(thi, tip[k]);
-            }
-        }
-        for (int a = 0; a < 4; ++a)
-            for (int c = 0; c < 2; ++c) {
-                const int g = dof2band[2 * (m->ien[4 * (m->obs_ele - 1) + a] - 1) + c];
-                er[2 * a + c] = g;
-                if (g >= 0) {
-                    elo = std::min(elo, g);
-                    ehi = std::max(ehi, g);
-                }
-            }
-        bool ok = getenv("VBFEM_FORCE_GENERIC") == nullptr && b <= TB && ehi >= 0 && ehi - elo < TP;
-        bool flip = false;
-        if (ok && thi >= 0) {
-            if (thi < elo)
-                flip = true;  // observed node ahead of the observed element: reverse the band order
-            else if (tlo <= ehi)
-                ok = false;   // observed node inside the element's row range: generic kernel
-        }
+        constexpr int TB = kFrontB, TP = kFrontP, TNT = kFrontNT;
+        const FrontPlan plan = plan_front(m, dof2band, n, b, (size_t)prop.sharedMemPerMultiprocessor);
+        const bool ok = plan.ok, flip = plan.flip;
+        const int pT = plan.pT;
+        const int *tip = plan.tip, *er = plan.er;
         auto ori = [&](int g) { return (g < 0) ? g : (flip ? n - 1 - g : g); };
-        int pT = 0;
-        if (ok) {
-            const int lo = flip ? n - 1 - ehi : elo, hi = flip ? n - 1 - elo : ehi;
-            const int tmin = (thi < 0) ? n : (flip ? n - 1 - thi : tlo);
-            // pT in [hi-P+1, lo], the observed node inside the bottom front, both fronts at least 32 columns
-            const int pmin = std::max(hi - TP + 1, 32), pmax = std::min({lo, n - TP - 32, tmin - TP});
-            if (pmin > pmax) ok = false;
-            // balance: the top front also eliminates the middle block
-            pT = std::min(std::max((int)((n - 2 * TP) * 0.565), pmin), pmax);  // a 3-rhs column costs about 1.3 x a 1-rhs column
-        }
-        const size_t fr_doubles = (size_t)n * TP + 5 * (size_t)n + 32 + 32 + 8 * (TNT / 32);
-        const size_t fr_smem = fr_doubles * sizeof(double);
-        // the first two vectors double as the zero extension behind the bottom front's band
-        // ((TP-1)*TP + 1 doubles) and as the Schur hand-over scratch (TP*TP + 3*TP + 4 doubles)
-        if (ok && 2 * n < TP * TP + 3 * TP + 4) ok = false;
-        if (ok && (n % 2 != 0 || (size_t)n * TP >= 32000 ||
-                   2 * (fr_smem + 1024) > (size_t)prop.sharedMemPerMultiprocessor))
-            ok = false;
+        const size_t fr_smem = front_smem_bytes(n);
         if (ok) {
             const int me = pT + TP, nB = n - me;
             M.b = TB;
@@ -1482,6 +1510,35 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
     guard.p = nullptr;
     *out = h;
+    return 0;
+}
+
+extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out) {
+    if (!m || !out) return fail(-1, "null argument");
+    if (m->nnodes <= 0 || m->nele <= 0 || m->nfree <= 0 || !m->coord || !m->ien || !m->free_dof)
+        return fail(-1, "incomplete mesh description");
+    const int nn = m->nnodes, ndof = 2 * nn;
+    for (int i = 0; i < 4 * m->nele; ++i)
+        if (m->ien[i] < 1 || m->ien[i] > nn) return fail(-1, "IEN entry %d out of range", m->ien[i]);
+    if (m->obs_node < 1 || m->obs_node > nn || m->obs_ele < 1 || m->obs_ele > m->nele)
+        return fail(-1, "observation node/element out of range");
+    std::vector<char> is_free(ndof, 0);
+    for (int i = 0; i < m->nfree; ++i) {
+        const int g = m->free_dof[i];
+        if (g < 1 || g > ndof) return fail(-1, "free_dof entry %d out of range", g);
+        is_free[g - 1] = 1;
+    }
+    std::vector<int> dof2band;
+    const int b = std::max(choose_numbering(m, is_free, dof2band), 1), n = m->nfree;
+    const FrontPlan P = plan_front(m, dof2band, n, b, (size_t)(smem_per_sm > 0 ? smem_per_sm : 233472));
+    out[0] = P.ok ? 2 : 0;
+    out[1] = n;
+    out[2] = b;
+    out[3] = P.ok ? P.pT : 0;
+    out[4] = P.ok ? n - P.pT - kFrontP : 0;
+    out[5] = P.ok && P.flip;
+    out[6] = P.ok ? (int64_t)front_smem_bytes(n) : 0;
+    out[7] = 0;
     return 0;
 }
 

@@ -28,6 +28,39 @@ def _as_c(a, dtype):
     return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_double if dtype == np.float64 else ctypes.c_int32))
 
 
+def mesh_struct(md, theta_mean=(math.log(20.0), 0.0), theta_std=(0.1, 0.015), node_id=231, ele_id=12,
+                nipt_id=(1, 3)):
+    """``struct vbfem_mesh`` (include/vbfem.h) from the reference's ``model_data`` dict.  Returns the
+    ctypes structure and the arrays it points into (keep them alive while the structure is used)."""
+    mi, di = md["mesh_info"], md["dof_info"]
+    keep = []
+    mesh = _lib.VbfemMesh()
+    mesh.nnodes, mesh.nele, mesh.nfree = int(mi["nnodes"]), int(mi["nele"]), int(di["nfree"])
+    a, mesh.coord = _as_c(np.asarray(mi["coord"])[:, 1:3], np.float64); keep.append(a)
+    a, mesh.ien = _as_c(di["IEN"], np.int32); keep.append(a)
+    a, mesh.free_dof = _as_c(di["free_dof"], np.int32); keep.append(a)
+    pf = md["loading"]["Pf"]
+    pf = pf.toarray() if hasattr(pf, "toarray") else np.asarray(pf)
+    a, mesh.pf = _as_c(pf.reshape(-1), np.float64); keep.append(a)
+    mesh.thk = float(md["section"][0]["thk"]) if "section" in md else 10.0
+    mesh.obs_node, mesh.obs_ele = int(node_id), int(ele_id)
+    mesh.obs_gp[0], mesh.obs_gp[1] = int(nipt_id[0]), int(nipt_id[1])
+    for k in range(2):
+        mesh.theta_mean[k] = float(theta_mean[k])
+        mesh.theta_std[k] = float(theta_std[k])
+    return mesh, keep
+
+
+def plan_layout(md, node_id=231, ele_id=12, nipt_id=(1, 3), smem_per_sm=0):
+    """What ``vbfem_create`` would decide for this mesh and observation set-up, computed on the host
+    without a GPU (``vbfem_plan``): kernel variant, order, half bandwidth, front split, orientation."""
+    mesh, keep = mesh_struct(md, node_id=node_id, ele_id=ele_id, nipt_id=nipt_id)
+    out = (ctypes.c_int64 * 8)()
+    _lib.check(_lib.load().vbfem_plan(ctypes.byref(mesh), int(smem_per_sm), out), "vbfem_plan")
+    names = ["kernel_variant", "nfree", "half_bw", "twist_row", "bottom_cols", "flipped", "smem_bytes"]
+    return {k: int(out[i]) for i, k in enumerate(names)}
+
+
 class CookFemEngine:
     """One libvbfem handle (= one GPU).  Not re-entrant."""
 
@@ -46,21 +79,7 @@ class CookFemEngine:
         mi, di = md["mesh_info"], md["dof_info"]
         self.nnodes, self.nele, self.ndof = int(mi["nnodes"]), int(mi["nele"]), int(di["ndof"])
         self.nfree = int(di["nfree"])
-        keep = []
-        mesh = _lib.VbfemMesh()
-        mesh.nnodes, mesh.nele, mesh.nfree = self.nnodes, self.nele, self.nfree
-        a, mesh.coord = _as_c(np.asarray(mi["coord"])[:, 1:3], np.float64); keep.append(a)
-        a, mesh.ien = _as_c(di["IEN"], np.int32); keep.append(a)
-        a, mesh.free_dof = _as_c(di["free_dof"], np.int32); keep.append(a)
-        pf = md["loading"]["Pf"]
-        pf = pf.toarray() if hasattr(pf, "toarray") else np.asarray(pf)
-        a, mesh.pf = _as_c(pf.reshape(-1), np.float64); keep.append(a)
-        mesh.thk = float(md["section"][0]["thk"]) if "section" in md else 10.0
-        mesh.obs_node, mesh.obs_ele = int(node_id), int(ele_id)
-        mesh.obs_gp[0], mesh.obs_gp[1] = int(nipt_id[0]), int(nipt_id[1])
-        for k in range(2):
-            mesh.theta_mean[k] = float(theta_mean[k])
-            mesh.theta_std[k] = float(theta_std[k])
+        mesh, keep = mesh_struct(md, theta_mean, theta_std, node_id, ele_id, nipt_id)
         h = ctypes.c_void_p()
         _lib.check(self.lib.vbfem_create(ctypes.byref(h), ctypes.byref(mesh), self.device_index), "vbfem_create")
         self._h = h
