@@ -65,8 +65,11 @@ enum {
     VBFEM_INFO_CTAS_PER_SM = 7,
     VBFEM_INFO_NUM_SMS = 8,
     VBFEM_INFO_BLOCK_THREADS = 9,
-    VBFEM_INFO_KERNEL_VARIANT = 10, /* 0 = generic per-column kernel, 2 = on-chip two-front kernel */
+    VBFEM_INFO_KERNEL_VARIANT = 10, /* 0 = generic per-column kernel, 2 = on-chip two-front kernel,
+                                       3 = blocked panel kernel (wide bands, factor streamed to HBM) */
     VBFEM_INFO_TWIST_ROW = 11,      /* first middle row of the twisted factorisation */
+    VBFEM_INFO_PANEL_BLOCKS = 12,   /* panel kernel: block half bandwidth (8x8 blocks below the diagonal block) */
+    VBFEM_INFO_PANEL_RING = 13,     /* panel kernel: capacity of the element-matrix ring */
     VBFEM_INFO_COUNT = 16
 };
 
@@ -77,7 +80,7 @@ int vbfem_create(vbfem_t **out, const vbfem_mesh *mesh, int device);
 
 /* The host-side plan vbfem_create would make for this mesh and observation set-up, WITHOUT touching
  * a GPU (unit tests of the numbering / orientation / front split): out[0] = kernel variant (2 = on-chip
- * two-front kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
+ * two-front kernel, 3 = blocked panel kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
  * middle row pT, out[4] = bottom-front columns nB, out[5] = 1 if the band order was reversed so that
  * it ends at the observed node, out[6] = shared memory per CTA in bytes, out[7] reserved.
  * smem_per_sm: shared memory per SM assumed for the fit test (<= 0: 233472, B200). */
@@ -86,13 +89,19 @@ void vbfem_destroy(vbfem_t *h);
 const char *vbfem_last_error(void);
 int vbfem_info(const vbfem_t *h, int64_t *out /* [VBFEM_INFO_COUNT] */);
 
+/* Size every per-sample buffer of the handle (status words, kept Jacobians, ELBO scratch, host staging)
+ * for batches of up to n_samples_max.  Optional outside stream capture (the buffers grow on demand);
+ * REQUIRED before capturing launches in a CUDA graph: a launch that would have to allocate during
+ * capture fails with -6 instead. */
+int vbfem_reserve(vbfem_t *h, int64_t n_samples_max);
+
 /* y,h = fem_fh_fun_loop_rev(x): for each sample theta->(E,nu)
  * (data_generation_2sam_more_loss.py:181-186), assemble
  * (fem_solver_tf.py:229-341, mat_subroutine_tf.py:23-110), solve
  * (fem_solver_tf.py:129-153), observe u at obs_node and the von Mises stress
  * at (obs_ele, obs_gp) (fem_postprocess.py:172-185).  With keep_factor != 0
  * the library also keeps what vbfem_backward needs: the 4x2 Jacobian d(y, h)/dx
- * per sample (front kernel) or the factor and solution (generic kernel). */
+ * per sample, in a buffer owned by the handle (every such call gets a new ticket). */
 int vbfem_forward(vbfem_t *h, int64_t n_samples, const double *x_dev /* [N][2] */,
                   double *y_dev /* [N][2] */, double *h_dev /* [N][2] */,
                   int keep_factor, void *stream);
@@ -103,6 +112,23 @@ int vbfem_forward(vbfem_t *h, int64_t n_samples, const double *x_dev /* [N][2] *
  * the stored Jacobians, or an adjoint solve with the stored factor). */
 int vbfem_backward(vbfem_t *h, int64_t n_samples, const double *gy_dev, const double *gh_dev,
                    double *gx_dev /* [N][2] */, void *stream);
+
+/* Ticket of the Jacobians the handle currently keeps (0: none).  vbfem_backward_ticket applies them only
+ * if `ticket` is still current and fails with -5 otherwise: a differentiable wrapper that took its
+ * ticket right after vbfem_forward(keep_factor=1) can never consume another call's Jacobians. */
+int64_t vbfem_keep_ticket(const vbfem_t *h);
+int vbfem_backward_ticket(vbfem_t *h, int64_t ticket, int64_t n_samples, const double *gy_dev,
+                          const double *gh_dev, double *gx_dev, void *stream);
+
+/* Stateless pair for autograd nodes that own their state (the counterpart of one tf.custom_gradient
+ * closure, main_custom_training.py:191-196 + 252-256): vbfem_forward_jac writes the per-sample
+ * Jacobians [N][4][2] (rows y0, y1, h0, h1; columns x0, x1) into a CALLER-owned buffer,
+ * vbfem_jac_vjp computes gx = J^T (gy, gh) from any such buffer.  Several forward calls may be
+ * outstanding before their backward passes run. */
+int vbfem_forward_jac(vbfem_t *h, int64_t n_samples, const double *x_dev, double *y_dev, double *h_dev,
+                      double *jac_dev /* [N][8] */, void *stream);
+int vbfem_jac_vjp(vbfem_t *h, int64_t n_samples, const double *jac_dev, const double *gy_dev,
+                  const double *gh_dev, double *gx_dev, void *stream);
 
 /* Fused forward + adjoint in one launch (no workspace round trip). */
 int vbfem_forward_backward(vbfem_t *h, int64_t n_samples, const double *x_dev,
@@ -149,12 +175,17 @@ int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t 
 int64_t vbfem_status(vbfem_t *h, int32_t *flags_host /* [N] or NULL */, int64_t n_samples);
 
 /* Host-buffer entry points (what a NumPy/TF caller uses): copy in from host
- * memory, run, copy out, synchronise. */
+ * memory, run on the handle's own stream, copy out, synchronise.  Batches of up to 64
+ * samples -- the one-sample-at-a-time callers, src/postprocess_lib.py:78-103 (Metropolis
+ * log-posterior) -- skip the copies: the kernel works on mapped pinned host memory. */
 int vbfem_forward_host(vbfem_t *h, int64_t n_samples, const double *x_host, double *y_host,
                        double *h_host);
 int vbfem_forward_backward_host(vbfem_t *h, int64_t n_samples, const double *x_host,
                                 const double *gy_host, const double *gh_host, double *y_host,
                                 double *h_host, double *gx_host);
+
+/* Test hook, GPU-free: the host tables of the blocked panel kernel for a mesh (see vbfem.cu). */
+int64_t vbfem_debug_panel_tables(const vbfem_mesh *mesh, int which, void *out, int64_t cap_bytes);
 
 /* Roofline denominators measured on this GPU: dependent-free DFMA loop
  * (TFLOP/s) and a device copy (GB/s, read+write bytes). */

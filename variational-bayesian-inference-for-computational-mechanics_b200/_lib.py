@@ -18,7 +18,8 @@ REPO = os.path.dirname(_HERE)
 INCLUDE = os.path.join(REPO, "include")
 LIB_PATH = os.environ.get("VBFEM_LIB", os.path.join(CSRC, "libvbfem.so"))  # VBFEM_LIB: profiling builds
 SOURCES = ["vbfem.cu"]
-HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", os.path.join(INCLUDE, "vbfem.h")]
+HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", "vbfem_panel.cuh",
+           os.path.join(INCLUDE, "vbfem.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -27,12 +28,13 @@ NVCC_FLAGS = [
 
 INFO_COUNT = 16
 INFO_NAMES = ["nfree", "half_bw", "ndof", "nele", "ncolors", "band_in_smem", "smem_bytes", "ctas_per_sm",
-              "num_sms", "block_threads", "kernel_variant", "twist_row"]
+              "num_sms", "block_threads", "kernel_variant", "twist_row", "panel_blocks", "panel_ring"]
 
 # every symbol include/vbfem.h declares
 SYMBOLS = [
-    "vbfem_create", "vbfem_plan", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_forward", "vbfem_backward",
-    "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
+    "vbfem_create", "vbfem_plan", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_reserve", "vbfem_forward",
+    "vbfem_backward", "vbfem_keep_ticket", "vbfem_backward_ticket", "vbfem_forward_jac", "vbfem_jac_vjp",
+    "vbfem_debug_panel_tables", "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
     "vbfem_forward_backward_host", "vbfem_measure_peaks",
 ]
 
@@ -116,6 +118,18 @@ def load():
     lib.vbfem_forward.restype = ctypes.c_int
     lib.vbfem_backward.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp, c_dp]
     lib.vbfem_backward.restype = ctypes.c_int
+    lib.vbfem_reserve.argtypes = [ctypes.c_void_p, i64]
+    lib.vbfem_reserve.restype = ctypes.c_int
+    lib.vbfem_keep_ticket.argtypes = [ctypes.c_void_p]
+    lib.vbfem_keep_ticket.restype = i64
+    lib.vbfem_backward_ticket.argtypes = [ctypes.c_void_p, i64, i64, c_dp, c_dp, c_dp, c_dp]
+    lib.vbfem_backward_ticket.restype = ctypes.c_int
+    lib.vbfem_forward_jac.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.vbfem_forward_jac.restype = ctypes.c_int
+    lib.vbfem_jac_vjp.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.vbfem_jac_vjp.restype = ctypes.c_int
+    lib.vbfem_debug_panel_tables.argtypes = [ctypes.POINTER(VbfemMesh), ctypes.c_int, c_dp, i64]
+    lib.vbfem_debug_panel_tables.restype = i64
     lib.vbfem_forward_backward.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     lib.vbfem_forward_backward.restype = ctypes.c_int
     lib.vbfem_fields.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]

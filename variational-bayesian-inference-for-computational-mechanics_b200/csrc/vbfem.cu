@@ -23,6 +23,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <queue>
 #include <string>
@@ -73,9 +74,8 @@ struct DevModel {
 };
 
 enum : int {
-    kKeep = 1,    // store factor + solution in the workspace
+    kKeep = 1,    // also store the 4x2 Jacobian d(y, h)/dx per sample (vbfem_forward with keep_factor)
     kAdjoint = 2, // run the adjoint in the same launch
-    kLoad = 4,    // skip assembly/factorisation: load factor + solution from the workspace
     kFields = 8,  // write u / strain / stress / F_int
     kElbo = 16    // x from (mu, sig2, e); upstream gradient from the ELBO data term
 };
@@ -97,6 +97,12 @@ struct Args {
     long long j_begin;
     double gcoef;  // 1 / (sig_e * B * (B*S))
     double *f_out;
+    // generic kernel, Jacobian mode: constant cotangent (gy0, gy1, gh0, gh1) for every sample, gx written
+    // to gx[s * gx_stride + gx_off + k] (one launch per row of the 4x2 Jacobian)
+    int const_g;
+    double gc[4];
+    long long gx_stride;
+    int gx_off;
     long long *timeline;  // profiling builds (-DVBFEM_TIMELINE): clock64 marks per CTA and warp
 };
 
@@ -190,6 +196,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 #endif
 }  // namespace vbfem
 #include "vbfem_front_kernel.cuh"
+#include "vbfem_panel.cuh"
 namespace vbfem {
 
 // ------------------------------------------------------------------------------------------
@@ -384,14 +391,10 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
             x0 = A.x[2 * s];
             x1 = A.x[2 * s + 1];
         }
-        double *ws_s = A.ws ? A.ws + (size_t)((A.mode & (kKeep | kLoad)) ? s : (long long)blockIdx.x) * A.ws_stride
-                            : nullptr;
+        double *ws_s = A.ws ? A.ws + (size_t)blockIdx.x * A.ws_stride : nullptr;  // per-CTA scratch (band in HBM)
         if (A.emat) {
             E = A.emat[2 * s];
             nu = A.emat[2 * s + 1];
-        } else if (A.mode & kLoad) {
-            E = ws_s[band_len];
-            nu = ws_s[band_len + 1];
         } else {
             E = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
             nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
         double *band = M.band_in_smem ? smem : ws_s;
         if (tid == 0) s_flag = 0;
 
-        if (!(A.mode & kLoad)) {
+        {
             // ---------------- zero the band, load the right-hand side
             for (int i = tid; i < band_len; i += NT) band[i] = 0.0;
             __syncthreads();
@@ -599,39 +602,21 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                 staged_sweep<NT, -1>(band, ring, ring_ch, n, b, ldb, vec_u, 0, tid);
             }
             __syncthreads();
-            if (A.mode & kKeep) {  // solution travels in the rhs slot of the stored factor
-                for (int r = tid; r < n; r += NT) band[r * ldb + (b + 1)] = vec_u[r];
-                if (tid == 0) {
-                    ws_s[band_len] = E;
-                    ws_s[band_len + 1] = nu;
-                }
-                if (M.band_in_smem) {
-                    __syncthreads();
-                    for (int i = tid; i < band_len; i += NT) ws_s[i] = band[i];
-                }
-            }
-        } else {
-            // ---------------- reload factor + solution kept by a previous forward launch
-            if (M.band_in_smem)
-                for (int i = tid; i < band_len; i += NT) band[i] = ws_s[i];
-            __syncthreads();
-            for (int r = tid; r < n; r += NT) vec_u[r] = band[r * ldb + (b + 1)];
-            __syncthreads();
         }
 
         // ---------------- (d) observations: y = u(obs node), h = von Mises at (obs ele, obs gps)
-        const bool adj = (A.mode & (kAdjoint | kLoad)) != 0;
+        const bool adj = (A.mode & kAdjoint) != 0;
         if (lane == 0 && warp < 2) {
             double ue[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) ue[a] = (M.obs_lmb[a] >= 0) ? vec_u[M.obs_lmb[a]] : 0.0;
             double *o = obs_s + 12 * warp;
             o[0] = obs_eval(M, mat, ue, M.obs_gp[warp], adj ? o + 1 : nullptr, o + 9, o + 10);
-            if (A.h && !(A.mode & kLoad)) A.h[2 * s + warp] = o[0];
+            if (A.h) A.h[2 * s + warp] = o[0];
         }
         const double f0 = (M.obs_dof[0] >= 0) ? vec_u[M.obs_dof[0]] : 0.0;
         const double f1 = (M.obs_dof[1] >= 0) ? vec_u[M.obs_dof[1]] : 0.0;
-        if (tid == 0 && !(A.mode & kLoad)) {
+        if (tid == 0) {
             if (A.y) {
                 A.y[2 * s] = f0;
                 A.y[2 * s + 1] = f1;
@@ -726,6 +711,11 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                 // d(loss)/d f_j through term2 with the [B, B*S] broadcast (main_custom_training.py:205-214)
                 gy0 = A.gcoef * ((double)A.B * f0 - A.ysum[0]);
                 gy1 = A.gcoef * ((double)A.B * f1 - A.ysum[1]);
+            } else if (A.const_g) {
+                gy0 = A.gc[0];
+                gy1 = A.gc[1];
+                gh0 = A.gc[2];
+                gh1 = A.gc[3];
             } else {
                 gy0 = A.gy[2 * s];
                 gy1 = A.gy[2 * s + 1];
@@ -823,11 +813,12 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                 const double gE = gl * dl_dE + gm * dm_dE;
                 const double gnu = gl * dl_dnu + gm * dm_dnu;
                 // dE/dx0 = std0 * E ; dnu/dx1 = std1 * nu (1 - 2 nu)
-                A.gx[2 * s] = gE * M.theta_std[0] * E;
-                A.gx[2 * s + 1] = gnu * M.theta_std[1] * nu * (1.0 - 2.0 * nu);
+                double *gxo = A.gx + (A.gx_stride ? (size_t)s * A.gx_stride + A.gx_off : (size_t)2 * s);
+                gxo[0] = gE * M.theta_std[0] * E;
+                gxo[1] = gnu * M.theta_std[1] * nu * (1.0 - 2.0 * nu);
             }
         }
-        if (tid == 0 && A.status && !(A.mode & kLoad)) A.status[s] = s_flag;
+        if (tid == 0 && A.status) A.status[s] = s_flag;
         __syncthreads();
     }
 }
@@ -958,6 +949,7 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 typedef void (*kernel_fn)(const DevModel, const Args);
+typedef void (*panel_fn)(const DevModel, const PanelModel, const Args);
 
 struct vbfem_handle {
     int device = 0;
@@ -967,27 +959,32 @@ struct vbfem_handle {
     size_t smem_bytes = 0;
     kernel_fn kern = nullptr;
     kernel_fn kern_front[3] = {nullptr, nullptr, nullptr};  // forward / forward+adjoint / Jacobian
-    // generic kernel configuration (fields mode, meshes the front kernel does not take)
+    // blocked panel kernel (wide bands, factor streamed to HBM)
+    PanelModel PM{};
+    panel_fn kern_panel[3] = {nullptr, nullptr, nullptr};
+    // generic kernel configuration (fields mode, meshes neither fast kernel takes)
     DevModel M_gen{};
     int gen_block = 0, gen_ctas = 0;
     size_t gen_smem_bytes = 0;
-    long long gen_ws_stride = 0, ws_gen_slots = 0;
-    double *ws_gen = nullptr;
+    long long gen_ws_stride = 0;
+    double *ws_gen = nullptr;  // per-CTA band scratch when the band does not fit in shared memory (sized at create)
     std::vector<void *> dev_allocs;
-    // workspace
-    double *ws = nullptr;
-    long long ws_stride = 0, ws_slots = 0;
+    // per-sample buffers: they grow in vbfem_reserve or, outside stream capture, on demand
+    double *jac = nullptr;  // 4x2 Jacobians d(y, h)/dx kept by vbfem_forward(keep_factor=1)
+    long long jac_cap = 0, kept_n = 0;
+    int64_t ticket = 0, kept_ticket = 0;
     int *status = nullptr;
     long long status_cap = 0, last_n = 0;
     // ELBO scratch
     double *elbo_f = nullptr, *elbo_g = nullptr, *elbo_ysum = nullptr;
     long long elbo_cap = 0;
-    // host staging
-    double *pin = nullptr, *stage = nullptr;
+    // host entry points: pinned (mapped) staging, device staging, their own stream
+    double *pin = nullptr, *pin_dev = nullptr, *stage = nullptr;
     long long stage_cap = 0;
+    cudaStream_t host_stream = nullptr;
     int info_colors = 0;
     int n_real = 0;   // order of the system without padding rows
-    int variant = 0;  // 0 = generic per-column kernel, 2 = on-chip front kernel
+    int variant = 0;  // 0 = generic per-column kernel, 2 = on-chip front kernel, 3 = blocked panel kernel
     long long *timeline = nullptr;
 };
 
@@ -1207,6 +1204,199 @@ static FrontPlan plan_front(const vbfem_mesh *m, const std::vector<int> &dof2ban
     return P;
 }
 
+// ------------------------------------------------------------------------------------------
+// Blocked panel kernel (vbfem_panel.cuh): host-side plan.  Everything the kernel indexes by --
+// padded band rows, block rows, the gather table that assembles a fresh block row from the ring of
+// element matrices, the order in which the element matrices are needed, the initial right-hand-side
+// blocks, the update schedule and the shared-memory layout -- is computed here, GPU-free.
+// ------------------------------------------------------------------------------------------
+struct PanelPlan {
+    bool ok = false, flip = false;
+    std::string why;
+    int n = 0, off = 0, npad = 0, NQ = 0, NB = 0, R = 0, nub = 0, nele = 0;
+    int obs_loc[2] = {-1, -1};
+    int kstart[kPanelNW + 1] = {0};
+    int o_win = 0, o_rhs = 0, o_lst = 0, o_ke = 0, smem_bytes = 0, stages = 0;
+    std::vector<int> gptr, eneed, eord, elm;
+    std::vector<unsigned short> gdst, gsrc, ub;  // gsrc: four entries per target
+    std::vector<double> rhs0;
+};
+
+static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2band, int n) {
+    PanelPlan P;
+    auto no = [&](const char *why) {
+        P.ok = false;
+        P.why = why;
+        return P;
+    };
+    const int ne = m->nele;
+    P.n = n;
+    P.nele = ne;
+    if (n < 16) return no("fewer than 16 unknowns");
+    // orientation: the free dofs of the observed node must be the LAST rows of the band (their unit
+    // vectors then live in the last diagonal block)
+    int tip[2], nt = 0, tlo = 1 << 30, thi = -1;
+    for (int k = 0; k < 2; ++k) {
+        tip[k] = dof2band[2 * (m->obs_node - 1) + k];
+        if (tip[k] >= 0) {
+            ++nt;
+            tlo = std::min(tlo, tip[k]);
+            thi = std::max(thi, tip[k]);
+        }
+    }
+    if (nt > 0) {
+        if (tlo == n - nt && thi == n - 1)
+            P.flip = false;
+        else if (tlo == 0 && thi == nt - 1)
+            P.flip = true;
+        else
+            return no("the observed node is not at an end of the band order");
+    }
+    P.off = (8 - n % 8) % 8;
+    P.npad = n + P.off;
+    P.NQ = P.npad / 8;
+    auto prow = [&](int r) { return r < 0 ? -1 : (P.flip ? n - 1 - r : r) + P.off; };
+    for (int k = 0; k < 2; ++k) P.obs_loc[k] = tip[k] >= 0 ? prow(tip[k]) - 8 * (P.NQ - 1) : -1;
+
+    // element rows, block half bandwidth, first / last block row of every element
+    P.elm.assign((size_t)8 * ne, -1);
+    std::vector<int> first(ne, 1 << 30), last(ne, -1);
+    int NB = 1;
+    for (int e = 0; e < ne; ++e) {
+        int lo = 1 << 30, hi = -1;
+        for (int a = 0; a < 4; ++a)
+            for (int c = 0; c < 2; ++c) {
+                const int r = prow(dof2band[2 * (m->ien[4 * e + a] - 1) + c]);
+                P.elm[8 * e + 2 * a + c] = r;
+                if (r >= 0) {
+                    lo = std::min(lo, r);
+                    hi = std::max(hi, r);
+                }
+            }
+        if (hi >= 0) {
+            first[e] = lo / 8;
+            last[e] = hi / 8;
+            NB = std::max(NB, hi / 8 - lo / 8);
+        }
+    }
+    if (NB > kPanelNBMax) return no("band wider than the panel kernel's window");
+    P.NB = NB;
+    const int NB1 = NB + 1;
+
+    // first-use order of the elements, how many of them block row q needs, ring capacity
+    P.eord.resize(ne);
+    std::iota(P.eord.begin(), P.eord.end(), 0);
+    std::stable_sort(P.eord.begin(), P.eord.end(), [&](int a, int c) { return first[a] < first[c]; });
+    std::vector<int> pos(ne);
+    for (int k = 0; k < ne; ++k) pos[P.eord[k]] = k;
+    P.eneed.assign(P.NQ, 0);
+    {
+        int k = 0;
+        for (int q = 0; q < P.NQ; ++q) {
+            while (k < ne && first[P.eord[k]] <= q) ++k;
+            P.eneed[q] = k;
+        }
+    }
+    {
+        std::vector<int> minpos(P.NQ + 1, 1 << 30);  // smallest position among elements still needed at row >= q
+        for (int e = 0; e < ne; ++e)
+            if (last[e] >= 0) minpos[last[e]] = std::min(minpos[last[e]], pos[e]);
+        for (int q = P.NQ - 1; q >= 0; --q) minpos[q] = std::min(minpos[q], minpos[q + 1]);
+        const int cap = (ne + kPanelEB - 1) / kPanelEB * kPanelEB;
+        int R = kPanelEB;
+        for (int q = 0; q < P.NQ; ++q) {
+            const int computed = std::min((P.eneed[q] + kPanelEB - 1) / kPanelEB * kPanelEB, cap);
+            if (minpos[q] < computed) R = std::max(R, computed - minpos[q]);
+        }
+        P.R = R;
+    }
+    if ((size_t)P.R * 36 + 2 > 65535) return no("element ring too large for 16-bit gather indices");
+    const unsigned short ZERO = (unsigned short)(P.R * 36), ONE = (unsigned short)(P.R * 36 + 1);
+
+    // gather table: target (block row, d * 64 + g * 8 + c) <- element-ring entries
+    struct Tgt {
+        int n = 0;
+        unsigned short s[4];
+    };
+    std::vector<std::map<int, Tgt>> rows(P.NQ);
+    for (int r = 0; r < P.off; ++r) {  // leading pad rows: identity
+        Tgt &t = rows[0][r * 8 + r];
+        t.n = 1;
+        t.s[0] = ONE;
+    }
+    for (int e = 0; e < ne; ++e) {
+        const int slot = pos[e] % P.R;
+        for (int a = 0; a < 8; ++a)
+            for (int q = 0; q <= a; ++q) {
+                const int ra = P.elm[8 * e + a], rq = P.elm[8 * e + q];
+                if (ra < 0 || rq < 0) continue;
+                const int rr = std::max(ra, rq), cc = std::min(ra, rq);
+                const int d = rr / 8 - cc / 8;
+                Tgt &t = rows[rr / 8][d * 64 + (rr % 8) * 8 + cc % 8];
+                if (t.n >= 4) return no("more than four elements share a matrix entry");
+                t.s[t.n++] = (unsigned short)(slot * 36 + tri(a, q));
+            }
+    }
+    P.gptr.assign(P.NQ + 1, 0);
+    for (int q = 0; q < P.NQ; ++q) {
+        for (auto &kv : rows[q]) {
+            P.gdst.push_back((unsigned short)kv.first);
+            for (int i = 0; i < 4; ++i) P.gsrc.push_back(i < kv.second.n ? kv.second.s[i] : ZERO);
+        }
+        P.gptr[q + 1] = (int)P.gdst.size();
+    }
+
+    // initial right-hand-side blocks [q][a][c]: row 0 the load vector, rows 1..6 the strain functionals
+    // (exx, eyy, gxy) of the two observed Gauss points (src/mat_subroutine_tf.py:112-145 as vectors)
+    P.rhs0.assign((size_t)P.NQ * 64, 0.0);
+    for (int i = 0; i < n; ++i) {
+        const int r = prow(dof2band[m->free_dof[i] - 1]);
+        P.rhs0[(size_t)(r / 8) * 64 + r % 8] = m->pf[i];
+    }
+    {
+        double ox[4], oy[4];
+        int orow[8];
+        for (int a = 0; a < 4; ++a) {
+            const int nd = m->ien[4 * (m->obs_ele - 1) + a] - 1;
+            ox[a] = m->coord[2 * nd];
+            oy[a] = m->coord[2 * nd + 1];
+            for (int c = 0; c < 2; ++c) orow[2 * a + c] = prow(dof2band[2 * nd + c]);
+        }
+        for (int g = 0; g < 2; ++g) {
+            double nx[4], ny[4];
+            host_shapef_q4(ox, oy, m->obs_gp[g] - 1, nx, ny);
+            auto add = [&](int row, int r, double v) {
+                if (r >= 0) P.rhs0[(size_t)(r / 8) * 64 + row * 8 + r % 8] += v;
+            };
+            for (int a = 0; a < 4; ++a) {
+                add(1 + 3 * g, orow[2 * a], nx[a]);      // exx = sum dN/dx ux
+                add(2 + 3 * g, orow[2 * a + 1], ny[a]);  // eyy = sum dN/dy uy
+                add(3 + 3 * g, orow[2 * a + 1], nx[a]);  // gxy = sum dN/dx uy + dN/dy ux
+                add(3 + 3 * g, orow[2 * a], ny[a]);
+            }
+        }
+    }
+
+    // trailing-update schedule: blocks (I, J), 1 <= J <= I <= NB, then the right-hand-side row I = NB+1
+    for (int I = 1; I <= NB + 1; ++I)
+        for (int J = 1; J <= std::min(I, NB); ++J) P.ub.push_back((unsigned short)((I << 8) | J));
+    P.nub = (int)P.ub.size();
+    for (int w = 0; w <= kPanelNW; ++w) P.kstart[w] = (int)((long long)P.nub * w / kPanelNW);
+
+    // shared-memory layout
+    const int nwin = NB1 * (NB1 + 1) / 2, LPBb = (NB + 2) * 512;
+    P.o_win = (int)((sizeof(PanelSmem) + 15) & ~(size_t)15);
+    P.o_rhs = P.o_win + nwin * 512;
+    P.o_lst = P.o_rhs + NB1 * 512;
+    P.o_ke = P.o_lst + 2 * LPBb;
+    const int ke_bytes = std::max((P.R * 36 + 2) * 8, (NB1 + kPanelNW) * 512);
+    P.smem_bytes = P.o_ke + ((ke_bytes + 15) & ~15);
+    P.stages = std::min(kPanelStagesMax, (nwin + NB1) * 512 / LPBb);
+    if (P.stages < 1) return no("window too small for the reverse pass");
+    P.ok = true;
+    return P;
+}
+
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
@@ -1238,6 +1428,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     std::vector<int> dof2band;
     const int best_bw = choose_numbering(m, is_free, dof2band);
     const int n = m->nfree, b = std::max(best_bw, 1), ldb = b + 2;
+    if (n > 32767) return fail(-3, "system too large for 16-bit band rows (n = %d)", n);
 
     // ---- element colouring (no two elements of a colour share a node) and colour-sorted order
     std::vector<int> color(ne, -1);
@@ -1333,10 +1524,6 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     std::vector<double> coord(m->coord, m->coord + 2 * nn), pf(n, 0.0);
     std::vector<int> ien(4 * ne), lmg(8 * ne), band2dof(n);
     std::vector<short> lmb(8 * ne);
-    if (n > 32767) {
-        delete h;
-        return fail(-3, "system too large for 16-bit band rows (n = %d)", n);
-    }
     for (int e = 0; e < ne; ++e)
         for (int a = 0; a < 4; ++a) {
             const int nd = m->ien[4 * e + a] - 1;
@@ -1408,19 +1595,22 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
         if (rc) {
             return rc;
         }
-        h->ws_stride = (long long)band_doubles + 8;
-        h->gen_ws_stride = h->ws_stride;
+        h->gen_ws_stride = (long long)band_doubles + 8;
         h->gen_block = h->block;
         h->gen_ctas = h->ctas_per_sm;
         h->gen_smem_bytes = h->smem_bytes;
         h->M_gen = h->M;
     }
+    CU(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
+    h->info_colors = ncolors;
+    const bool force_panel = getenv("VBFEM_FORCE_PANEL") != nullptr;
 
     // ---- on-chip front kernel: band (n x 26 doubles) + five vectors must fit twice per SM
     {
         constexpr int TB = kFrontB, TP = kFrontP, TNT = kFrontNT;
         const FrontPlan plan = plan_front(m, dof2band, n, b, (size_t)prop.sharedMemPerMultiprocessor);
-        const bool ok = plan.ok, flip = plan.flip;
+        const bool ok = plan.ok && !force_panel, flip = plan.flip;
         const int pT = plan.pT;
         const int *tip = plan.tip, *er = plan.er;
         auto ori = [&](int g) { return (g < 0) ? g : (flip ? n - 1 - g : g); };
@@ -1496,18 +1686,91 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             h->smem_bytes = fr_smem;
             h->variant = 2;
             h->n_real = n;
-            h->ws_stride = 8;  // the 4x2 Jacobian d(y, h)/dx per sample
-            h->info_colors = ncolors;
-            CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
             guard.p = nullptr;
             *out = h;
             return 0;
         }
     }
 
-    // ---- no front kernel for this mesh / observation set-up: the generic kernel serves every mode
-    h->info_colors = ncolors;
-    CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
+    // ---- blocked panel kernel: wide bands (factor streamed to HBM), band order ending at the observed node
+    if (getenv("VBFEM_FORCE_GENERIC") == nullptr) {
+        PanelPlan P = plan_panel(m, dof2band, n);
+        if (P.ok) {
+            PanelModel &Q = h->PM;
+            Q.n = P.n;
+            Q.off = P.off;
+            Q.npad = P.npad;
+            Q.NQ = P.NQ;
+            Q.NB = P.NB;
+            Q.R = P.R;
+            Q.nub = P.nub;
+            Q.obs_loc[0] = P.obs_loc[0];
+            Q.obs_loc[1] = P.obs_loc[1];
+            Q.o_win = P.o_win;
+            Q.o_rhs = P.o_rhs;
+            Q.o_lst = P.o_lst;
+            Q.o_ke = P.o_ke;
+            Q.smem_bytes = P.smem_bytes;
+            Q.stages = P.stages;
+            for (int w = 0; w <= kPanelNW; ++w) Q.kstart[w] = P.kstart[w];
+            for (size_t i = 0; i < P.ub.size(); ++i) Q.ub[i] = P.ub[i];
+            const bool dfma = getenv("VBFEM_PANEL_DFMA") != nullptr;  // the DMMA-vs-DFMA comparison
+            panel_fn ks[3] = {dfma ? fem_panel_kernel<0, false> : fem_panel_kernel<0, true>,
+                              dfma ? fem_panel_kernel<1, false> : fem_panel_kernel<1, true>,
+                              dfma ? fem_panel_kernel<2, false> : fem_panel_kernel<2, true>};
+            int nbmin = 1 << 30;
+            bool fits = true;
+            for (int q = 0; q < 3 && fits; ++q) {
+                cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
+                int nb = 0;
+                if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], kPanelNT, P.smem_bytes);
+                if (e1 != cudaSuccess || nb < 1) {
+                    fits = false;
+                    cudaGetLastError();
+                }
+                nbmin = std::min(nbmin, nb);
+                h->kern_panel[q] = ks[q];
+            }
+            if (fits) {
+                int rc2 = 0;
+                const ushort4 *gs4 = nullptr;
+                {
+                    std::vector<ushort4> g4(P.gdst.size());
+                    for (size_t i = 0; i < g4.size(); ++i)
+                        g4[i] = make_ushort4(P.gsrc[4 * i], P.gsrc[4 * i + 1], P.gsrc[4 * i + 2], P.gsrc[4 * i + 3]);
+                    rc2 |= upload(h, g4, &gs4);
+                }
+                Q.gsrc = gs4;
+                rc2 |= upload(h, P.gptr, &Q.gptr);
+                rc2 |= upload(h, P.gdst, &Q.gdst);
+                rc2 |= upload(h, P.eneed, &Q.eneed);
+                rc2 |= upload(h, P.eord, &Q.eord);
+                rc2 |= upload(h, P.rhs0, &Q.rhs0);
+                rc2 |= upload(h, P.elm, &Q.elm);
+                if (rc2) return -2;
+                h->block = kPanelNT;
+                h->ctas_per_sm = std::min(nbmin, 2);
+                h->smem_bytes = (size_t)P.smem_bytes;
+                const long long grid = (long long)h->num_sms * h->ctas_per_sm;
+                Q.lws_stride = (long long)P.NQ * (P.NB + 2) * 64;
+                Q.xws_stride = 5LL * P.npad;
+                void *pl = nullptr, *px = nullptr;
+                CU(cudaMalloc(&pl, (size_t)grid * Q.lws_stride * sizeof(double)));
+                h->dev_allocs.push_back(pl);
+                CU(cudaMalloc(&px, (size_t)grid * Q.xws_stride * sizeof(double)));
+                h->dev_allocs.push_back(px);
+                Q.lws = (double *)pl;
+                Q.xws = (double *)px;
+                h->variant = 3;
+                h->n_real = n;
+                guard.p = nullptr;
+                *out = h;
+                return 0;
+            }
+        }
+    }
+
+    // ---- neither fast kernel takes this mesh / observation set-up: the generic kernel serves every mode
     guard.p = nullptr;
     *out = h;
     return 0;
@@ -1530,8 +1793,14 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
     }
     std::vector<int> dof2band;
     const int b = std::max(choose_numbering(m, is_free, dof2band), 1), n = m->nfree;
+    if (n > 32767) return fail(-3, "system too large for 16-bit band rows (n = %d)", n);
     const FrontPlan P = plan_front(m, dof2band, n, b, (size_t)(smem_per_sm > 0 ? smem_per_sm : 233472));
-    out[0] = P.ok ? 2 : 0;
+    int variant = P.ok ? 2 : 0;
+    if (!P.ok && getenv("VBFEM_FORCE_GENERIC") == nullptr && m->pf) {
+        const PanelPlan Q = plan_panel(m, dof2band, n);
+        if (Q.ok) variant = 3;
+    }
+    out[0] = variant;
     out[1] = n;
     out[2] = b;
     out[3] = P.ok ? P.pT : 0;
@@ -1542,11 +1811,50 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
     return 0;
 }
 
+// The panel kernel's host tables for a mesh, GPU-free (tests/panel_emulator.py replays the kernel's
+// index logic on them).  which: 0 header (int32: ok, n, off, npad, NQ, NB, R, nub, obs_loc[2], flip,
+// entries, smem_bytes, stages, nele, EB), 1 gptr, 2 gdst (u16), 3 gsrc (u16 x 4), 4 eneed, 5 eord,
+// 6 rhs0 (f64), 7 elm, 8 ub (u16), 9 kstart.  Returns the byte size of the table (copied when it fits).
+extern "C" int64_t vbfem_debug_panel_tables(const vbfem_mesh *m, int which, void *out, int64_t cap_bytes) {
+    if (!m) return fail(-1, "null argument");
+    const int nn = m->nnodes, ndof = 2 * nn;
+    std::vector<char> is_free(ndof, 0);
+    for (int i = 0; i < m->nfree; ++i) is_free[m->free_dof[i] - 1] = 1;
+    std::vector<int> dof2band;
+    choose_numbering(m, is_free, dof2band);
+    const PanelPlan P = plan_panel(m, dof2band, m->nfree);
+    std::vector<int> hdr = {P.ok, P.n, P.off, P.npad, P.NQ, P.NB, P.R, P.nub, P.obs_loc[0], P.obs_loc[1],
+                            P.flip, (int)P.gdst.size(), P.smem_bytes, P.stages, P.nele, kPanelEB};
+    std::vector<int> ks(P.kstart, P.kstart + kPanelNW + 1);
+    const void *src = nullptr;
+    int64_t bytes = 0;
+    auto pick = [&](const void *p, size_t b) {
+        src = p;
+        bytes = (int64_t)b;
+    };
+    switch (which) {
+        case 0: pick(hdr.data(), hdr.size() * 4); break;
+        case 1: pick(P.gptr.data(), P.gptr.size() * 4); break;
+        case 2: pick(P.gdst.data(), P.gdst.size() * 2); break;
+        case 3: pick(P.gsrc.data(), P.gsrc.size() * 2); break;
+        case 4: pick(P.eneed.data(), P.eneed.size() * 4); break;
+        case 5: pick(P.eord.data(), P.eord.size() * 4); break;
+        case 6: pick(P.rhs0.data(), P.rhs0.size() * 8); break;
+        case 7: pick(P.elm.data(), P.elm.size() * 4); break;
+        case 8: pick(P.ub.data(), P.ub.size() * 2); break;
+        case 9: pick(ks.data(), ks.size() * 4); break;
+        default: return fail(-1, "unknown table %d", which);
+    }
+    if (out && bytes <= cap_bytes && bytes > 0) memcpy(out, src, (size_t)bytes);
+    return bytes;
+}
+
 extern "C" void vbfem_destroy(vbfem_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
     for (void *p : h->dev_allocs) cudaFree(p);
-    cudaFree(h->ws);
+    cudaFree(h->jac);
     cudaFree(h->ws_gen);
     cudaFree(h->status);
     cudaFree(h->elbo_f);
@@ -1554,94 +1862,140 @@ extern "C" void vbfem_destroy(vbfem_t *h) {
     cudaFree(h->elbo_ysum);
     cudaFree(h->stage);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
 }
 
 extern "C" int vbfem_info(const vbfem_t *h, int64_t *out) {
     if (!h || !out) return fail(-1, "null argument");
     for (int i = 0; i < VBFEM_INFO_COUNT; ++i) out[i] = 0;
-    out[VBFEM_INFO_NFREE] = h->variant ? h->n_real : h->M.n;
-    out[VBFEM_INFO_HALF_BW] = h->M.b;
+    out[VBFEM_INFO_NFREE] = h->variant == 2 ? h->n_real : h->M_gen.n;
+    out[VBFEM_INFO_HALF_BW] = h->M_gen.b;
     out[VBFEM_INFO_NDOF] = h->M.ndof;
     out[VBFEM_INFO_NELE] = h->M.nele;
     out[VBFEM_INFO_NCOLORS] = h->M.ncolors;
-    out[VBFEM_INFO_BAND_IN_SMEM] = h->M.band_in_smem;
+    out[VBFEM_INFO_BAND_IN_SMEM] = h->variant == 3 ? 0 : h->M.band_in_smem;
     out[VBFEM_INFO_SMEM_BYTES] = (int64_t)h->smem_bytes;
     out[VBFEM_INFO_CTAS_PER_SM] = h->ctas_per_sm;
     out[VBFEM_INFO_NUM_SMS] = h->num_sms;
     out[VBFEM_INFO_BLOCK_THREADS] = h->block;
     out[VBFEM_INFO_KERNEL_VARIANT] = h->variant;
-    out[VBFEM_INFO_TWIST_ROW] = h->variant ? h->M.pT : 0;
+    out[VBFEM_INFO_TWIST_ROW] = h->variant == 2 ? h->M.pT : 0;
+    out[VBFEM_INFO_PANEL_BLOCKS] = h->variant == 3 ? h->PM.NB : 0;
+    out[VBFEM_INFO_PANEL_RING] = h->variant == 3 ? h->PM.R : 0;
     return 0;
 }
 
-static int ensure_ws(vbfem_handle *h, double **ws, long long *have, long long stride, long long slots) {
-    if (slots <= *have) return 0;
+// Per-sample buffers grow on demand, but never during stream capture (cudaMalloc is illegal there):
+// vbfem_reserve sizes them up front.
+static int ensure_buf(vbfem_handle *h, void **p, long long *cap, long long need, size_t elem, void *stream,
+                      const char *what) {
+    if (need <= *cap) return 0;
+    cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+    if (stream && cudaStreamIsCapturing((cudaStream_t)stream, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone)
+        return fail(-6, "%s buffer must grow to %lld entries during stream capture: call vbfem_reserve first", what, need);
+    CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
-    cudaFree(*ws);
-    *ws = nullptr;
-    *have = 0;
-    CU(cudaMalloc(ws, (size_t)slots * stride * sizeof(double)));
-    *have = slots;
-    (void)h;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(p, (size_t)need * elem));
+    *cap = need;
     return 0;
 }
-static int ensure_status(vbfem_handle *h, long long n) {
-    if (n <= h->status_cap) return 0;
+static int ensure_elbo(vbfem_handle *h, long long nloc, void *stream) {
+    if (nloc <= h->elbo_cap) return 0;
+    long long c1 = h->elbo_cap, c2 = h->elbo_cap;
+    int rc = ensure_buf(h, (void **)&h->elbo_f, &c1, nloc, 2 * sizeof(double), stream, "ELBO");
+    if (!rc) rc = ensure_buf(h, (void **)&h->elbo_g, &c2, nloc, 2 * sizeof(double), stream, "ELBO");
+    h->elbo_cap = rc ? 0 : nloc;
+    return rc;
+}
+static int ensure_stage(vbfem_handle *h, long long n) {
+    if (n <= h->stage_cap) return 0;
+    CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
-    cudaFree(h->status);
-    h->status = nullptr;
-    h->status_cap = 0;
-    CU(cudaMalloc(&h->status, (size_t)n * sizeof(int)));
-    h->status_cap = n;
+    cudaFree(h->stage);
+    if (h->pin) cudaFreeHost(h->pin);
+    h->stage = h->pin = h->pin_dev = nullptr;
+    h->stage_cap = 0;
+    CU(cudaMalloc(&h->stage, (size_t)n * 12 * sizeof(double)));
+    CU(cudaHostAlloc(&h->pin, (size_t)n * 12 * sizeof(double), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **)&h->pin_dev, h->pin, 0));
+    h->stage_cap = n;
     return 0;
+}
+static int ensure_ws_gen(vbfem_handle *h, void *stream) {
+    if (h->M_gen.band_in_smem || h->ws_gen) return 0;
+    long long cap = 0;
+    return ensure_buf(h, (void **)&h->ws_gen, &cap, (long long)h->num_sms * h->gen_ctas * h->gen_ws_stride,
+                      sizeof(double), stream, "band scratch");
+}
+
+extern "C" int vbfem_reserve(vbfem_t *h, int64_t n_samples_max) {
+    if (!h || n_samples_max < 0) return fail(-1, "bad argument");
+    const long long n = std::max<long long>(n_samples_max, 1);
+    int rc = ensure_buf(h, (void **)&h->status, &h->status_cap, n, sizeof(int), nullptr, "status");
+    if (!rc) rc = ensure_buf(h, (void **)&h->jac, &h->jac_cap, n, 8 * sizeof(double), nullptr, "Jacobian");
+    if (!rc) rc = ensure_elbo(h, n, nullptr);
+    if (!rc) rc = ensure_stage(h, n);
+    if (!rc && h->variant == 0) rc = ensure_ws_gen(h, nullptr);
+    return rc;
 }
 
 static int launch(vbfem_handle *h, Args &a, void *stream) {
     if (a.N <= 0) return 0;
     CU(cudaSetDevice(h->device));
-    const bool front = h->variant == 2 && !(a.mode & kFields);
-    if (!(a.mode & kLoad)) {
-        int rc = ensure_status(h, a.N);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_buf(h, (void **)&h->status, &h->status_cap, a.N, sizeof(int), stream, "status");
+    if (rc) return rc;
+    a.status = h->status;
+    h->last_n = a.N;
+    const bool fields = (a.mode & kFields) != 0;
+    if ((a.mode & kKeep) && !a.ws) {  // Jacobians into the handle's own buffer (vbfem_forward with keep_factor)
+        rc = ensure_buf(h, (void **)&h->jac, &h->jac_cap, a.N, 8 * sizeof(double), stream, "Jacobian");
         if (rc) return rc;
-        a.status = h->status;
-        h->last_n = a.N;
+        a.ws = h->jac;
     }
-    if (front) {
+    if (a.mode & kKeep) a.ws_stride = 8;
+    const int mode = (a.mode & kKeep) ? 2 : ((a.mode & kAdjoint) ? 1 : 0);
+    if (h->variant == 2 && !fields) {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);
-        if (a.mode & (kKeep | kLoad)) {
-            int rc = ensure_ws(h, &h->ws, &h->ws_slots, h->ws_stride, std::max(a.N, h->ws_slots));
-            if (rc) return rc;
-            a.ws = h->ws;
-            a.ws_stride = h->ws_stride;
-        }
-        if (a.mode & kLoad) {  // backward: gx = J^T (gy, gh) with the Jacobians a forward(keep) left behind
-            const int nt = 256;
-            jac_apply_kernel<<<(unsigned)((a.N + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
-                a.N, h->ws, h->ws_stride, a.gy, a.gh, a.gx);
-        } else {
-            const int mode = (a.mode & kKeep) ? 2 : ((a.mode & kAdjoint) ? 1 : 0);
 #ifdef VBFEM_TIMELINE
-            if (!h->timeline) {
-                CU(cudaMalloc(&h->timeline, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long)));
-            }
-            CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long),
-                               (cudaStream_t)stream));
-            a.timeline = h->timeline;
-#endif
-            h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, (cudaStream_t)stream>>>(h->M, a);
+        if (!h->timeline) {
+            CU(cudaMalloc(&h->timeline, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long)));
         }
+        CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long), st));
+        a.timeline = h->timeline;
+#endif
+        h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M, a);
+    } else if (h->variant == 3 && !fields) {
+        const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);
+        h->kern_panel[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->PM, a);
     } else {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->gen_ctas);
-        const bool per_sample_ws = (a.mode & (kKeep | kLoad)) != 0;
-        if (per_sample_ws || !h->M_gen.band_in_smem) {
-            int rc = ensure_ws(h, &h->ws_gen, &h->ws_gen_slots, h->gen_ws_stride,
-                               per_sample_ws ? std::max(a.N, h->ws_gen_slots) : std::max(grid, h->ws_gen_slots));
-            if (rc) return rc;
-            a.ws = h->ws_gen;
-            a.ws_stride = h->gen_ws_stride;
+        rc = ensure_ws_gen(h, stream);
+        if (rc) return rc;
+        a.ws_stride = h->gen_ws_stride;
+        double *jac = a.ws;
+        a.ws = h->ws_gen;
+        if (a.mode & kKeep) {
+            // Jacobian mode through the generic kernel: one fused forward+adjoint launch per row of
+            // d(y0, y1, h0, h1)/dx with a unit cotangent (the rarely used fallback; four factorisations)
+            for (int row = 0; row < 4; ++row) {
+                Args b = a;
+                b.mode = (a.mode & ~kKeep) | kAdjoint;
+                b.const_g = 1;
+                for (int k = 0; k < 4; ++k) b.gc[k] = (k == row) ? 1.0 : 0.0;
+                b.gx = jac;
+                b.gx_stride = 8;
+                b.gx_off = 2 * row;
+                if (row > 0) b.y = b.h = b.f_out = nullptr;
+                h->kern<<<(unsigned)grid, h->gen_block, h->gen_smem_bytes, st>>>(h->M_gen, b);
+            }
+        } else {
+            h->kern<<<(unsigned)grid, h->gen_block, h->gen_smem_bytes, st>>>(h->M_gen, a);
         }
-        h->kern<<<(unsigned)grid, h->gen_block, h->gen_smem_bytes, (cudaStream_t)stream>>>(h->M_gen, a);
     }
     CU(cudaGetLastError());
     return 0;
@@ -1655,20 +2009,54 @@ extern "C" int vbfem_forward(vbfem_t *h, int64_t N, const double *x, double *y, 
     a.x = x;
     a.y = y;
     a.h = hh;
-    return launch(h, a, stream);
+    int rc = launch(h, a, stream);
+    if (!rc && keep) {
+        h->kept_n = N;
+        h->kept_ticket = ++h->ticket;
+    }
+    return rc;
+}
+
+extern "C" int64_t vbfem_keep_ticket(const vbfem_t *h) { return h ? h->kept_ticket : 0; }
+
+extern "C" int vbfem_jac_vjp(vbfem_t *h, int64_t N, const double *jac, const double *gy, const double *gh,
+                             double *gx, void *stream) {
+    if (!h || (N > 0 && (!jac || !gy || !gh || !gx))) return fail(-1, "null argument");
+    if (N <= 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const int nt = 256;
+    jac_apply_kernel<<<(unsigned)((N + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(N, jac, 8, gy, gh, gx);
+    CU(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int vbfem_backward(vbfem_t *h, int64_t N, const double *gy, const double *gh, double *gx, void *stream) {
     if (!h || (N > 0 && (!gy || !gh || !gx))) return fail(-1, "null argument");
-    if (N > (h->variant == 2 ? h->ws_slots : h->ws_gen_slots) || N > h->last_n)
-        return fail(-5, "vbfem_backward: no stored factor for %lld samples (call vbfem_forward with keep_factor=1)",
-                    (long long)N);
+    if (h->kept_n <= 0 || N != h->kept_n)
+        return fail(-5, "vbfem_backward: %lld samples requested, the last vbfem_forward(keep_factor=1) kept %lld",
+                    (long long)N, (long long)h->kept_n);
+    return vbfem_jac_vjp(h, N, h->jac, gy, gh, gx, stream);
+}
+
+extern "C" int vbfem_backward_ticket(vbfem_t *h, int64_t ticket, int64_t N, const double *gy, const double *gh,
+                                     double *gx, void *stream) {
+    if (!h) return fail(-1, "null argument");
+    if (ticket <= 0 || ticket != h->kept_ticket)
+        return fail(-5, "vbfem_backward: stale ticket %lld (the handle now keeps the Jacobians of ticket %lld)",
+                    (long long)ticket, (long long)h->kept_ticket);
+    return vbfem_backward(h, N, gy, gh, gx, stream);
+}
+
+extern "C" int vbfem_forward_jac(vbfem_t *h, int64_t N, const double *x, double *y, double *hh, double *jac,
+                                 void *stream) {
+    if (!h || (N > 0 && (!x || !jac))) return fail(-1, "null argument");
     Args a{};
     a.N = N;
-    a.mode = kLoad;
-    a.gy = gy;
-    a.gh = gh;
-    a.gx = gx;
+    a.mode = kKeep;
+    a.x = x;
+    a.y = y;
+    a.h = hh;
+    a.ws = jac;
     return launch(h, a, stream);
 }
 
@@ -1710,16 +2098,8 @@ extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
         return fail(-1, "bad ELBO sample range");
     CU(cudaSetDevice(h->device));
     const long long nloc = j_end - j_begin;
-    if (nloc > h->elbo_cap) {
-        CU(cudaDeviceSynchronize());
-        cudaFree(h->elbo_f);
-        cudaFree(h->elbo_g);
-        h->elbo_f = h->elbo_g = nullptr;
-        h->elbo_cap = 0;
-        CU(cudaMalloc(&h->elbo_f, (size_t)std::max<long long>(nloc, 1) * 2 * sizeof(double)));
-        CU(cudaMalloc(&h->elbo_g, (size_t)std::max<long long>(nloc, 1) * 2 * sizeof(double)));
-        h->elbo_cap = nloc;
-    }
+    int rc = ensure_elbo(h, std::max<long long>(nloc, 1), stream);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     ysum_kernel<<<1, 32, 0, st>>>(B, ybatch, h->elbo_ysum);
     Args a{};
@@ -1735,7 +2115,7 @@ extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
     a.gcoef = 1.0 / (sig_e * (double)B * ((double)B * (double)S));
     a.f_out = f_out ? f_out : h->elbo_f;
     a.gx = h->elbo_g;
-    int rc = launch(h, a, stream);
+    rc = launch(h, a, stream);
     if (rc) return rc;
     const int nblk = 1 + (2 * B + 255) / 256;
     elbo_reduce_kernel<<<nblk, 256, 0, st>>>(B, S, j_begin, j_end, a.f_out, h->elbo_g, e, sig2, sums, gmu, gsig2);
@@ -1750,16 +2130,8 @@ extern "C" int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
         return fail(-1, "bad ELBO sample range");
     CU(cudaSetDevice(h->device));
     const long long nloc = j_end - j_begin;
-    if (nloc > h->elbo_cap) {
-        CU(cudaDeviceSynchronize());
-        cudaFree(h->elbo_f);
-        cudaFree(h->elbo_g);
-        h->elbo_f = h->elbo_g = nullptr;
-        h->elbo_cap = 0;
-        CU(cudaMalloc(&h->elbo_f, (size_t)std::max<long long>(nloc, 1) * 2 * sizeof(double)));
-        CU(cudaMalloc(&h->elbo_g, (size_t)std::max<long long>(nloc, 1) * 2 * sizeof(double)));
-        h->elbo_cap = nloc;
-    }
+    int rc = ensure_elbo(h, std::max<long long>(nloc, 1), stream);
+    if (rc) return rc;
     Args a{};
     a.N = nloc;
     a.mode = kElbo;  // forward only: the theta nets are frozen in step 2 (main_custom_training.py:305)
@@ -1770,7 +2142,7 @@ extern "C" int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
     a.S = S;
     a.j_begin = j_begin;
     a.h = h_out ? h_out : h->elbo_g;
-    int rc = launch(h, a, stream);
+    rc = launch(h, a, stream);
     if (rc) return rc;
     hsum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(nloc, a.h, sums);
     CU(cudaGetLastError());
@@ -1793,18 +2165,10 @@ extern "C" int64_t vbfem_status(vbfem_t *h, int32_t *flags_host, int64_t N) {
     return bad;
 }
 
-static int ensure_stage(vbfem_handle *h, long long n) {
-    if (n <= h->stage_cap) return 0;
-    CU(cudaDeviceSynchronize());
-    cudaFree(h->stage);
-    if (h->pin) cudaFreeHost(h->pin);
-    h->stage = h->pin = nullptr;
-    h->stage_cap = 0;
-    CU(cudaMalloc(&h->stage, (size_t)n * 12 * sizeof(double)));
-    CU(cudaMallocHost(&h->pin, (size_t)n * 12 * sizeof(double)));
-    h->stage_cap = n;
-    return 0;
-}
+// Host-buffer entry points.  They run on the handle's own stream.  Small batches (the one-sample-at-a-time
+// callers: Metropolis steps and KDE evaluators, src/postprocess_lib.py:78-103) skip the staging copies: the
+// kernel reads x from, and writes its results to, mapped pinned host memory -- one launch, one synchronise.
+constexpr int64_t kMappedMax = 64;
 
 extern "C" int vbfem_forward_host(vbfem_t *h, int64_t N, const double *x, double *y, double *hh) {
     if (!h || (N > 0 && (!x || !y || !hh))) return fail(-1, "null argument");
@@ -1812,13 +2176,19 @@ extern "C" int vbfem_forward_host(vbfem_t *h, int64_t N, const double *x, double
     CU(cudaSetDevice(h->device));
     int rc = ensure_stage(h, N);
     if (rc) return rc;
-    double *dx = h->stage, *dy = dx + 2 * N, *dh = dy + 2 * N;
+    cudaStream_t st = h->host_stream;
     memcpy(h->pin, x, (size_t)N * 2 * sizeof(double));
-    CU(cudaMemcpyAsync(dx, h->pin, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, 0));
-    rc = vbfem_forward(h, N, dx, dy, dh, 0, nullptr);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h->pin + 2 * N, dy, (size_t)N * 4 * sizeof(double), cudaMemcpyDeviceToHost, 0));
-    CU(cudaStreamSynchronize(0));
+    if (N <= kMappedMax) {
+        rc = vbfem_forward(h, N, h->pin_dev, h->pin_dev + 2 * N, h->pin_dev + 4 * N, 0, st);
+        if (rc) return rc;
+    } else {
+        double *dx = h->stage, *dy = dx + 2 * N, *dh = dy + 2 * N;
+        CU(cudaMemcpyAsync(dx, h->pin, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = vbfem_forward(h, N, dx, dy, dh, 0, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->pin + 2 * N, dy, (size_t)N * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
     memcpy(y, h->pin + 2 * N, (size_t)N * 2 * sizeof(double));
     memcpy(hh, h->pin + 4 * N, (size_t)N * 2 * sizeof(double));
     return 0;
@@ -1831,15 +2201,22 @@ extern "C" int vbfem_forward_backward_host(vbfem_t *h, int64_t N, const double *
     CU(cudaSetDevice(h->device));
     int rc = ensure_stage(h, N);
     if (rc) return rc;
-    double *d = h->stage;  // x | gy | gh | y | h | gx
-    memcpy(h->pin, x, (size_t)N * 2 * sizeof(double));
+    cudaStream_t st = h->host_stream;
+    memcpy(h->pin, x, (size_t)N * 2 * sizeof(double));  // x | gy | gh | y | h | gx
     memcpy(h->pin + 2 * N, gy, (size_t)N * 2 * sizeof(double));
     memcpy(h->pin + 4 * N, gh, (size_t)N * 2 * sizeof(double));
-    CU(cudaMemcpyAsync(d, h->pin, (size_t)N * 6 * sizeof(double), cudaMemcpyHostToDevice, 0));
-    rc = vbfem_forward_backward(h, N, d, d + 2 * N, d + 4 * N, d + 6 * N, d + 8 * N, d + 10 * N, nullptr);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h->pin + 6 * N, d + 6 * N, (size_t)N * 6 * sizeof(double), cudaMemcpyDeviceToHost, 0));
-    CU(cudaStreamSynchronize(0));
+    if (N <= kMappedMax) {
+        double *d = h->pin_dev;
+        rc = vbfem_forward_backward(h, N, d, d + 2 * N, d + 4 * N, d + 6 * N, d + 8 * N, d + 10 * N, st);
+        if (rc) return rc;
+    } else {
+        double *d = h->stage;
+        CU(cudaMemcpyAsync(d, h->pin, (size_t)N * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = vbfem_forward_backward(h, N, d, d + 2 * N, d + 4 * N, d + 6 * N, d + 8 * N, d + 10 * N, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->pin + 6 * N, d + 6 * N, (size_t)N * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
     memcpy(y, h->pin + 6 * N, (size_t)N * 2 * sizeof(double));
     memcpy(hh, h->pin + 8 * N, (size_t)N * 2 * sizeof(double));
     memcpy(gx, h->pin + 10 * N, (size_t)N * 2 * sizeof(double));

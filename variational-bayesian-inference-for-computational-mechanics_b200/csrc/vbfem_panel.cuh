@@ -1,0 +1,655 @@
+// vbfem_panel.cuh -- blocked banded LDL^T for wide bands (Cook 80x40: n = 6560, half bandwidth 85):
+// one CTA per Monte-Carlo sample, two CTAs per SM, the factor streamed to HBM with bulk copies.
+//
+// The matrix is cut into 8x8 blocks.  A "panel" is one block column: the diagonal block and the
+// NB blocks below it (NB = 11 for b = 85) plus ONE extra block row that carries up to eight
+// right-hand sides through the elimination (row 0: the load vector, rows 1..6: the six strain
+// functionals B^T of the two observed Gauss points).  Per panel:
+//   diag   the 8x8 diagonal block is factored (LDL^T) and its unit lower factor inverted, in
+//          registers, by one warp;
+//   solve  every block below becomes V = X * L11^-T (two FP64 tensor-core MMAs m8n8k4 per block);
+//   update the trailing window, (NB+1) NB/2 + NB blocks, takes its rank-8 update C -= L V^T, again
+//          two DMMAs per block.  Fragments are read and written as ONE 16-byte access per lane at
+//          (block base + 16 * lane): the 8x8 row-major block is exactly the C fragment layout,
+//          and with the contraction index split {0,2,4,6} / {1,3,5,7} over the two MMAs it is
+//          the A and B fragment layout too -- no shuffles, no bank conflicts;
+//   fresh  the block row entering the window is assembled on the fly by an atomics-free GATHER
+//          (host table: target entry <- up to four element-matrix entries) from a ring of element
+//          matrices that the per-element Q4 kernels fill a batch ahead (src/mat_subroutine_tf.py:23-110,
+//          src/fem_solver_tf.py:229-341 upstream).  K itself never exists in HBM.
+// Only the lower triangle of the window is kept ((NB+1)(NB+2)/2 blocks, 40 KB): diagonal d of the
+// window is a ring of NB+1-d block slots, the slot of block (I, J) is J mod (NB+1-d).
+//
+// The band order ENDS at the observed node, so its displacement y falls out of the last diagonal
+// block; the observed strains are eps_i = q_i^T K^-1 f = sum_c z_qi[c] z_f[c] / d_c, accumulated from
+// the right-hand-side rows while they are eliminated: forward mode needs no back substitution and
+// writes nothing to HBM.  With an adjoint (fused or Jacobian mode) the scaled panels (L^T blocks, the
+// INVERSE of the diagonal block's unit factor, D^-1 z rows) go to a per-CTA HBM slab by
+// cp.async.bulk, and ONE reverse pass (bulk loads through an mbarrier ring) back-substitutes u and
+// up to four adjoint vectors together: the right-hand side of psi = K^-1 w is a combination of the
+// stored rows, since w lies in the span of the strain functionals and the observed node.
+// Replaces tf.linalg.solve (src/fem_solver_tf.py:137 upstream) and its gradient on wide bands.
+#pragma once
+#include "vbfem_front.cuh"
+
+namespace vbfem {
+
+constexpr int kPanelNT = 256, kPanelNW = kPanelNT / 32, kPanelEB = 32, kPanelNBMax = 15, kPanelStagesMax = 8;
+constexpr int kPanelAsm = kPanelNT - 32;  // threads of the assembling warps (1..7)
+
+struct PanelModel {
+    int n, off, npad, NQ, NB;  // order, leading pad rows, padded order, panels, block half bandwidth
+    int R;                     // capacity of the element-matrix ring
+    int nub;                   // blocks of one trailing update
+    int obs_loc[2];            // row inside the last panel of the observed node's (x, y) dof, -1 if supported
+    int o_win, o_rhs, o_lst, o_ke, smem_bytes;  // shared-memory offsets in bytes
+    int stages;                // bulk-load ring of the reverse pass
+    int kstart[kPanelNW + 1];  // update blocks [kstart[w], kstart[w+1]) belong to warp w
+    unsigned short ub[kPanelNBMax * (kPanelNBMax + 1) / 2 + kPanelNBMax];  // (I << 8) | J
+    const int *gptr;             // [NQ + 1] gather entries of block row q
+    const unsigned short *gdst;  // target inside the fresh block row: d * 64 + g * 8 + c
+    const ushort4 *gsrc;         // up to four element-ring entries (slot * 36 + tri), unused -> the zero entry
+    const int *eneed;            // [NQ] elements (first-use order) block row q needs
+    const int *eord;             // [nele] elements in first-use order
+    const double *rhs0;          // [NQ][8][8] initial right-hand-side blocks
+    const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported
+    double *lws;                 // per-CTA factor slab
+    long long lws_stride;        // doubles
+    double *xws;                 // per-CTA solution vectors [5][npad]
+    long long xws_stride;
+};
+
+struct PanelSmem {
+    double rd[8];       // 1/d of the current diagonal block
+    double W[64];       // [v][a]: weight of right-hand-side row a in the right-hand side of vector v
+    double nodew[16];   // [v][2]: weight of the observed node's unit vectors
+    double nodeL[16];   // [2][8]: D^-1 L11^-1 e_(observed dof) inside the last panel
+    double G[8];        // q_a^T K^-1 f
+    double lf_last[8];  // D^-1 z_f of the last panel
+    double obs[32];
+    double red[2 * 5 * kPanelNW];
+    unsigned long long bar[kPanelStagesMax];
+    int colslot[2][kPanelNBMax + 2];
+    int flag;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// One 8x8x8 block product C += A * B^T on fragments (a = A[g][2t..2t+1], b = B[g][2t..2t+1], c = C[g][2t..2t+1]).
+// DMMA: two tensor-core MMAs.  The alternative distributes the operands by shuffles and runs 16 DFMAs
+// per lane -- the same arithmetic on the FP64 pipe, kept for the ncu comparison the design notes quote.
+template <bool DMMA>
+__device__ __forceinline__ void block_mma(double2 &c, const double2 a, const double2 b, int lane) {
+    if (DMMA) {
+        dmma884(c.x, c.y, a.x, b.x);
+        dmma884(c.x, c.y, a.y, b.y);
+    } else {
+        const int g4 = lane & ~3, t = lane & 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double ax = __shfl_sync(kFull, a.x, g4 + k), ay = __shfl_sync(kFull, a.y, g4 + k);
+            const int r0 = 8 * t + k;  // lane holding B[2t][2k..2k+1], the next row is 4 lanes up
+            const double b0x = __shfl_sync(kFull, b.x, r0), b0y = __shfl_sync(kFull, b.y, r0);
+            const double b1x = __shfl_sync(kFull, b.x, r0 + 4), b1y = __shfl_sync(kFull, b.y, r0 + 4);
+            c.x = fma(ax, b0x, c.x);
+            c.x = fma(ay, b0y, c.x);
+            c.y = fma(ax, b1x, c.y);
+            c.y = fma(ay, b1y, c.y);
+        }
+    }
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// MODE 0: y, h   MODE 1: y, h, gx = J^T (gy, gh)   MODE 2: y, h, J = d(y, h)/dx
+template <int MODE, bool DMMA>
+__global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_constant__ DevModel M,
+                                                                const __grid_constant__ PanelModel Q,
+                                                                const __grid_constant__ Args A) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    PanelSmem &S = *reinterpret_cast<PanelSmem *>(smraw);
+    double *win = reinterpret_cast<double *>(smraw + Q.o_win);  // window blocks, then (contiguous) the rhs ring
+    double *rhs = reinterpret_cast<double *>(smraw + Q.o_rhs);  // NB+1 right-hand-side blocks
+    double *lst = reinterpret_cast<double *>(smraw + Q.o_lst);  // two staging panels (transposed, scaled)
+    double *ke = reinterpret_cast<double *>(smraw + Q.o_ke);    // R element matrices (36 each), then 0.0, 1.0
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int NB = Q.NB, NQ = Q.NQ, NB1 = NB + 1, LPB = (NB + 2) * 64;  // doubles per stored panel
+    constexpr int NV = (MODE == 2) ? 5 : 2;
+    auto dbase = [&](int d) { return d * NB1 - (d * (d - 1)) / 2; };  // first slot of window diagonal d
+    double *lws = Q.lws + (size_t)blockIdx.x * Q.lws_stride;
+    double *xws = Q.xws + (size_t)blockIdx.x * Q.xws_stride;
+    // mbarriers of the reverse pass: initialised once, their phases run on across the CTA's samples
+    if (MODE > 0) {
+        if (tid == 0) {
+            for (int i = 0; i < Q.stages; ++i) mbar_init(&S.bar[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    unsigned sweep_base = 0;  // bulk loads issued per stage ring so far (all samples of this CTA)
+
+    for (long long s = blockIdx.x; s < A.N; s += gridDim.x) {
+        // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu)
+        // src/data_generation_2sam_more_loss.py:181-186
+        double x0, x1;
+        if (A.mode & kElbo) {
+            // main_custom_training.py:199-209: theta = e * sqrt(sig2) + mu, flattened [B*S]
+            const long long j = A.j_begin + s;
+            const int bb = (int)(j / A.S), ss = (int)(j % A.S);
+            x0 = A.e[2 * ss] * sqrt(A.sig2[2 * bb]) + A.mu[2 * bb];
+            x1 = A.e[2 * ss + 1] * sqrt(A.sig2[2 * bb + 1]) + A.mu[2 * bb + 1];
+        } else {
+            x0 = A.x[2 * s];
+            x1 = A.x[2 * s + 1];
+        }
+        const double E = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
+        const double nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
+        const Lame mat = lame_from_E_nu(E, nu);
+
+        // ---------------- reset: window and rhs ring to zero, ring constants, slot tables
+        {
+            double2 *w2 = reinterpret_cast<double2 *>(win);
+            const int nz = (dbase(NB1) + NB1) * 32;  // window blocks + rhs ring, 32 double2 per block
+            for (int i = tid; i < nz; i += kPanelNT) w2[i] = make_double2(0.0, 0.0);
+            if (tid == 0) {
+                ke[Q.R * 36] = 0.0;
+                ke[Q.R * 36 + 1] = 1.0;
+                S.flag = 0;
+            }
+            if (tid <= NB1) S.colslot[0][tid] = 0;
+        }
+        __syncthreads();
+
+        int ecomp = 0;         // element matrices computed so far (assembling warps)
+        double gacc = 0.0;     // warp 0: partial sum of G[g] over this lane's columns
+        // Element matrices of the next batch into the ring: thread = (element, Gauss point), the four
+        // Gauss-point contributions are summed by two shuffles (src/mat_subroutine_tf.py:23-110: shape
+        // functions, material subroutine at the zero predictor, kt += dvol B^T Ct B).  Warps 1..4.
+        auto element_batch = [&](int tq) {
+            const int k = ecomp + (tq >> 2), gp = tq & 3;
+            double kev[36];
+#pragma unroll
+            for (int q = 0; q < 36; ++q) kev[q] = 0.0;
+            if (k < M.nele) {
+                const int e = Q.eord[k];
+                double xl[4], yl[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int nd = M.ien[4 * e + a];
+                    const double2 xy = *reinterpret_cast<const double2 *>(M.coord + 2 * nd);
+                    xl[a] = xy.x;
+                    yl[a] = xy.y;
+                }
+                ShapeQ4 sh;
+                shapef_q4(xl, yl, gp, M.thk, sh);
+                double sig[4];
+                Tangent C;
+                mat_isotropic_plane_strain(mat, 0.0, 0.0, 0.0, sig, C);
+                accumulate_kt(sh, C, kev);
+            }
+#pragma unroll
+            for (int q = 0; q < 36; ++q) {
+                kev[q] += __shfl_xor_sync(kFull, kev[q], 1);
+                kev[q] += __shfl_xor_sync(kFull, kev[q], 2);
+            }
+            if (k < M.nele) {
+                double *dst = ke + (k % Q.R) * 36;
+#pragma unroll
+                for (int q = 0; q < 36; ++q)
+                    if ((q & 3) == gp) dst[q] = kev[q];
+            }
+        };
+        // Block row q enters the window (warps 1..7, tq = tid - 32): clear its blocks, fetch its
+        // right-hand-side block, make sure its element matrices exist, gather.  slots == nullptr: the
+        // initial rows, block (q, q-d) sits in slot q-d of diagonal d.
+        auto fresh_row = [&](int q, const int *slots, int rslot, int tq) {
+            for (int idx = tq; idx < (NB + 2) * 32; idx += kPanelAsm) {
+                const int blk = idx >> 5, l = idx & 31;
+                if (blk <= NB) {
+                    if (q - blk >= 0) {
+                        const int sl = slots ? slots[blk] : q - blk;
+                        reinterpret_cast<double2 *>(win + (dbase(blk) + sl) * 64)[l] = make_double2(0.0, 0.0);
+                    }
+                } else {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (q < NQ) v = reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64)[l];
+                    reinterpret_cast<double2 *>(rhs + rslot * 64)[l] = v;
+                }
+            }
+            if (q < NQ) {
+                const int need = Q.eneed[q];
+                while (ecomp < need) {
+                    if (tq < 4 * kPanelEB) element_batch(tq);
+                    ecomp += kPanelEB;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kPanelAsm) : "memory");
+            if (q < NQ) {
+                const int i1 = Q.gptr[q + 1];
+                for (int i = Q.gptr[q] + tq; i < i1; i += kPanelAsm) {
+                    const int dst = Q.gdst[i];
+                    const ushort4 sr = Q.gsrc[i];
+                    const double v = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+                    const int d = dst >> 6;
+                    const int sl = slots ? slots[d] : q - d;
+                    win[(dbase(d) + sl) * 64 + (dst & 63)] = v;
+                }
+            }
+        };
+
+        // ---------------- the first NB+1 block rows fill the window
+        if (warp > 0) {
+            for (int q = 0; q <= NB; ++q) {
+                fresh_row(q, nullptr, q, tid - 32);
+                asm volatile("bar.sync 1, %0;" ::"n"(kPanelAsm) : "memory");  // ring slots may be reused by the next batch
+            }
+        }
+        __syncthreads();
+
+        // ---------------- panels
+        int rslot = 0;  // p mod (NB+1): slot of panel p in the rhs ring
+        for (int p = 0; p < NQ; ++p) {
+            const int *cs = S.colslot[p & 1];
+            double *stg = lst + (p & 1) * LPB;  // staging panel: [0] inverse unit factor^T, [1..NB] L^T blocks, [NB+1] rhs
+            // ---- phase A: warp 0 factors the diagonal block; warps 1..7 bring in block row p+NB
+            //      (slots of panel p-1, which the trailing update has just finished reading)
+            if (warp == 0) {
+                if (MODE > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const double *D = win + (dbase(0) + cs[0]) * 64;
+                double a[36];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) a[tri(i, j)] = D[i * 8 + j];
+                double rdv[8];
+                int bad = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double d = a[tri(k, k)];
+                    bad |= !(d > 0.0 && d < 1.0e300);
+                    rdv[k] = fast_rcp3(d);
+#pragma unroll
+                    for (int j = k + 1; j < 8; ++j) {
+                        const double ljk = a[tri(j, k)] * rdv[k];
+#pragma unroll
+                        for (int i = j; i < 8; ++i) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
+                        a[tri(j, k)] = ljk;  // rows i > j of column k stay unscaled until their own turn
+                    }
+                }
+                if (bad && lane == 0) S.flag = 1;
+                // inverse of the unit lower factor, column by column; stored transposed ([c][k] = Minv[k][c])
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double m[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int k = j; k < i; ++k) acc = fma(a[tri(i, k)], m[k], acc);
+                            m[i] = -acc;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2)
+                            reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2)
+                        reinterpret_cast<double2 *>(S.rd)[k >> 1] = make_double2(rdv[k], rdv[k + 1]);
+                }
+            } else if (p > 0) {
+                int rs = rslot - 1;
+                rs += (rs < 0) ? NB1 : 0;
+                fresh_row(p + NB, S.colslot[(p - 1) & 1], rs, tid - 32);
+            }
+            __syncthreads();
+
+            // ---- phase B: V = X L11^-T for the blocks below (in place), scaled copy to the staging panel
+            {
+                const double2 mi = make_double2(stg[(2 * t) * 8 + g], stg[(2 * t + 1) * 8 + g]);  // Minv[g][2t..2t+1]
+                const double2 r2 = reinterpret_cast<const double2 *>(S.rd)[t];
+                for (int b = warp; b <= NB; b += kPanelNW) {  // b = 0: right-hand sides, else block row p+b
+                    double2 *X = reinterpret_cast<double2 *>(b ? win + (dbase(b) + cs[b]) * 64 : rhs + rslot * 64);
+                    const double2 xv = X[lane];
+                    double2 v = make_double2(0.0, 0.0);
+                    block_mma<DMMA>(v, xv, mi, lane);
+                    X[lane] = v;
+                    const double2 l = make_double2(v.x * r2.x, v.y * r2.y);
+                    if (MODE > 0 || b == 0) {
+                        double *Lt = stg + (b ? b : NB + 1) * 64;
+                        Lt[(2 * t) * 8 + g] = l.x;
+                        Lt[(2 * t + 1) * 8 + g] = l.y;
+                    }
+                    if (b == 0) {  // warp 0: strains / node rows against the load row, G[g] += sum_c V[g][c] L[0][c]
+                        const double lfx = __shfl_sync(kFull, l.x, t), lfy = __shfl_sync(kFull, l.y, t);
+                        gacc = fma(v.x, lfx, fma(v.y, lfy, gacc));
+                        if (p == NQ - 1 && g == 0) {
+                            S.lf_last[2 * t] = l.x;
+                            S.lf_last[2 * t + 1] = l.y;
+                        }
+                    }
+                }
+                if (tid <= NB1) {  // slot tables of panel p+1: (p+1) mod (NB+1-d)
+                    int v = cs[tid] + 1;
+                    v = (v >= NB1 - tid) ? 0 : v;
+                    S.colslot[(p + 1) & 1][tid] = (tid <= NB) ? v : 0;
+                }
+                if (MODE > 0) fence_async_smem();
+            }
+            __syncthreads();
+
+            // ---- phase C: trailing update C(I,J) -= L_I V_J^T; thread 0 first sends the staged panel to HBM
+            {
+                if (MODE > 0 && tid == 0) bulk_store(lws + (size_t)p * LPB, stg, LPB * 8);
+                const double2 r2 = reinterpret_cast<const double2 *>(S.rd)[t];
+                int lastI = -1;
+                double2 a = make_double2(0.0, 0.0);
+                const int k1 = Q.kstart[warp + 1];
+                for (int k = Q.kstart[warp]; k < k1; ++k) {
+                    const int ub = Q.ub[k], I = ub >> 8, J = ub & 255;
+                    if (I != lastI) {
+                        const double2 v = reinterpret_cast<const double2 *>(
+                            I <= NB ? win + (dbase(I) + cs[I]) * 64 : rhs + rslot * 64)[lane];
+                        a = make_double2(-v.x * r2.x, -v.y * r2.y);
+                        lastI = I;
+                    }
+                    const double2 bv = reinterpret_cast<const double2 *>(win + (dbase(J) + cs[J]) * 64)[lane];
+                    double2 *C;
+                    if (I <= NB) {
+                        const int d = I - J, m = NB1 - d;
+                        int sl = cs[d] + J;
+                        sl -= (sl >= m) ? m : 0;
+                        C = reinterpret_cast<double2 *>(win + (dbase(d) + sl) * 64);
+                    } else {
+                        int sl = rslot + J;
+                        sl -= (sl >= NB1) ? NB1 : 0;
+                        C = reinterpret_cast<double2 *>(rhs + sl * 64);
+                    }
+                    double2 c = C[lane];
+                    block_mma<DMMA>(c, a, bv, lane);
+                    C[lane] = c;
+                }
+            }
+            __syncthreads();
+            rslot = (rslot + 1 == NB1) ? 0 : rslot + 1;
+        }
+
+        // ---------------- observations: y from the last diagonal block, strains from the accumulated
+        //                  products, h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
+        const double *stgl = lst + ((NQ - 1) & 1) * LPB;  // last panel: [c][k] = Minv[k][c]
+        if (warp == 0) {
+            if (MODE > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            gacc += __shfl_xor_sync(kFull, gacc, 1);
+            gacc += __shfl_xor_sync(kFull, gacc, 2);
+            if (t == 0) S.G[g] = gacc;
+            // D^-1 L11^-1 e_j for the observed node's dofs j (their unit vectors start in the last panel)
+            if (lane < 16) {
+                const int k = lane >> 3, c = lane & 7, j = Q.obs_loc[k];
+                S.nodeL[lane] = (j >= 0) ? stgl[j * 8 + c] * S.rd[c] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid < 2) {
+            double exx = S.G[1 + 3 * tid], eyy = S.G[2 + 3 * tid], gxy = S.G[3 + 3 * tid];
+            double sig[4];
+            Tangent C;
+            mat_isotropic_plane_strain(mat, exx, eyy, gxy, sig, C);
+            double ds[4];
+            const double hv = von_mises_ref(sig, ds);
+            const double l2m = mat.lam + 2.0 * mat.mu;
+            double *o = S.obs + 8 * tid;
+            o[0] = hv;
+            o[1] = ds[0] * l2m + ds[1] * mat.lam + ds[2] * mat.lam;  // dh/d(exx)
+            o[2] = ds[0] * mat.lam + ds[1] * l2m + ds[2] * mat.lam;  // dh/d(eyy)
+            o[3] = ds[3] * mat.mu;                                   // dh/d(gxy)
+            o[4] = (ds[0] + ds[1] + ds[2]) * (exx + eyy);            // dh/d(lambda) at fixed u
+            o[5] = 2.0 * ds[0] * exx + 2.0 * ds[1] * eyy + ds[3] * gxy;
+            if (A.h) A.h[2 * s + tid] = hv;
+            // y_k = (L11^-T D^-1 z_f)[j] = sum_c Minv[c][j] lf[c]
+            const int j = Q.obs_loc[tid];
+            double yv = 0.0;
+            if (j >= 0)
+                for (int c = 0; c < 8; ++c) yv = fma(stgl[j * 8 + c], S.lf_last[c], yv);
+            S.obs[16 + tid] = yv;
+            if (A.y) A.y[2 * s + tid] = yv;
+            if (A.f_out) A.f_out[2 * s + tid] = yv;
+            if (!(fabs(yv) < 1.0e300) || !(hv < 1.0e300)) S.flag = 1;
+        }
+        if (MODE > 0) {
+            __syncthreads();
+            // ---------------- right-hand sides of the reverse pass: v = 0 is u (row 0 = D^-1 z_f); the adjoint
+            //                  vectors combine the strain rows and the observed node's unit vectors
+            if (tid < 64) S.W[tid] = 0.0;
+            if (tid < 16) S.nodew[tid] = 0.0;
+            __syncthreads();
+            if (tid == 0) {
+                S.W[0] = 1.0;
+                if (MODE == 1) {
+                    double gy0, gy1, gh0 = 0.0, gh1 = 0.0;
+                    if (A.mode & kElbo) {
+                        // d(loss)/d f_j through term2 with the [B, B*S] broadcast (main_custom_training.py:205-214)
+                        gy0 = A.gcoef * ((double)A.B * S.obs[16] - A.ysum[0]);
+                        gy1 = A.gcoef * ((double)A.B * S.obs[17] - A.ysum[1]);
+                    } else {
+                        gy0 = A.gy[2 * s];
+                        gy1 = A.gy[2 * s + 1];
+                        gh0 = A.gh[2 * s];
+                        gh1 = A.gh[2 * s + 1];
+                    }
+                    S.obs[20] = gh0;
+                    S.obs[21] = gh1;
+                    for (int i = 0; i < 3; ++i) {
+                        S.W[8 + 1 + i] = gh0 * S.obs[1 + i];
+                        S.W[8 + 4 + i] = gh1 * S.obs[8 + 1 + i];
+                    }
+                    S.nodew[2] = gy0;
+                    S.nodew[3] = gy1;
+                } else {
+                    // vectors 1, 2: adjoints of y0, y1; 3, 4: adjoints of h0, h1
+                    S.nodew[2 * 1] = 1.0;
+                    S.nodew[2 * 2 + 1] = 1.0;
+                    for (int i = 0; i < 3; ++i) {
+                        S.W[3 * 8 + 1 + i] = S.obs[1 + i];
+                        S.W[4 * 8 + 4 + i] = S.obs[8 + 1 + i];
+                    }
+                }
+            }
+            // ---------------- reverse pass: x_p = Minv_p^T (W Lrhs_p - sum_d x_(p+d) L_(p+d,p)), panels descending
+            double *stage0 = win;                                   // bulk-load ring (window + rhs ring are free now)
+            double *xr = ke;                                        // NB+1 solution blocks [v][k]
+            double *part = ke + NB1 * 64;                           // 8 partial products
+            const int NS = Q.stages;
+            for (int i = tid; i < NB1 * 64; i += kPanelNT) xr[i] = 0.0;
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                for (int i = 0; i < NS && i < NQ; ++i) {
+                    const int st = (sweep_base + i) % NS;
+                    mbar_expect_tx(&S.bar[st], LPB * 8);
+                    bulk_load(stage0 + st * LPB, lws + (size_t)(NQ - 1 - i) * LPB, LPB * 8, &S.bar[st]);
+                }
+            }
+            int xs = (NQ - 1) % NB1;  // slot of panel p in the solution ring
+            for (int i = 0; i < NQ; ++i) {
+                const int p = NQ - 1 - i;
+                const unsigned use = sweep_base + i;
+                const int st = (int)(use % NS);
+                const double *pan = stage0 + st * LPB;
+                mbar_wait(&S.bar[st], (use / NS) & 1u);
+                double2 c = make_double2(0.0, 0.0);
+                for (int b = warp; b <= NB; b += kPanelNW) {
+                    double2 a;
+                    if (b == 0) {
+                        a = reinterpret_cast<const double2 *>(S.W)[lane];
+                    } else {
+                        int sl = xs + b;
+                        sl -= (sl >= NB1) ? NB1 : 0;
+                        a = reinterpret_cast<const double2 *>(xr + sl * 64)[lane];
+                        a.x = -a.x;
+                        a.y = -a.y;
+                    }
+                    const double2 bv = reinterpret_cast<const double2 *>(pan + (b ? b : NB + 1) * 64)[lane];
+                    block_mma<DMMA>(c, a, bv, lane);
+                }
+                reinterpret_cast<double2 *>(part + warp * 64)[lane] = c;
+                __syncthreads();
+                if (warp == 0) {
+                    double2 d = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int w = 0; w < kPanelNW; ++w) {
+                        const double2 q = reinterpret_cast<const double2 *>(part + w * 64)[lane];
+                        d.x += q.x;
+                        d.y += q.y;
+                    }
+                    if (p == NQ - 1) {
+                        const double w0 = S.nodew[2 * g], w1 = S.nodew[2 * g + 1];
+                        d.x += w0 * S.nodeL[2 * t] + w1 * S.nodeL[8 + 2 * t];
+                        d.y += w0 * S.nodeL[2 * t + 1] + w1 * S.nodeL[8 + 2 * t + 1];
+                    }
+                    const double2 mi = reinterpret_cast<const double2 *>(pan)[lane];  // [c][k] = Minv[k][c]
+                    double2 x = make_double2(0.0, 0.0);
+                    block_mma<DMMA>(x, d, mi, lane);
+                    reinterpret_cast<double2 *>(xr + xs * 64)[lane] = x;
+                    if (g < NV) *reinterpret_cast<double2 *>(xws + (size_t)g * Q.npad + 8 * p + 2 * t) = x;
+                }
+                __syncthreads();
+                if (tid == 0 && i + NS < NQ) {
+                    mbar_expect_tx(&S.bar[st], LPB * 8);
+                    bulk_load(stage0 + st * LPB, lws + (size_t)(p - NS) * LPB, LPB * 8, &S.bar[st]);
+                }
+                xs = (xs == 0) ? NB : xs - 1;
+            }
+            sweep_base += (unsigned)NQ;
+
+            // ---------------- element-wise contraction -psi^T (dK/dp) u + explicit dh/dp, chained to x
+            constexpr int NADJ = NV - 1;
+            double sl[NADJ], sm[NADJ];
+#pragma unroll
+            for (int v = 0; v < NADJ; ++v) sl[v] = sm[v] = 0.0;
+            for (int e = tid; e < M.nele; e += kPanelNT) {
+                double xl[4], yl[4], ue[8];
+                int lm[8];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int nd = M.ien[4 * e + a];
+                    const double2 xy = *reinterpret_cast<const double2 *>(M.coord + 2 * nd);
+                    xl[a] = xy.x;
+                    yl[a] = xy.y;
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    lm[a] = Q.elm[8 * e + a];
+                    ue[a] = (lm[a] >= 0) ? xws[lm[a]] : 0.0;
+                }
+#pragma unroll 1
+                for (int gp = 0; gp < 4; ++gp) {
+                    ShapeQ4 sh;
+                    shapef_q4(xl, yl, gp, M.thk, sh);
+                    double uxx, uyy, uxy;
+                    strain_q4(sh, ue, uxx, uyy, uxy);
+#pragma unroll
+                    for (int v = 0; v < NADJ; ++v) {
+                        const double *pv = xws + (size_t)(v + 1) * Q.npad;
+                        double pe[8], pxx, pyy, pxy, cl, cm;
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) pe[a] = (lm[a] >= 0) ? pv[lm[a]] : 0.0;
+                        strain_q4(sh, pe, pxx, pyy, pxy);
+                        mat_tangent_param_contract(pxx, pyy, pxy, uxx, uyy, uxy, cl, cm);
+                        sl[v] = fma(sh.dvol, cl, sl[v]);
+                        sm[v] = fma(sh.dvol, cm, sm[v]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NADJ; ++v) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sl[v] += __shfl_down_sync(kFull, sl[v], o);
+                    sm[v] += __shfl_down_sync(kFull, sm[v], o);
+                }
+                if (lane == 0) {
+                    S.red[2 * (v * kPanelNW + warp)] = sl[v];
+                    S.red[2 * (v * kPanelNW + warp) + 1] = sm[v];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // d lambda, d mu / d(E, nu), then dE/dx0 = std0 * E ; dnu/dx1 = std1 * nu (1 - 2 nu)
+                const double tt = (1.0 + nu) * (1.0 - 2.0 * nu);
+                const double dl_dE = mat.lam / E, dm_dE = mat.mu / E;
+                const double dl_dnu = E * (1.0 + 2.0 * nu * nu) / (tt * tt);
+                const double dm_dnu = -0.5 * E / ((1.0 + nu) * (1.0 + nu));
+                const double dE_dx0 = M.theta_std[0] * E, dnu_dx1 = M.theta_std[1] * nu * (1.0 - 2.0 * nu);
+                double tl[NADJ], tm[NADJ];
+#pragma unroll
+                for (int v = 0; v < NADJ; ++v) {
+                    tl[v] = tm[v] = 0.0;
+                    for (int w = 0; w < kPanelNW; ++w) {
+                        tl[v] += S.red[2 * (v * kPanelNW + w)];
+                        tm[v] += S.red[2 * (v * kPanelNW + w) + 1];
+                    }
+                }
+                if (MODE == 1) {
+                    const double gh0 = S.obs[20], gh1 = S.obs[21];
+                    const double gl = -tl[0] + gh0 * S.obs[4] + gh1 * S.obs[8 + 4];
+                    const double gm = -tm[0] + gh0 * S.obs[5] + gh1 * S.obs[8 + 5];
+                    A.gx[2 * s] = (gl * dl_dE + gm * dm_dE) * dE_dx0;
+                    A.gx[2 * s + 1] = (gl * dl_dnu + gm * dm_dnu) * dnu_dx1;
+                } else {
+                    // adjoint vectors v = 0, 1: y0, y1; v = 2, 3: h0, h1 -- the storage order of J
+                    double *J = A.ws + (size_t)s * A.ws_stride;
+#pragma unroll
+                    for (int v = 0; v < NADJ; ++v) {
+                        const double gl = -tl[v] + (v >= 2 ? S.obs[8 * (v - 2) + 4] : 0.0);
+                        const double gm = -tm[v] + (v >= 2 ? S.obs[8 * (v - 2) + 5] : 0.0);
+                        J[2 * v] = (gl * dl_dE + gm * dm_dE) * dE_dx0;
+                        J[2 * v + 1] = (gl * dl_dnu + gm * dm_dnu) * dnu_dx1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && A.status) A.status[s] = S.flag;
+        __syncthreads();
+    }
+}
+
+}  // namespace vbfem

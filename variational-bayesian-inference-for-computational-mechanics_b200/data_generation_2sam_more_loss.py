@@ -33,17 +33,20 @@ def _fem_function():
 
         @staticmethod
         def forward(ctx, x, engine):
+            # every autograd node owns its state: the 4x2 Jacobian per sample (64 B) is saved on ctx,
+            # so several FEM calls may sit in one graph and backward in any order
             ctx.engine = engine
             ctx.n = x.shape[0]
-            y, h = engine.forward(x.contiguous(), keep_factor=True)
-            ctx.mark_non_differentiable()
+            y, h, jac = engine.forward_jac(x.contiguous())
+            ctx.save_for_backward(jac)
             return y, h
 
         @staticmethod
         def backward(ctx, gy, gh):
+            (jac,) = ctx.saved_tensors
             z = lambda g: torch.zeros(ctx.n, 2, dtype=torch.float64, device=ctx.engine.device) if g is None \
                 else g.contiguous()
-            return ctx.engine.backward(z(gy), z(gh)), None
+            return ctx.engine.jac_vjp(jac, z(gy), z(gh)), None
 
     return FemFH
 

@@ -126,13 +126,55 @@ class CookFemEngine:
             self.launches += 1
         return y, h
 
-    def backward(self, gy, gh):
-        """(gy, gh) -> gx for the batch of the last forward(keep_factor=True)."""
+    def reserve(self, n_samples_max):
+        """Size the handle's per-sample buffers up front (required before CUDA-graph capture)."""
+        _lib.check(self.lib.vbfem_reserve(self._h, int(n_samples_max)), "vbfem_reserve")
+
+    def keep_ticket(self):
+        """Ticket of the Jacobians kept by the last forward(keep_factor=True) (0: none)."""
+        return int(self.lib.vbfem_keep_ticket(self._h))
+
+    def backward(self, gy, gh, ticket=None):
+        """(gy, gh) -> gx for the batch of the last forward(keep_factor=True).  With ``ticket`` (from
+        ``keep_ticket()`` right after that forward) a stale request raises instead of silently using
+        another call's Jacobians."""
         n = gy.shape[0]
         gx = self._new(n, 2)
         if n:
-            _lib.check(self.lib.vbfem_backward(self._h, n, self._chk(gy, n, "gy"), self._chk(gh, n, "gh"),
-                                               ctypes.c_void_p(gx.data_ptr()), self._stream()), "vbfem_backward")
+            if ticket is None:
+                rc = self.lib.vbfem_backward(self._h, n, self._chk(gy, n, "gy"), self._chk(gh, n, "gh"),
+                                             ctypes.c_void_p(gx.data_ptr()), self._stream())
+            else:
+                rc = self.lib.vbfem_backward_ticket(self._h, int(ticket), n, self._chk(gy, n, "gy"),
+                                                    self._chk(gh, n, "gh"), ctypes.c_void_p(gx.data_ptr()),
+                                                    self._stream())
+            _lib.check(rc, "vbfem_backward")
+            self.launches += 1
+        return gx
+
+    def forward_jac(self, x):
+        """x[N,2] -> y[N,2], h[N,2], J[N,4,2] = d(y0, y1, h0, h1)/d(x0, x1): the state a differentiable
+        wrapper saves per call (64 B per sample)."""
+        n = x.shape[0]
+        y, h, jac = self._new(n, 2), self._new(n, 2), self._new(n, 4, 2)
+        if n:
+            _lib.check(self.lib.vbfem_forward_jac(self._h, n, self._chk(x, n, "x"), ctypes.c_void_p(y.data_ptr()),
+                                                  ctypes.c_void_p(h.data_ptr()), ctypes.c_void_p(jac.data_ptr()),
+                                                  self._stream()), "vbfem_forward_jac")
+            self.launches += 1
+        return y, h, jac
+
+    def jac_vjp(self, jac, gy, gh):
+        """gx = J^T (gy, gh) for Jacobians from ``forward_jac`` (stateless)."""
+        n = gy.shape[0]
+        gx = self._new(n, 2)
+        if n:
+            if jac.device != self.device or jac.dtype != self.torch.float64 or not jac.is_contiguous() \
+                    or tuple(jac.shape) != (n, 4, 2):
+                raise ValueError(f"jac must be a contiguous float64 [{n},4,2] tensor on {self.device}")
+            _lib.check(self.lib.vbfem_jac_vjp(self._h, n, ctypes.c_void_p(jac.data_ptr()), self._chk(gy, n, "gy"),
+                                              self._chk(gh, n, "gh"), ctypes.c_void_p(gx.data_ptr()),
+                                              self._stream()), "vbfem_jac_vjp")
             self.launches += 1
         return gx
 
