@@ -1218,6 +1218,9 @@ struct PanelPlan {
     int kstart[kPanelNW + 1] = {0};
     int o_win = 0, o_rhs = 0, o_lst = 0, o_ke = 0, smem_bytes = 0, stages = 0;
     std::vector<int> gptr, eneed, eord, elm;
+    std::vector<double> ecoord;
+    std::vector<unsigned char> rec;  // row records (PanelModel::rec)
+    int rec_stride = 0, rec_o_coord = 0, rec_o_src = 0, rec_o_dst = 0, o_rec = 0;
     std::vector<unsigned short> gdst, gsrc, ub;  // gsrc: four entries per target
     std::vector<double> rhs0;
 };
@@ -1289,6 +1292,10 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
     std::stable_sort(P.eord.begin(), P.eord.end(), [&](int a, int c) { return first[a] < first[c]; });
     std::vector<int> pos(ne);
     for (int k = 0; k < ne; ++k) pos[P.eord[k]] = k;
+    P.ecoord.resize((size_t)8 * ne);
+    for (int k = 0; k < ne; ++k)
+        for (int a = 0; a < 4; ++a)
+            for (int c = 0; c < 2; ++c) P.ecoord[8 * k + 2 * a + c] = m->coord[2 * (m->ien[4 * P.eord[k] + a] - 1) + c];
     P.eneed.assign(P.NQ, 0);
     {
         int k = 0;
@@ -1302,12 +1309,10 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
         for (int e = 0; e < ne; ++e)
             if (last[e] >= 0) minpos[last[e]] = std::min(minpos[last[e]], pos[e]);
         for (int q = P.NQ - 1; q >= 0; --q) minpos[q] = std::min(minpos[q], minpos[q + 1]);
-        const int cap = (ne + kPanelEB - 1) / kPanelEB * kPanelEB;
+        // row q brings exactly the elements it is the first to need
         int R = kPanelEB;
-        for (int q = 0; q < P.NQ; ++q) {
-            const int computed = std::min((P.eneed[q] + kPanelEB - 1) / kPanelEB * kPanelEB, cap);
-            if (minpos[q] < computed) R = std::max(R, computed - minpos[q]);
-        }
+        for (int q = 0; q < P.NQ; ++q)
+            if (minpos[q] < P.eneed[q]) R = std::max(R, P.eneed[q] - minpos[q]);
         P.R = R;
     }
     if ((size_t)P.R * 36 + 2 > 65535) return no("element ring too large for 16-bit gather indices");
@@ -1377,22 +1382,49 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
         }
     }
 
-    // trailing-update schedule: blocks (I, J), 1 <= J <= I <= NB, then the right-hand-side row I = NB+1
+    // trailing-update schedule of warps 0..5: blocks (I, J), 1 <= J <= I <= NB, then the right-hand-side row
+    // I = NB+1; block (1, 1) -- the next diagonal block -- belongs to the look-ahead warp
     for (int I = 1; I <= NB + 1; ++I)
-        for (int J = 1; J <= std::min(I, NB); ++J) P.ub.push_back((unsigned short)((I << 8) | J));
+        for (int J = 1; J <= std::min(I, NB); ++J)
+            if (!(I == 1 && J == 1)) P.ub.push_back((unsigned short)((I << 8) | J));
     P.nub = (int)P.ub.size();
-    for (int w = 0; w <= kPanelNW; ++w) P.kstart[w] = (int)((long long)P.nub * w / kPanelNW);
+    for (int w = 0; w <= kPanelNW; ++w) P.kstart[w] = (int)((long long)P.nub * std::min(w, kPanelUpdW) / kPanelUpdW);
 
-    // shared-memory layout
-    const int nwin = NB1 * (NB1 + 1) / 2, LPBb = (NB + 2) * 512;
+    // row records
+    {
+        int maxnew = 0, maxcnt = 0;
+        for (int q = 0; q < P.NQ; ++q) {
+            maxnew = std::max(maxnew, P.eneed[q] - (q ? P.eneed[q - 1] : 0));
+            maxcnt = std::max(maxcnt, P.gptr[q + 1] - P.gptr[q]);
+        }
+        P.rec_o_coord = 16 + 512;
+        P.rec_o_src = P.rec_o_coord + 64 * maxnew;
+        P.rec_o_dst = P.rec_o_src + 8 * maxcnt;
+        P.rec_stride = (P.rec_o_dst + 2 * maxcnt + 15) & ~15;
+        P.rec.assign((size_t)P.NQ * P.rec_stride, 0);
+        for (int q = 0; q < P.NQ; ++q) {
+            unsigned char *rc = P.rec.data() + (size_t)q * P.rec_stride;
+            const int e0 = q ? P.eneed[q - 1] : 0, nnew = P.eneed[q] - e0, cnt = P.gptr[q + 1] - P.gptr[q];
+            int hd[4] = {nnew, cnt, e0, 0};
+            memcpy(rc, hd, 16);
+            memcpy(rc + 16, P.rhs0.data() + (size_t)q * 64, 512);
+            memcpy(rc + P.rec_o_coord, P.ecoord.data() + (size_t)8 * e0, (size_t)64 * nnew);
+            memcpy(rc + P.rec_o_src, P.gsrc.data() + (size_t)4 * P.gptr[q], (size_t)8 * cnt);
+            memcpy(rc + P.rec_o_dst, P.gdst.data() + P.gptr[q], (size_t)2 * cnt);
+        }
+    }
+
+    // shared-memory layout: window (diagonal d: ring of NB+2-d blocks), rhs ring, two staging panels, element ring
+    const int nwin = NB1 * (NB + 4) / 2, LPBb = (NB + 2) * 512;
     P.o_win = (int)((sizeof(PanelSmem) + 15) & ~(size_t)15);
     P.o_rhs = P.o_win + nwin * 512;
-    P.o_lst = P.o_rhs + NB1 * 512;
+    P.o_lst = P.o_rhs + (NB + 2) * 512;
     P.o_ke = P.o_lst + 2 * LPBb;
-    const int ke_bytes = std::max((P.R * 36 + 2) * 8, (NB1 + kPanelNW) * 512);
-    P.smem_bytes = P.o_ke + ((ke_bytes + 15) & ~15);
-    P.stages = std::min(kPanelStagesMax, (nwin + NB1) * 512 / LPBb);
-    if (P.stages < 1) return no("window too small for the reverse pass");
+    const int ke_bytes = std::max((P.R * 36 + 2) * 8, (NB1 + 2 * kPanelNW) * 512);
+    P.o_rec = P.o_ke + ((ke_bytes + 15) & ~15);
+    P.smem_bytes = P.o_rec + kPanelRecDepth * P.rec_stride;
+    P.stages = std::min(kPanelStagesMax, (nwin + NB + 2) * 512 / LPBb);
+    if (P.stages < 2) return no("window too small for the reverse pass");
     P.ok = true;
     return P;
 }
@@ -1712,6 +1744,11 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             Q.o_ke = P.o_ke;
             Q.smem_bytes = P.smem_bytes;
             Q.stages = P.stages;
+            Q.o_rec = P.o_rec;
+            Q.rec_stride = P.rec_stride;
+            Q.rec_o_coord = P.rec_o_coord;
+            Q.rec_o_src = P.rec_o_src;
+            Q.rec_o_dst = P.rec_o_dst;
             for (int w = 0; w <= kPanelNW; ++w) Q.kstart[w] = P.kstart[w];
             for (size_t i = 0; i < P.ub.size(); ++i) Q.ub[i] = P.ub[i];
             const bool dfma = getenv("VBFEM_PANEL_DFMA") != nullptr;  // the DMMA-vs-DFMA comparison
@@ -1733,19 +1770,8 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             }
             if (fits) {
                 int rc2 = 0;
-                const ushort4 *gs4 = nullptr;
-                {
-                    std::vector<ushort4> g4(P.gdst.size());
-                    for (size_t i = 0; i < g4.size(); ++i)
-                        g4[i] = make_ushort4(P.gsrc[4 * i], P.gsrc[4 * i + 1], P.gsrc[4 * i + 2], P.gsrc[4 * i + 3]);
-                    rc2 |= upload(h, g4, &gs4);
-                }
-                Q.gsrc = gs4;
-                rc2 |= upload(h, P.gptr, &Q.gptr);
-                rc2 |= upload(h, P.gdst, &Q.gdst);
+                rc2 |= upload(h, P.rec, &Q.rec);
                 rc2 |= upload(h, P.eneed, &Q.eneed);
-                rc2 |= upload(h, P.eord, &Q.eord);
-                rc2 |= upload(h, P.rhs0, &Q.rhs0);
                 rc2 |= upload(h, P.elm, &Q.elm);
                 if (rc2) return -2;
                 h->block = kPanelNT;
@@ -1971,6 +1997,13 @@ static int launch(vbfem_handle *h, Args &a, void *stream) {
         h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M, a);
     } else if (h->variant == 3 && !fields) {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);
+#ifdef VBFEM_TIMELINE
+        if (!h->timeline) {
+            CU(cudaMalloc(&h->timeline, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long)));
+        }
+        CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * h->ctas_per_sm * 4 * 16 * sizeof(long long), st));
+        a.timeline = h->timeline;
+#endif
         h->kern_panel[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->PM, a);
     } else {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->gen_ctas);

@@ -17,8 +17,15 @@
 //          (host table: target entry <- up to four element-matrix entries) from a ring of element
 //          matrices that the per-element Q4 kernels fill a batch ahead (src/mat_subroutine_tf.py:23-110,
 //          src/fem_solver_tf.py:229-341 upstream).  K itself never exists in HBM.
-// Only the lower triangle of the window is kept ((NB+1)(NB+2)/2 blocks, 40 KB): diagonal d of the
-// window is a ring of NB+1-d block slots, the slot of block (I, J) is J mod (NB+1-d).
+// Only the lower triangle of the window is kept: diagonal d of the window is a ring of NB+2-d block
+// slots (NB+1-d live blocks and one spare), the slot of block (I, J) is J mod (NB+2-d); 46 KB for NB = 11.
+// The spare slot lets the block row entering the window be assembled WHILE the current panel is
+// being applied.  Warp roles inside a panel step (two block barriers per panel):
+//   solve   warps 0..5: the blocks below the (already factored) diagonal block
+//   update  warps 0..5: the trailing blocks, software pipelined (the next block's fragments are in
+//           flight while the current block's two MMAs run);
+//           warp 6: updates the NEXT diagonal block first and factors it at once (look-ahead), and
+//           sends the finished panel to HBM;  warp 7: element matrices + gather of the entering row.
 //
 // The band order ENDS at the observed node, so its displacement y falls out of the last diagonal
 // block; the observed strains are eps_i = q_i^T K^-1 f = sum_c z_qi[c] z_f[c] / d_c, accumulated from
@@ -34,8 +41,10 @@
 
 namespace vbfem {
 
-constexpr int kPanelNT = 256, kPanelNW = kPanelNT / 32, kPanelEB = 32, kPanelNBMax = 15, kPanelStagesMax = 8;
-constexpr int kPanelAsm = kPanelNT - 32;  // threads of the assembling warps (1..7)
+constexpr int kPanelNT = 256, kPanelNW = kPanelNT / 32, kPanelNBMax = 15, kPanelStagesMax = 8;
+constexpr int kPanelUpdW = 6;   // warps 0..5 solve and update; warp 6: diagonal look-ahead; warp 7: assembly
+constexpr int kPanelEB = 8;     // element matrices per pass of one warp (lane = element x Gauss point)
+constexpr int kPanelRecDepth = 4;  // row records in flight to the assembling warp (bulk copies into a shared-memory ring)
 
 struct PanelModel {
     int n, off, npad, NQ, NB;  // order, leading pad rows, padded order, panels, block half bandwidth
@@ -44,14 +53,15 @@ struct PanelModel {
     int obs_loc[2];            // row inside the last panel of the observed node's (x, y) dof, -1 if supported
     int o_win, o_rhs, o_lst, o_ke, smem_bytes;  // shared-memory offsets in bytes
     int stages;                // bulk-load ring of the reverse pass
-    int kstart[kPanelNW + 1];  // update blocks [kstart[w], kstart[w+1]) belong to warp w
+    int o_rec, rec_stride, rec_o_coord, rec_o_src, rec_o_dst;  // row-record ring in shared memory / record layout (bytes)
+    int kstart[kPanelNW + 1];  // update blocks [kstart[w], kstart[w+1]) belong to warp w < kPanelUpdW
     unsigned short ub[kPanelNBMax * (kPanelNBMax + 1) / 2 + kPanelNBMax];  // (I << 8) | J
-    const int *gptr;             // [NQ + 1] gather entries of block row q
-    const unsigned short *gdst;  // target inside the fresh block row: d * 64 + g * 8 + c
-    const ushort4 *gsrc;         // up to four element-ring entries (slot * 36 + tri), unused -> the zero entry
+    // Row record of block row q (rec_stride bytes, what the row needs to enter the window): int32 header
+    // {new elements, gather entries, first new element (first-use order)}, the 8x8 right-hand-side block,
+    // the nodal coordinates [new][4][2] of the new elements, gather sources (ushort4: element-ring entries
+    // slot * 36 + tri, unused -> the zero entry) and gather targets (u16: d * 64 + g * 8 + c)
+    const unsigned char *rec;
     const int *eneed;            // [NQ] elements (first-use order) block row q needs
-    const int *eord;             // [nele] elements in first-use order
-    const double *rhs0;          // [NQ][8][8] initial right-hand-side blocks
     const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported
     double *lws;                 // per-CTA factor slab
     long long lws_stride;        // doubles
@@ -60,7 +70,7 @@ struct PanelModel {
 };
 
 struct PanelSmem {
-    double rd[8];       // 1/d of the current diagonal block
+    double rd[2][8];    // 1/d of the diagonal block, by panel parity
     double W[64];       // [v][a]: weight of right-hand-side row a in the right-hand side of vector v
     double nodew[16];   // [v][2]: weight of the observed node's unit vectors
     double nodeL[16];   // [2][8]: D^-1 L11^-1 e_(observed dof) inside the last panel
@@ -69,12 +79,13 @@ struct PanelSmem {
     double obs[32];
     double red[2 * 5 * kPanelNW];
     unsigned long long bar[kPanelStagesMax];
+    unsigned long long rbar[kPanelRecDepth];
     int colslot[2][kPanelNBMax + 2];
     int flag;
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -136,6 +147,26 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, uns
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+#ifdef VBFEM_TIMELINE
+#define PTL_DECL long long ptl[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ptl_t = clock64()
+#define PTL(i)                          \
+    do {                                \
+        const long long now_ = clock64(); \
+        ptl[i] += now_ - ptl_t;         \
+        ptl_t = now_;                   \
+    } while (0)
+#define PTL_FLUSH                                                                                  \
+    do {                                                                                           \
+        if (A.timeline && lane == 0 && (warp < 2 || warp >= 6))                                    \
+            for (int i_ = 0; i_ < 16; ++i_)                                                        \
+                A.timeline[(blockIdx.x * 4 + (warp < 2 ? warp : warp - 4)) * 16 + i_] = ptl[i_];   \
+    } while (0)
+#else
+#define PTL_DECL ((void)0)
+#define PTL(i) ((void)0)
+#define PTL_FLUSH ((void)0)
+#endif
+
 // MODE 0: y, h   MODE 1: y, h, gx = J^T (gy, gh)   MODE 2: y, h, J = d(y, h)/dx
 template <int MODE, bool DMMA>
 __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_constant__ DevModel M,
@@ -144,25 +175,28 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smraw[];
     PanelSmem &S = *reinterpret_cast<PanelSmem *>(smraw);
     double *win = reinterpret_cast<double *>(smraw + Q.o_win);  // window blocks, then (contiguous) the rhs ring
-    double *rhs = reinterpret_cast<double *>(smraw + Q.o_rhs);  // NB+1 right-hand-side blocks
+    double *rhs = reinterpret_cast<double *>(smraw + Q.o_rhs);  // NB+2 right-hand-side blocks
     double *lst = reinterpret_cast<double *>(smraw + Q.o_lst);  // two staging panels (transposed, scaled)
     double *ke = reinterpret_cast<double *>(smraw + Q.o_ke);    // R element matrices (36 each), then 0.0, 1.0
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int NB = Q.NB, NQ = Q.NQ, NB1 = NB + 1, LPB = (NB + 2) * 64;  // doubles per stored panel
+    const int NB = Q.NB, NQ = Q.NQ, NB1 = NB + 1, NB2 = NB + 2, LPB = (NB + 2) * 64;  // LPB: doubles per stored panel
     constexpr int NV = (MODE == 2) ? 5 : 2;
-    auto dbase = [&](int d) { return d * NB1 - (d * (d - 1)) / 2; };  // first slot of window diagonal d
+    auto dbase = [&](int d) { return d * NB2 - (d * (d - 1)) / 2; };  // first slot of window diagonal d (ring of NB+2-d)
+    auto wrap = [](int v, int m) { return v >= m ? v - m : v; };
+    auto ldv = [&](unsigned off) { return reinterpret_cast<const double2 *>(smraw + off)[lane]; };
     double *lws = Q.lws + (size_t)blockIdx.x * Q.lws_stride;
     double *xws = Q.xws + (size_t)blockIdx.x * Q.xws_stride;
-    // mbarriers of the reverse pass: initialised once, their phases run on across the CTA's samples
-    if (MODE > 0) {
-        if (tid == 0) {
-            for (int i = 0; i < Q.stages; ++i) mbar_init(&S.bar[i], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
+    // mbarriers (row records; reverse pass): initialised once, their phases run on across the CTA's samples
+    if (tid == 0) {
+        for (int i = 0; i < Q.stages; ++i) mbar_init(&S.bar[i], 1);
+        for (int i = 0; i < kPanelRecDepth; ++i) mbar_init(&S.rbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
     unsigned sweep_base = 0;  // bulk loads issued per stage ring so far (all samples of this CTA)
+    unsigned rec_base = 0;    // row records loaded so far
+    unsigned char *recs = smraw + Q.o_rec;
 
     for (long long s = blockIdx.x; s < A.N; s += gridDim.x) {
         // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu)
@@ -181,38 +215,40 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         const double E = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
         const double nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
         const Lame mat = lame_from_E_nu(E, nu);
+        PTL_DECL;
 
         // ---------------- reset: window and rhs ring to zero, ring constants, slot tables
         {
             double2 *w2 = reinterpret_cast<double2 *>(win);
-            const int nz = (dbase(NB1) + NB1) * 32;  // window blocks + rhs ring, 32 double2 per block
+            const int nz = (dbase(NB1) + NB2) * 32;  // window blocks + rhs ring, 32 double2 per block
             for (int i = tid; i < nz; i += kPanelNT) w2[i] = make_double2(0.0, 0.0);
             if (tid == 0) {
                 ke[Q.R * 36] = 0.0;
                 ke[Q.R * 36 + 1] = 1.0;
                 S.flag = 0;
             }
-            if (tid <= NB1) S.colslot[0][tid] = 0;
+            if (tid <= NB2) S.colslot[0][tid] = 0;
         }
         __syncthreads();
 
-        int ecomp = 0;         // element matrices computed so far (assembling warps)
-        double gacc = 0.0;     // warp 0: partial sum of G[g] over this lane's columns
-        // Element matrices of the next batch into the ring: thread = (element, Gauss point), the four
-        // Gauss-point contributions are summed by two shuffles (src/mat_subroutine_tf.py:23-110: shape
-        // functions, material subroutine at the zero predictor, kt += dvol B^T Ct B).  Warps 1..4.
-        auto element_batch = [&](int tq) {
-            const int k = ecomp + (tq >> 2), gp = tq & 3;
+        double gacc = 0.0;  // warp 0: partial sum of G[g] over this lane's columns
+        // Element matrices into the ring: lane = (element, Gauss point), the four Gauss-point contributions
+        // are summed by two shuffles (src/mat_subroutine_tf.py:23-110: shape functions, material
+        // subroutine at the zero predictor, kt += dvol B^T Ct B).  k0: first element of this warp's eight.
+        // Element matrices into the ring: lane = (element, Gauss point), the four Gauss-point contributions
+        // are summed by two shuffles (src/mat_subroutine_tf.py:23-110: shape functions, material
+        // subroutine at the zero predictor, kt += dvol B^T Ct B).  Elements k0 + (lane >> 2) < kend of the
+        // first-use order, nodal coordinates at xy8[8 * (lane >> 2)].
+        auto element_batch = [&](int k0, int kend, const double *xy8) {
+            const int k = k0 + (lane >> 2), gp = lane & 3;
             double kev[36];
 #pragma unroll
             for (int q = 0; q < 36; ++q) kev[q] = 0.0;
-            if (k < M.nele) {
-                const int e = Q.eord[k];
+            if (k < kend) {
                 double xl[4], yl[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    const int nd = M.ien[4 * e + a];
-                    const double2 xy = *reinterpret_cast<const double2 *>(M.coord + 2 * nd);
+                    const double2 xy = reinterpret_cast<const double2 *>(xy8 + 8 * (lane >> 2))[a];
                     xl[a] = xy.x;
                     yl[a] = xy.y;
                 }
@@ -228,125 +264,106 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                 kev[q] += __shfl_xor_sync(kFull, kev[q], 1);
                 kev[q] += __shfl_xor_sync(kFull, kev[q], 2);
             }
-            if (k < M.nele) {
+            if (k < kend) {
                 double *dst = ke + (k % Q.R) * 36;
 #pragma unroll
                 for (int q = 0; q < 36; ++q)
                     if ((q & 3) == gp) dst[q] = kev[q];
             }
         };
-        // Block row q enters the window (warps 1..7, tq = tid - 32): clear its blocks, fetch its
-        // right-hand-side block, make sure its element matrices exist, gather.  slots == nullptr: the
-        // initial rows, block (q, q-d) sits in slot q-d of diagonal d.
-        auto fresh_row = [&](int q, const int *slots, int rslot, int tq) {
-            for (int idx = tq; idx < (NB + 2) * 32; idx += kPanelAsm) {
-                const int blk = idx >> 5, l = idx & 31;
-                if (blk <= NB) {
-                    if (q - blk >= 0) {
-                        const int sl = slots ? slots[blk] : q - blk;
-                        reinterpret_cast<double2 *>(win + (dbase(blk) + sl) * 64)[l] = make_double2(0.0, 0.0);
-                    }
-                } else {
-                    double2 v = make_double2(0.0, 0.0);
-                    if (q < NQ) v = reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64)[l];
-                    reinterpret_cast<double2 *>(rhs + rslot * 64)[l] = v;
+        // LDL^T of the diagonal block (p, p) and the inverse of its unit factor, by one warp: every lane
+        // factors the 36 entries redundantly in registers (no exchange on the pivot chain), lane j < 8 then
+        // forms column j of the inverse and stores it as row j of the transposed block stg[c][k] = Minv[k][c].
+        auto diag_factor = [&](const double *D, double *stg, double *rdo) {
+            double a[36];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; j += 2) {
+                    const double2 v = reinterpret_cast<const double2 *>(D + i * 8)[j >> 1];
+                    a[tri(i, j)] = v.x;
+                    if (j + 1 <= i) a[tri(i, j + 1)] = v.y;
+                }
+            double rdv[8];
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double d = a[tri(k, k)];
+                bad |= !(d > 0.0 && d < 1.0e300);
+                rdv[k] = fast_rcp3(d);
+#pragma unroll
+                for (int j = k + 1; j < 8; ++j) {
+                    const double ljk = a[tri(j, k)] * rdv[k];
+#pragma unroll
+                    for (int i = j; i < 8; ++i) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
+                    a[tri(j, k)] = ljk;  // rows i > j of column k stay unscaled until their own turn
                 }
             }
-            if (q < NQ) {
-                const int need = Q.eneed[q];
-                while (ecomp < need) {
-                    if (tq < 4 * kPanelEB) element_batch(tq);
-                    ecomp += kPanelEB;
-                }
+            if (bad && lane == 0) S.flag = 1;
+            const int j = lane & 7;
+            double m[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) acc = fma(a[tri(i, k)], m[k], acc);  // m[k] = 0 for k < j
+                m[i] = (i > j) ? -acc : m[i];
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kPanelAsm) : "memory");
-            if (q < NQ) {
-                const int i1 = Q.gptr[q + 1];
-                for (int i = Q.gptr[q] + tq; i < i1; i += kPanelAsm) {
-                    const int dst = Q.gdst[i];
-                    const ushort4 sr = Q.gsrc[i];
-                    const double v = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
-                    const int d = dst >> 6;
-                    const int sl = slots ? slots[d] : q - d;
-                    win[(dbase(d) + sl) * 64 + (dst & 63)] = v;
-                }
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2)
+                    reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
+            } else if (lane == 8) {
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) reinterpret_cast<double2 *>(rdo)[k >> 1] = make_double2(rdv[k], rdv[k + 1]);
             }
         };
 
-        // ---------------- the first NB+1 block rows fill the window
-        if (warp > 0) {
-            for (int q = 0; q <= NB; ++q) {
-                fresh_row(q, nullptr, q, tid - 32);
-                asm volatile("bar.sync 1, %0;" ::"n"(kPanelAsm) : "memory");  // ring slots may be reused by the next batch
+        // ---------------- the first NB+1 block rows fill the window (all warps, records read from global;
+        //                  block (q, q-d) in slot q-d).  Meanwhile the records of the next rows are on their way.
+        const int nrec = (NQ > NB1) ? NQ - NB1 : 0;  // rows that enter during the panel loop
+        if (tid == 7 * 32) {
+            for (int j = 0; j < kPanelRecDepth && j < nrec; ++j) {
+                const int sl = (int)((rec_base + j) % kPanelRecDepth);
+                mbar_expect_tx(&S.rbar[sl], Q.rec_stride);
+                bulk_load(recs + sl * Q.rec_stride, Q.rec + (size_t)(NB1 + j) * Q.rec_stride, Q.rec_stride, &S.rbar[sl]);
             }
         }
+        for (int q = 0; q <= NB && q < NQ; ++q) {
+            const unsigned char *rc = Q.rec + (size_t)q * Q.rec_stride;
+            const int4 hd = *reinterpret_cast<const int4 *>(rc);  // new elements, entries, first new element
+            for (int k0 = 8 * warp; k0 < hd.x; k0 += 8 * kPanelNW)
+                element_batch(hd.z + k0, hd.z + hd.x, reinterpret_cast<const double *>(rc + Q.rec_o_coord) + 8 * k0);
+            if (tid < 32) reinterpret_cast<double2 *>(rhs + q * 64)[tid] = reinterpret_cast<const double2 *>(rc + 16)[tid];
+            __syncthreads();
+            const ushort4 *src = reinterpret_cast<const ushort4 *>(rc + Q.rec_o_src);
+            const unsigned short *dstp = reinterpret_cast<const unsigned short *>(rc + Q.rec_o_dst);
+            for (int i = tid; i < hd.y; i += kPanelNT) {
+                const int dst = dstp[i];
+                const ushort4 sr = src[i];
+                const int d = dst >> 6;
+                win[(dbase(d) + q - d) * 64 + (dst & 63)] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+            }
+            __syncthreads();  // the next row's element matrices may overwrite ring slots this row has just read
+        }
+        if (warp == 6) diag_factor(win, lst, S.rd[0]);  // block (0, 0): diagonal 0, slot 0
         __syncthreads();
+        PTL(0);
 
         // ---------------- panels
-        int rslot = 0;  // p mod (NB+1): slot of panel p in the rhs ring
+        int rslot = 0;  // p mod (NB+2): slot of panel p in the rhs ring
         for (int p = 0; p < NQ; ++p) {
-            const int *cs = S.colslot[p & 1];
-            double *stg = lst + (p & 1) * LPB;  // staging panel: [0] inverse unit factor^T, [1..NB] L^T blocks, [NB+1] rhs
-            // ---- phase A: warp 0 factors the diagonal block; warps 1..7 bring in block row p+NB
-            //      (slots of panel p-1, which the trailing update has just finished reading)
-            if (warp == 0) {
-                if (MODE > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                const double *D = win + (dbase(0) + cs[0]) * 64;
-                double a[36];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) a[tri(i, j)] = D[i * 8 + j];
-                double rdv[8];
-                int bad = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const double d = a[tri(k, k)];
-                    bad |= !(d > 0.0 && d < 1.0e300);
-                    rdv[k] = fast_rcp3(d);
-#pragma unroll
-                    for (int j = k + 1; j < 8; ++j) {
-                        const double ljk = a[tri(j, k)] * rdv[k];
-#pragma unroll
-                        for (int i = j; i < 8; ++i) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
-                        a[tri(j, k)] = ljk;  // rows i > j of column k stay unscaled until their own turn
-                    }
-                }
-                if (bad && lane == 0) S.flag = 1;
-                // inverse of the unit lower factor, column by column; stored transposed ([c][k] = Minv[k][c])
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        double m[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                        for (int i = j + 1; i < 8; ++i) {
-                            double acc = 0.0;
-#pragma unroll
-                            for (int k = j; k < i; ++k) acc = fma(a[tri(i, k)], m[k], acc);
-                            m[i] = -acc;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; i += 2)
-                            reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; k += 2)
-                        reinterpret_cast<double2 *>(S.rd)[k >> 1] = make_double2(rdv[k], rdv[k + 1]);
-                }
-            } else if (p > 0) {
-                int rs = rslot - 1;
-                rs += (rs < 0) ? NB1 : 0;
-                fresh_row(p + NB, S.colslot[(p - 1) & 1], rs, tid - 32);
-            }
-            __syncthreads();
-
-            // ---- phase B: V = X L11^-T for the blocks below (in place), scaled copy to the staging panel
-            {
+            const int par = p & 1;
+            const int *cs = S.colslot[par];
+            double *stg = lst + par * LPB;  // staging panel: [0] inverse unit factor^T, [1..NB] L^T blocks, [NB+1] rhs
+            const double2 r2 = reinterpret_cast<const double2 *>(S.rd[par])[t];
+            // ---- phase B: V = X L11^-T for the blocks below the diagonal block (in place) and the
+            //      right-hand-side block; the scaled copy goes to the staging panel
+            if (warp < kPanelUpdW) {
                 const double2 mi = make_double2(stg[(2 * t) * 8 + g], stg[(2 * t + 1) * 8 + g]);  // Minv[g][2t..2t+1]
-                const double2 r2 = reinterpret_cast<const double2 *>(S.rd)[t];
-                for (int b = warp; b <= NB; b += kPanelNW) {  // b = 0: right-hand sides, else block row p+b
+                for (int b = warp; b <= NB; b += kPanelUpdW) {  // b = 0: right-hand sides, else block row p+b
                     double2 *X = reinterpret_cast<double2 *>(b ? win + (dbase(b) + cs[b]) * 64 : rhs + rslot * 64);
                     const double2 xv = X[lane];
                     double2 v = make_double2(0.0, 0.0);
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                         Lt[(2 * t) * 8 + g] = l.x;
                         Lt[(2 * t + 1) * 8 + g] = l.y;
                     }
-                    if (b == 0) {  // warp 0: strains / node rows against the load row, G[g] += sum_c V[g][c] L[0][c]
+                    if (b == 0) {  // warp 0: strain rows against the load row, G[g] += sum_c V[g][c] L[0][c]
                         const double lfx = __shfl_sync(kFull, l.x, t), lfy = __shfl_sync(kFull, l.y, t);
                         gacc = fma(v.x, lfx, fma(v.y, lfy, gacc));
                         if (p == NQ - 1 && g == 0) {
@@ -367,63 +384,158 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                         }
                     }
                 }
-                if (tid <= NB1) {  // slot tables of panel p+1: (p+1) mod (NB+1-d)
-                    int v = cs[tid] + 1;
-                    v = (v >= NB1 - tid) ? 0 : v;
-                    S.colslot[(p + 1) & 1][tid] = (tid <= NB) ? v : 0;
-                }
                 if (MODE > 0) fence_async_smem();
+            } else if (warp == 7 && lane <= NB2) {  // slot tables of panel p+1: (p+1) mod (NB+2-d)
+                const int v = cs[lane] + 1;
+                S.colslot[par ^ 1][lane] = (lane <= NB && v < NB2 - lane) ? v : 0;
             }
+            PTL(1);
             __syncthreads();
+            PTL(2);
 
-            // ---- phase C: trailing update C(I,J) -= L_I V_J^T; thread 0 first sends the staged panel to HBM
-            {
-                if (MODE > 0 && tid == 0) bulk_store(lws + (size_t)p * LPB, stg, LPB * 8);
-                const double2 r2 = reinterpret_cast<const double2 *>(S.rd)[t];
-                int lastI = -1;
-                double2 a = make_double2(0.0, 0.0);
-                const int k1 = Q.kstart[warp + 1];
-                for (int k = Q.kstart[warp]; k < k1; ++k) {
-                    const int ub = Q.ub[k], I = ub >> 8, J = ub & 255;
-                    if (I != lastI) {
-                        const double2 v = reinterpret_cast<const double2 *>(
-                            I <= NB ? win + (dbase(I) + cs[I]) * 64 : rhs + rslot * 64)[lane];
-                        a = make_double2(-v.x * r2.x, -v.y * r2.y);
-                        lastI = I;
-                    }
-                    const double2 bv = reinterpret_cast<const double2 *>(win + (dbase(J) + cs[J]) * 64)[lane];
-                    double2 *C;
+            // ---- phase C
+            if (warp < kPanelUpdW) {
+                // trailing update C(I,J) -= L_I V_J^T.  Lane i works out the shared-memory offsets of this
+                // warp's i-th block; the loop fetches the next block's fragments while the current MMAs run.
+                const int k0 = Q.kstart[warp], cnt = Q.kstart[warp + 1] - k0;
+                unsigned oA = 0, oB = 0, oC = 0;
+                if (lane < cnt) {
+                    const int ub = Q.ub[k0 + lane], I = ub >> 8, J = ub & 255;
+                    oB = Q.o_win + (dbase(J) + cs[J]) * 512;
                     if (I <= NB) {
-                        const int d = I - J, m = NB1 - d;
-                        int sl = cs[d] + J;
-                        sl -= (sl >= m) ? m : 0;
-                        C = reinterpret_cast<double2 *>(win + (dbase(d) + sl) * 64);
+                        const int d = I - J;
+                        oA = Q.o_win + (dbase(I) + cs[I]) * 512;
+                        oC = Q.o_win + (dbase(d) + wrap(cs[d] + J, NB2 - d)) * 512;
                     } else {
-                        int sl = rslot + J;
-                        sl -= (sl >= NB1) ? NB1 : 0;
-                        C = reinterpret_cast<double2 *>(rhs + sl * 64);
+                        oA = Q.o_rhs + rslot * 512;
+                        oC = Q.o_rhs + wrap(rslot + J, NB2) * 512;
                     }
-                    double2 c = C[lane];
-                    block_mma<DMMA>(c, a, bv, lane);
-                    C[lane] = c;
+                }
+                // two blocks per trip, their MMA chains interleaved; the fragments of the next pair are fetched
+                // behind the MMAs and the results stored last, so no instruction waits on the MMA it follows
+                unsigned cA0 = __shfl_sync(kFull, oA, 0), cB0 = __shfl_sync(kFull, oB, 0), cC0 = __shfl_sync(kFull, oC, 0);
+                unsigned cA1 = __shfl_sync(kFull, oA, 1), cB1 = __shfl_sync(kFull, oB, 1), cC1 = __shfl_sync(kFull, oC, 1);
+                double2 va0 = make_double2(0.0, 0.0), vb0 = va0, vc0 = va0, va1 = va0, vb1 = va0, vc1 = va0;
+                if (cnt > 0) {
+                    va0 = ldv(cA0);
+                    vb0 = ldv(cB0);
+                    vc0 = ldv(cC0);
+                }
+                if (cnt > 1) {
+                    va1 = (cA1 != cA0) ? ldv(cA1) : va0;
+                    vb1 = ldv(cB1);
+                    vc1 = ldv(cC1);
+                }
+                for (int i = 0; i < cnt; i += 2) {
+                    const bool two = i + 1 < cnt;
+                    const double2 a0 = make_double2(-va0.x * r2.x, -va0.y * r2.y);
+                    const double2 a1 = make_double2(-va1.x * r2.x, -va1.y * r2.y);
+                    if (DMMA) {
+                        dmma884(vc0.x, vc0.y, a0.x, vb0.x);
+                        if (two) dmma884(vc1.x, vc1.y, a1.x, vb1.x);
+                        dmma884(vc0.x, vc0.y, a0.y, vb0.y);
+                        if (two) dmma884(vc1.x, vc1.y, a1.y, vb1.y);
+                    } else {
+                        block_mma<false>(vc0, a0, vb0, lane);
+                        if (two) block_mma<false>(vc1, a1, vb1, lane);
+                    }
+                    unsigned nA0 = cA0, nB0 = cB0, nC0 = cC0, nA1 = cA1, nB1 = cB1, nC1 = cC1;
+                    double2 na0 = va0, nb0 = vb0, nc0 = vc0, na1 = va1, nb1 = vb1, nc1 = vc1;
+                    if (i + 2 < cnt) {
+                        nA0 = __shfl_sync(kFull, oA, i + 2);
+                        nB0 = __shfl_sync(kFull, oB, i + 2);
+                        nC0 = __shfl_sync(kFull, oC, i + 2);
+                        na0 = (nA0 != cA1) ? ldv(nA0) : va1;
+                        nb0 = ldv(nB0);
+                        nc0 = ldv(nC0);
+                        if (i + 3 < cnt) {
+                            nA1 = __shfl_sync(kFull, oA, i + 3);
+                            nB1 = __shfl_sync(kFull, oB, i + 3);
+                            nC1 = __shfl_sync(kFull, oC, i + 3);
+                            na1 = (nA1 != nA0) ? ldv(nA1) : na0;
+                            nb1 = ldv(nB1);
+                            nc1 = ldv(nC1);
+                        }
+                    }
+                    reinterpret_cast<double2 *>(smraw + cC0)[lane] = vc0;
+                    if (two) reinterpret_cast<double2 *>(smraw + cC1)[lane] = vc1;
+                    cA0 = nA0; cB0 = nB0; cC0 = nC0; cA1 = nA1; cB1 = nB1; cC1 = nC1;
+                    va0 = na0; vb0 = nb0; vc0 = nc0; va1 = na1; vb1 = nb1; vc1 = nc1;
+                }
+            } else if (warp == 6) {
+                // the finished panel leaves for HBM; then block (p+1, p+1) gets its update ahead of the others and
+                // is factored at once, so that the next panel's solve can start right after the barrier
+                if (MODE > 0 && lane == 0) {
+                    bulk_store(lws + (size_t)p * LPB, stg, LPB * 8);
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // panel p-1 has left the other buffer
+                }
+                if (p + 1 < NQ) {
+                    __syncwarp();
+                    const double2 v1 = reinterpret_cast<const double2 *>(win + (dbase(1) + cs[1]) * 64)[lane];
+                    double *Dn = win + (dbase(0) + wrap(cs[0] + 1, NB2)) * 64;
+                    double2 c = reinterpret_cast<double2 *>(Dn)[lane];
+                    block_mma<DMMA>(c, make_double2(-v1.x * r2.x, -v1.y * r2.y), v1, lane);
+                    reinterpret_cast<double2 *>(Dn)[lane] = c;
+                    __syncwarp();
+                    diag_factor(Dn, lst + (par ^ 1) * LPB, S.rd[par ^ 1]);
+                }
+            } else {
+                // block row q = p+NB+1 enters the window through the spare slots (block (q, q-d): slot of
+                // relative column NB+1-d): clear, right-hand-side block, element matrices, gather -- all from
+                // the row's record, which a bulk copy brought into shared memory several panels ago
+                const int q = p + NB1;
+                const double2 z2 = make_double2(0.0, 0.0);
+                for (int d = 0; d <= NB; ++d)
+                    reinterpret_cast<double2 *>(win + (dbase(d) + wrap(cs[d] + NB1 - d, NB2 - d)) * 64)[lane] = z2;
+                double2 *rdst = reinterpret_cast<double2 *>(rhs + wrap(rslot + NB1, NB2) * 64);
+                if (q < NQ) {
+                    const unsigned use = rec_base + (unsigned)p;
+                    const int sl = (int)(use % kPanelRecDepth);
+                    const unsigned char *rc = recs + sl * Q.rec_stride;
+                    mbar_wait(&S.rbar[sl], (use / kPanelRecDepth) & 1u);
+                    const int4 hd = *reinterpret_cast<const int4 *>(rc);
+                    rdst[lane] = reinterpret_cast<const double2 *>(rc + 16)[lane];
+                    for (int k0 = 0; k0 < hd.x; k0 += 8)
+                        element_batch(hd.z + k0, hd.z + hd.x, reinterpret_cast<const double *>(rc + Q.rec_o_coord) + 8 * k0);
+                    __syncwarp();
+                    const ushort4 *src = reinterpret_cast<const ushort4 *>(rc + Q.rec_o_src);
+                    const unsigned short *dstp = reinterpret_cast<const unsigned short *>(rc + Q.rec_o_dst);
+                    for (int i = lane; i < hd.y; i += 32) {
+                        const int dst = dstp[i];
+                        const ushort4 sr = src[i];
+                        const int d = dst >> 6;
+                        win[(dbase(d) + wrap(cs[d] + NB1 - d, NB2 - d)) * 64 + (dst & 63)] =
+                            ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+                    }
+                    __syncwarp();
+                    if (lane == 0 && p + kPanelRecDepth < nrec) {  // this slot's next tenant
+                        mbar_expect_tx(&S.rbar[sl], Q.rec_stride);
+                        bulk_load(recs + sl * Q.rec_stride, Q.rec + (size_t)(q + kPanelRecDepth) * Q.rec_stride, Q.rec_stride,
+                                  &S.rbar[sl]);
+                    }
+                } else {
+                    rdst[lane] = z2;
                 }
             }
+            PTL(3);
             __syncthreads();
-            rslot = (rslot + 1 == NB1) ? 0 : rslot + 1;
+            PTL(4);
+            rslot = (rslot + 1 == NB2) ? 0 : rslot + 1;
         }
 
         // ---------------- observations: y from the last diagonal block, strains from the accumulated
         //                  products, h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
         const double *stgl = lst + ((NQ - 1) & 1) * LPB;  // last panel: [c][k] = Minv[k][c]
+        const double *rdl = S.rd[(NQ - 1) & 1];
+        if (MODE > 0 && tid == 6 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (warp == 0) {
-            if (MODE > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             gacc += __shfl_xor_sync(kFull, gacc, 1);
             gacc += __shfl_xor_sync(kFull, gacc, 2);
             if (t == 0) S.G[g] = gacc;
             // D^-1 L11^-1 e_j for the observed node's dofs j (their unit vectors start in the last panel)
             if (lane < 16) {
                 const int k = lane >> 3, c = lane & 7, j = Q.obs_loc[k];
-                S.nodeL[lane] = (j >= 0) ? stgl[j * 8 + c] * S.rd[c] : 0.0;
+                S.nodeL[lane] = (j >= 0) ? stgl[j * 8 + c] * rdl[c] : 0.0;
             }
         }
         __syncthreads();
@@ -492,12 +604,14 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     }
                 }
             }
-            // ---------------- reverse pass: x_p = Minv_p^T (W Lrhs_p - sum_d x_(p+d) L_(p+d,p)), panels descending
-            double *stage0 = win;                                   // bulk-load ring (window + rhs ring are free now)
-            double *xr = ke;                                        // NB+1 solution blocks [v][k]
-            double *part = ke + NB1 * 64;                           // 8 partial products
+            // ---------------- reverse pass: x_p = Minv_p^T (W Lrhs_p - sum_d x_(p+d) L_(p+d,p)), panels descending.
+            //   Warp 0 finishes panel p (its products with x_(p+2..) were formed one step earlier), warps 1..7
+            //   form the products of panel p-1 with the blocks that are already final: one barrier per panel.
+            double *stage0 = win;                 // bulk-load ring (window + rhs ring are free now)
+            double *xr = ke;                      // NB+1 solution blocks [v][k]
+            double *part = ke + NB1 * 64;         // [2][8] partial products, by panel parity
             const int NS = Q.stages;
-            for (int i = tid; i < NB1 * 64; i += kPanelNT) xr[i] = 0.0;
+            for (int i = tid; i < (NB1 + 2 * kPanelNW) * 64; i += kPanelNT) xr[i] = 0.0;
             fence_async_smem();
             __syncthreads();
             if (tid == 0) {
@@ -507,35 +621,28 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     bulk_load(stage0 + st * LPB, lws + (size_t)(NQ - 1 - i) * LPB, LPB * 8, &S.bar[st]);
                 }
             }
+            PTL(7);
             int xs = (NQ - 1) % NB1;  // slot of panel p in the solution ring
             for (int i = 0; i < NQ; ++i) {
                 const int p = NQ - 1 - i;
                 const unsigned use = sweep_base + i;
-                const int st = (int)(use % NS);
-                const double *pan = stage0 + st * LPB;
-                mbar_wait(&S.bar[st], (use / NS) & 1u);
-                double2 c = make_double2(0.0, 0.0);
-                for (int b = warp; b <= NB; b += kPanelNW) {
-                    double2 a;
-                    if (b == 0) {
-                        a = reinterpret_cast<const double2 *>(S.W)[lane];
-                    } else {
-                        int sl = xs + b;
-                        sl -= (sl >= NB1) ? NB1 : 0;
-                        a = reinterpret_cast<const double2 *>(xr + sl * 64)[lane];
+                if (warp == 0) {
+                    const int st = (int)(use % NS);
+                    const double *pan = stage0 + st * LPB;
+                    mbar_wait(&S.bar[st], (use / NS) & 1u);
+                    double2 c = make_double2(0.0, 0.0), c2 = c;
+                    block_mma<DMMA>(c, reinterpret_cast<const double2 *>(S.W)[lane],
+                                    reinterpret_cast<const double2 *>(pan + (NB + 1) * 64)[lane], lane);
+                    {
+                        double2 a = reinterpret_cast<const double2 *>(xr + wrap(xs + 1, NB1) * 64)[lane];
                         a.x = -a.x;
                         a.y = -a.y;
+                        block_mma<DMMA>(c2, a, reinterpret_cast<const double2 *>(pan + 64)[lane], lane);
                     }
-                    const double2 bv = reinterpret_cast<const double2 *>(pan + (b ? b : NB + 1) * 64)[lane];
-                    block_mma<DMMA>(c, a, bv, lane);
-                }
-                reinterpret_cast<double2 *>(part + warp * 64)[lane] = c;
-                __syncthreads();
-                if (warp == 0) {
-                    double2 d = make_double2(0.0, 0.0);
+                    double2 d = make_double2(c.x + c2.x, c.y + c2.y);
 #pragma unroll
-                    for (int w = 0; w < kPanelNW; ++w) {
-                        const double2 q = reinterpret_cast<const double2 *>(part + w * 64)[lane];
+                    for (int w = 1; w < kPanelNW; ++w) {
+                        const double2 q = reinterpret_cast<const double2 *>(part + ((p & 1) * kPanelNW + w) * 64)[lane];
                         d.x += q.x;
                         d.y += q.y;
                     }
@@ -549,15 +656,29 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     block_mma<DMMA>(x, d, mi, lane);
                     reinterpret_cast<double2 *>(xr + xs * 64)[lane] = x;
                     if (g < NV) *reinterpret_cast<double2 *>(xws + (size_t)g * Q.npad + 8 * p + 2 * t) = x;
+                } else if (p > 0) {
+                    const int st = (int)((use + 1) % NS);
+                    const double *pan = stage0 + st * LPB;
+                    mbar_wait(&S.bar[st], ((use + 1) / NS) & 1u);
+                    double2 c = make_double2(0.0, 0.0);
+                    for (int b = 1 + warp; b <= NB; b += kPanelNW - 1) {  // block rows (p-1)+b, b >= 2
+                        double2 a = reinterpret_cast<const double2 *>(xr + wrap(xs + b - 1, NB1) * 64)[lane];
+                        a.x = -a.x;
+                        a.y = -a.y;
+                        block_mma<DMMA>(c, a, reinterpret_cast<const double2 *>(pan + b * 64)[lane], lane);
+                    }
+                    reinterpret_cast<double2 *>(part + (((p - 1) & 1) * kPanelNW + warp) * 64)[lane] = c;
                 }
                 __syncthreads();
                 if (tid == 0 && i + NS < NQ) {
+                    const int st = (int)(use % NS);
                     mbar_expect_tx(&S.bar[st], LPB * 8);
                     bulk_load(stage0 + st * LPB, lws + (size_t)(p - NS) * LPB, LPB * 8, &S.bar[st]);
                 }
                 xs = (xs == 0) ? NB : xs - 1;
             }
             sweep_base += (unsigned)NQ;
+            PTL(8);
 
             // ---------------- element-wise contraction -psi^T (dK/dp) u + explicit dh/dp, chained to x
             constexpr int NADJ = NV - 1;
@@ -648,7 +769,10 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         }
         __syncthreads();
         if (tid == 0 && A.status) A.status[s] = S.flag;
+        rec_base += (unsigned)nrec;
         __syncthreads();
+        PTL(9);
+        PTL_FLUSH;
     }
 }
 
