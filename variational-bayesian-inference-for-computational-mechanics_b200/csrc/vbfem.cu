@@ -1216,11 +1216,11 @@ struct PanelPlan {
     int n = 0, off = 0, npad = 0, NQ = 0, NB = 0, R = 0, nub = 0, nele = 0;
     int obs_loc[2] = {-1, -1};
     int kstart[kPanelNW + 1] = {0};
-    int o_win = 0, o_rhs = 0, o_lst = 0, o_ke = 0, smem_bytes = 0, stages = 0;
+    int o_win = 0, o_rhs = 0, o_lst = 0, o_ke = 0, o_lneg = 0, smem_bytes = 0, stages = 0;
     std::vector<int> gptr, eneed, eord, elm;
     std::vector<double> ecoord;
     std::vector<unsigned char> rec;  // row records (PanelModel::rec)
-    int rec_stride = 0, rec_o_coord = 0, rec_o_src = 0, rec_o_dst = 0, o_rec = 0;
+    int rec_stride = 0, rec_o_src = 0, rec_o_dst = 0, o_rec = 0;
     std::vector<unsigned short> gdst, gsrc, ub;  // gsrc: four entries per target
     std::vector<double> rhs0;
 };
@@ -1309,10 +1309,12 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
         for (int e = 0; e < ne; ++e)
             if (last[e] >= 0) minpos[last[e]] = std::min(minpos[last[e]], pos[e]);
         for (int q = P.NQ - 1; q >= 0; --q) minpos[q] = std::min(minpos[q], minpos[q + 1]);
-        // row q brings exactly the elements it is the first to need
-        int R = kPanelEB;
-        for (int q = 0; q < P.NQ; ++q)
-            if (minpos[q] < P.eneed[q]) R = std::max(R, P.eneed[q] - minpos[q]);
+        // the element matrices of row q are fetched into the ring kPanelRecDepth rows ahead of the gather
+        int R = P.eneed[std::min(NB, P.NQ - 1)];
+        for (int q = 0; q < P.NQ; ++q) {
+            const int ahead = P.eneed[std::min(q + kPanelRecDepth, P.NQ - 1)];
+            if (minpos[q] < ahead) R = std::max(R, ahead - minpos[q]);
+        }
         P.R = R;
     }
     if ((size_t)P.R * 36 + 2 > 65535) return no("element ring too large for 16-bit gather indices");
@@ -1397,8 +1399,8 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
             maxnew = std::max(maxnew, P.eneed[q] - (q ? P.eneed[q - 1] : 0));
             maxcnt = std::max(maxcnt, P.gptr[q + 1] - P.gptr[q]);
         }
-        P.rec_o_coord = 16 + 512;
-        P.rec_o_src = P.rec_o_coord + 64 * maxnew;
+        (void)maxnew;
+        P.rec_o_src = 16 + 512;
         P.rec_o_dst = P.rec_o_src + 8 * maxcnt;
         P.rec_stride = (P.rec_o_dst + 2 * maxcnt + 15) & ~15;
         P.rec.assign((size_t)P.NQ * P.rec_stride, 0);
@@ -1408,7 +1410,6 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
             int hd[4] = {nnew, cnt, e0, 0};
             memcpy(rc, hd, 16);
             memcpy(rc + 16, P.rhs0.data() + (size_t)q * 64, 512);
-            memcpy(rc + P.rec_o_coord, P.ecoord.data() + (size_t)8 * e0, (size_t)64 * nnew);
             memcpy(rc + P.rec_o_src, P.gsrc.data() + (size_t)4 * P.gptr[q], (size_t)8 * cnt);
             memcpy(rc + P.rec_o_dst, P.gdst.data() + P.gptr[q], (size_t)2 * cnt);
         }
@@ -1421,7 +1422,8 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
     P.o_lst = P.o_rhs + (NB + 2) * 512;
     P.o_ke = P.o_lst + 2 * LPBb;
     const int ke_bytes = std::max((P.R * 36 + 2) * 8, (NB1 + 2 * kPanelNW) * 512);
-    P.o_rec = P.o_ke + ((ke_bytes + 15) & ~15);
+    P.o_lneg = P.o_ke + ((ke_bytes + 15) & ~15);
+    P.o_rec = P.o_lneg + (NB + 3) * 512;
     P.smem_bytes = P.o_rec + kPanelRecDepth * P.rec_stride;
     P.stages = std::min(kPanelStagesMax, (nwin + NB + 2) * 512 / LPBb);
     if (P.stages < 2) return no("window too small for the reverse pass");
@@ -1745,8 +1747,8 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             Q.smem_bytes = P.smem_bytes;
             Q.stages = P.stages;
             Q.o_rec = P.o_rec;
+            Q.o_lneg = P.o_lneg;
             Q.rec_stride = P.rec_stride;
-            Q.rec_o_coord = P.rec_o_coord;
             Q.rec_o_src = P.rec_o_src;
             Q.rec_o_dst = P.rec_o_dst;
             for (int w = 0; w <= kPanelNW; ++w) Q.kstart[w] = P.kstart[w];
@@ -1772,6 +1774,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                 int rc2 = 0;
                 rc2 |= upload(h, P.rec, &Q.rec);
                 rc2 |= upload(h, P.eneed, &Q.eneed);
+                rc2 |= upload(h, P.ecoord, &Q.ecoord);
                 rc2 |= upload(h, P.elm, &Q.elm);
                 if (rc2) return -2;
                 h->block = kPanelNT;
@@ -1787,6 +1790,11 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                 h->dev_allocs.push_back(px);
                 Q.lws = (double *)pl;
                 Q.xws = (double *)px;
+                Q.kews_stride = 36LL * ne;
+                void *pk = nullptr;
+                CU(cudaMalloc(&pk, (size_t)grid * Q.kews_stride * sizeof(double)));
+                h->dev_allocs.push_back(pk);
+                Q.kews = (double *)pk;
                 h->variant = 3;
                 h->n_real = n;
                 guard.p = nullptr;

@@ -53,15 +53,19 @@ struct PanelModel {
     int obs_loc[2];            // row inside the last panel of the observed node's (x, y) dof, -1 if supported
     int o_win, o_rhs, o_lst, o_ke, smem_bytes;  // shared-memory offsets in bytes
     int stages;                // bulk-load ring of the reverse pass
-    int o_rec, rec_stride, rec_o_coord, rec_o_src, rec_o_dst;  // row-record ring in shared memory / record layout (bytes)
+    int o_lneg;                // NB+2 blocks: -L of the current panel, row major (block b: block row p+b; NB+1: rhs), then a dummy block
+    int o_rec, rec_stride, rec_o_src, rec_o_dst;  // row-record ring in shared memory / record layout (bytes)
     int kstart[kPanelNW + 1];  // update blocks [kstart[w], kstart[w+1]) belong to warp w < kPanelUpdW
     unsigned short ub[kPanelNBMax * (kPanelNBMax + 1) / 2 + kPanelNBMax];  // (I << 8) | J
     // Row record of block row q (rec_stride bytes, what the row needs to enter the window): int32 header
     // {new elements, gather entries, first new element (first-use order)}, the 8x8 right-hand-side block,
-    // the nodal coordinates [new][4][2] of the new elements, gather sources (ushort4: element-ring entries
-    // slot * 36 + tri, unused -> the zero entry) and gather targets (u16: d * 64 + g * 8 + c)
+    // gather sources (ushort4: element-ring entries slot * 36 + tri, unused -> the zero entry) and gather
+    // targets (u16: d * 64 + g * 8 + c)
     const unsigned char *rec;
     const int *eneed;            // [NQ] elements (first-use order) block row q needs
+    const double *ecoord;        // [nele][4][2] nodal coordinates of the elements in first-use order
+    double *kews;                // per-CTA scratch: the sample's element matrices [nele][36], first-use order
+    long long kews_stride;
     const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported
     double *lws;                 // per-CTA factor slab
     long long lws_stride;        // doubles
@@ -80,6 +84,7 @@ struct PanelSmem {
     double red[2 * 5 * kPanelNW];
     unsigned long long bar[kPanelStagesMax];
     unsigned long long rbar[kPanelRecDepth];
+    uint4 utab[kPanelUpdW][32];  // per update warp: shared-memory byte offsets (A, B, C) of its blocks in this panel
     int colslot[2][kPanelNBMax + 2];
     int flag;
 };
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
     double *rhs = reinterpret_cast<double *>(smraw + Q.o_rhs);  // NB+2 right-hand-side blocks
     double *lst = reinterpret_cast<double *>(smraw + Q.o_lst);  // two staging panels (transposed, scaled)
     double *ke = reinterpret_cast<double *>(smraw + Q.o_ke);    // R element matrices (36 each), then 0.0, 1.0
+    double *lneg = reinterpret_cast<double *>(smraw + Q.o_lneg);  // -L blocks of the current panel, then a dummy block
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int NB = Q.NB, NQ = Q.NQ, NB1 = NB + 1, NB2 = NB + 2, LPB = (NB + 2) * 64;  // LPB: doubles per stored panel
@@ -232,26 +238,23 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         __syncthreads();
 
         double gacc = 0.0;  // warp 0: partial sum of G[g] over this lane's columns
-        // Element matrices into the ring: lane = (element, Gauss point), the four Gauss-point contributions
-        // are summed by two shuffles (src/mat_subroutine_tf.py:23-110: shape functions, material
-        // subroutine at the zero predictor, kt += dvol B^T Ct B).  k0: first element of this warp's eight.
-        // Element matrices into the ring: lane = (element, Gauss point), the four Gauss-point contributions
-        // are summed by two shuffles (src/mat_subroutine_tf.py:23-110: shape functions, material
-        // subroutine at the zero predictor, kt += dvol B^T Ct B).  Elements k0 + (lane >> 2) < kend of the
-        // first-use order, nodal coordinates at xy8[8 * (lane >> 2)].
-        auto element_batch = [&](int k0, int kend, const double *xy8) {
-            const int k = k0 + (lane >> 2), gp = lane & 3;
-            double kev[36];
+        // (a) Per-element Q4 Gauss-point kernels of this sample, all warps, thread = element: shape functions,
+        // material subroutine at the zero predictor, kt += dvol B^T Ct B over the 2x2 rule
+        // (src/mat_subroutine_tf.py:23-110).  The 36 lower-triangle entries go to the CTA's scratch slab in
+        // first-use order; the panel loop pulls them into the shared-memory ring a few rows ahead of their use.
+        double *kews = Q.kews + (size_t)blockIdx.x * Q.kews_stride;
+        for (int k = tid; k < M.nele; k += kPanelNT) {
+            double xl[4], yl[4], kev[36];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double2 xy = reinterpret_cast<const double2 *>(Q.ecoord + (size_t)8 * k)[a];
+                xl[a] = xy.x;
+                yl[a] = xy.y;
+            }
 #pragma unroll
             for (int q = 0; q < 36; ++q) kev[q] = 0.0;
-            if (k < kend) {
-                double xl[4], yl[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double2 xy = reinterpret_cast<const double2 *>(xy8 + 8 * (lane >> 2))[a];
-                    xl[a] = xy.x;
-                    yl[a] = xy.y;
-                }
+#pragma unroll 1
+            for (int gp = 0; gp < 4; ++gp) {
                 ShapeQ4 sh;
                 shapef_q4(xl, yl, gp, M.thk, sh);
                 double sig[4];
@@ -259,18 +262,13 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                 mat_isotropic_plane_strain(mat, 0.0, 0.0, 0.0, sig, C);
                 accumulate_kt(sh, C, kev);
             }
+            double2 *dst = reinterpret_cast<double2 *>(kews + (size_t)36 * k);
 #pragma unroll
-            for (int q = 0; q < 36; ++q) {
-                kev[q] += __shfl_xor_sync(kFull, kev[q], 1);
-                kev[q] += __shfl_xor_sync(kFull, kev[q], 2);
-            }
-            if (k < kend) {
-                double *dst = ke + (k % Q.R) * 36;
-#pragma unroll
-                for (int q = 0; q < 36; ++q)
-                    if ((q & 3) == gp) dst[q] = kev[q];
-            }
-        };
+            for (int q = 0; q < 18; ++q) dst[q] = make_double2(kev[2 * q], kev[2 * q + 1]);
+        }
+        __threadfence_block();
+        asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what was just written
+        __syncthreads();
         // LDL^T of the diagonal block (p, p) and the inverse of its unit factor, by one warp: every lane
         // factors the 36 entries redundantly in registers (no exchange on the pivot chain), lane j < 8 then
         // forms column j of the inverse and stores it as row j of the transposed block stg[c][k] = Minv[k][c].
@@ -321,23 +319,28 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             }
         };
 
-        // ---------------- the first NB+1 block rows fill the window (all warps, records read from global;
-        //                  block (q, q-d) in slot q-d).  Meanwhile the records of the next rows are on their way.
+        // ---------------- the first NB+1 block rows fill the window (all warps, records and element matrices
+        //                  read from global; block (q, q-d) in slot q-d).  Meanwhile the records and element
+        //                  matrices of the next rows are on their way into shared memory.
         const int nrec = (NQ > NB1) ? NQ - NB1 : 0;  // rows that enter during the panel loop
-        if (tid == 7 * 32) {
-            for (int j = 0; j < kPanelRecDepth && j < nrec; ++j) {
-                const int sl = (int)((rec_base + j) % kPanelRecDepth);
-                mbar_expect_tx(&S.rbar[sl], Q.rec_stride);
-                bulk_load(recs + sl * Q.rec_stride, Q.rec + (size_t)(NB1 + j) * Q.rec_stride, Q.rec_stride, &S.rbar[sl]);
+        auto fetch_row = [&](int q, int sl) {  // one thread: row record + the element matrices the row is first to need
+            const int e0 = Q.eneed[q - 1], e1 = Q.eneed[q];
+            mbar_expect_tx(&S.rbar[sl], Q.rec_stride + 288 * (e1 - e0));
+            bulk_load(recs + sl * Q.rec_stride, Q.rec + (size_t)q * Q.rec_stride, Q.rec_stride, &S.rbar[sl]);
+            for (int k = e0; k < e1; ++k) bulk_load(ke + (k % Q.R) * 36, kews + (size_t)36 * k, 288, &S.rbar[sl]);
+        };
+        {
+            const int e1 = Q.eneed[NB < NQ ? NB : NQ - 1];
+            for (int i = tid; i < e1 * 18; i += kPanelNT) {
+                const int k = i / 18, j = i - 18 * k;
+                reinterpret_cast<double2 *>(ke + (k % Q.R) * 36)[j] = reinterpret_cast<const double2 *>(kews + (size_t)36 * k)[j];
             }
         }
+        __syncthreads();
         for (int q = 0; q <= NB && q < NQ; ++q) {
             const unsigned char *rc = Q.rec + (size_t)q * Q.rec_stride;
             const int4 hd = *reinterpret_cast<const int4 *>(rc);  // new elements, entries, first new element
-            for (int k0 = 8 * warp; k0 < hd.x; k0 += 8 * kPanelNW)
-                element_batch(hd.z + k0, hd.z + hd.x, reinterpret_cast<const double *>(rc + Q.rec_o_coord) + 8 * k0);
             if (tid < 32) reinterpret_cast<double2 *>(rhs + q * 64)[tid] = reinterpret_cast<const double2 *>(rc + 16)[tid];
-            __syncthreads();
             const ushort4 *src = reinterpret_cast<const ushort4 *>(rc + Q.rec_o_src);
             const unsigned short *dstp = reinterpret_cast<const unsigned short *>(rc + Q.rec_o_dst);
             for (int i = tid; i < hd.y; i += kPanelNT) {
@@ -346,8 +349,11 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                 const int d = dst >> 6;
                 win[(dbase(d) + q - d) * 64 + (dst & 63)] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
             }
-            __syncthreads();  // the next row's element matrices may overwrite ring slots this row has just read
         }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 7 * 32)  // ring slots of elements the first rows no longer need may now be overwritten
+            for (int j = 0; j < kPanelRecDepth && j < nrec; ++j) fetch_row(NB1 + j, (int)((rec_base + j) % kPanelRecDepth));
         if (warp == 6) diag_factor(win, lst, S.rd[0]);  // block (0, 0): diagonal 0, slot 0
         __syncthreads();
         PTL(0);
@@ -370,6 +376,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     block_mma<DMMA>(v, xv, mi, lane);
                     X[lane] = v;
                     const double2 l = make_double2(v.x * r2.x, v.y * r2.y);
+                    reinterpret_cast<double2 *>(lneg + (b ? b : NB + 1) * 64)[lane] = make_double2(-l.x, -l.y);
                     if (MODE > 0 || b == 0) {
                         double *Lt = stg + (b ? b : NB + 1) * 64;
                         Lt[(2 * t) * 8 + g] = l.x;
@@ -395,73 +402,74 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
 
             // ---- phase C
             if (warp < kPanelUpdW) {
-                // trailing update C(I,J) -= L_I V_J^T.  Lane i works out the shared-memory offsets of this
-                // warp's i-th block; the loop fetches the next block's fragments while the current MMAs run.
-                const int k0 = Q.kstart[warp], cnt = Q.kstart[warp + 1] - k0;
-                unsigned oA = 0, oB = 0, oC = 0;
-                if (lane < cnt) {
-                    const int ub = Q.ub[k0 + lane], I = ub >> 8, J = ub & 255;
-                    oB = Q.o_win + (dbase(J) + cs[J]) * 512;
-                    if (I <= NB) {
-                        const int d = I - J;
-                        oA = Q.o_win + (dbase(I) + cs[I]) * 512;
-                        oC = Q.o_win + (dbase(d) + wrap(cs[d] + J, NB2 - d)) * 512;
-                    } else {
-                        oA = Q.o_rhs + rslot * 512;
-                        oC = Q.o_rhs + wrap(rslot + J, NB2) * 512;
-                    }
-                }
-                // two blocks per trip, their MMA chains interleaved; the fragments of the next pair are fetched
-                // behind the MMAs and the results stored last, so no instruction waits on the MMA it follows
-                unsigned cA0 = __shfl_sync(kFull, oA, 0), cB0 = __shfl_sync(kFull, oB, 0), cC0 = __shfl_sync(kFull, oC, 0);
-                unsigned cA1 = __shfl_sync(kFull, oA, 1), cB1 = __shfl_sync(kFull, oB, 1), cC1 = __shfl_sync(kFull, oC, 1);
-                double2 va0 = make_double2(0.0, 0.0), vb0 = va0, vc0 = va0, va1 = va0, vb1 = va0, vc1 = va0;
-                if (cnt > 0) {
-                    va0 = ldv(cA0);
-                    vb0 = ldv(cB0);
-                    vc0 = ldv(cC0);
-                }
-                if (cnt > 1) {
-                    va1 = (cA1 != cA0) ? ldv(cA1) : va0;
-                    vb1 = ldv(cB1);
-                    vc1 = ldv(cC1);
-                }
-                for (int i = 0; i < cnt; i += 2) {
-                    const bool two = i + 1 < cnt;
-                    const double2 a0 = make_double2(-va0.x * r2.x, -va0.y * r2.y);
-                    const double2 a1 = make_double2(-va1.x * r2.x, -va1.y * r2.y);
-                    if (DMMA) {
-                        dmma884(vc0.x, vc0.y, a0.x, vb0.x);
-                        if (two) dmma884(vc1.x, vc1.y, a1.x, vb1.x);
-                        dmma884(vc0.x, vc0.y, a0.y, vb0.y);
-                        if (two) dmma884(vc1.x, vc1.y, a1.y, vb1.y);
-                    } else {
-                        block_mma<false>(vc0, a0, vb0, lane);
-                        if (two) block_mma<false>(vc1, a1, vb1, lane);
-                    }
-                    unsigned nA0 = cA0, nB0 = cB0, nC0 = cC0, nA1 = cA1, nB1 = cB1, nC1 = cC1;
-                    double2 na0 = va0, nb0 = vb0, nc0 = vc0, na1 = va1, nb1 = vb1, nc1 = vc1;
-                    if (i + 2 < cnt) {
-                        nA0 = __shfl_sync(kFull, oA, i + 2);
-                        nB0 = __shfl_sync(kFull, oB, i + 2);
-                        nC0 = __shfl_sync(kFull, oC, i + 2);
-                        na0 = (nA0 != cA1) ? ldv(nA0) : va1;
-                        nb0 = ldv(nB0);
-                        nc0 = ldv(nC0);
-                        if (i + 3 < cnt) {
-                            nA1 = __shfl_sync(kFull, oA, i + 3);
-                            nB1 = __shfl_sync(kFull, oB, i + 3);
-                            nC1 = __shfl_sync(kFull, oC, i + 3);
-                            na1 = (nA1 != nA0) ? ldv(nA1) : na0;
-                            nb1 = ldv(nB1);
-                            nc1 = ldv(nC1);
+                // trailing update C(I,J) -= L_I V_J^T.  Lane i works out the shared-memory offsets of this warp's
+                // i-th block into a small table (one broadcast load per block in the loop); odd counts are padded
+                // with a dummy block.  Two blocks per step with interleaved MMA chains, two steps per trip on
+                // alternating register sets: the next pair's fragments are fetched behind the MMAs, the results
+                // are stored last, and no register is ever copied.
+                const int k0 = Q.kstart[warp], cnt = Q.kstart[warp + 1] - k0, cnt2 = (cnt + 1) & ~1;
+                if (lane < cnt2) {
+                    uint4 o = make_uint4(Q.o_lneg, Q.o_lneg, Q.o_lneg + (NB + 2) * 512, 0);  // dummy: results to the spare block
+                    if (lane < cnt) {
+                        const int ub = Q.ub[k0 + lane], I = ub >> 8, J = ub & 255;
+                        o.x = Q.o_lneg + I * 512;
+                        o.y = Q.o_win + (dbase(J) + cs[J]) * 512;
+                        if (I <= NB) {
+                            const int d = I - J;
+                            o.z = Q.o_win + (dbase(d) + wrap(cs[d] + J, NB2 - d)) * 512;
+                        } else {
+                            o.z = Q.o_rhs + wrap(rslot + J, NB2) * 512;
                         }
                     }
-                    reinterpret_cast<double2 *>(smraw + cC0)[lane] = vc0;
-                    if (two) reinterpret_cast<double2 *>(smraw + cC1)[lane] = vc1;
-                    cA0 = nA0; cB0 = nB0; cC0 = nC0; cA1 = nA1; cB1 = nB1; cC1 = nC1;
-                    va0 = na0; vb0 = nb0; vc0 = nc0; va1 = na1; vb1 = nb1; vc1 = nc1;
+                    S.utab[warp][lane] = o;
                 }
+                __syncwarp();
+                const uint4 *tab = S.utab[warp];
+                const unsigned lo = 16u * lane;
+#define UPD_LOAD(X, k)                                                             \
+    do {                                                                           \
+        const uint4 t0_ = tab[k], t1_ = tab[(k) + 1];                              \
+        X##c0 = t0_.z + lo;                                                        \
+        X##c1 = t1_.z + lo;                                                        \
+        X##a0 = *reinterpret_cast<const double2 *>(smraw + t0_.x + lo);           \
+        X##b0 = *reinterpret_cast<const double2 *>(smraw + t0_.y + lo);           \
+        X##v0 = *reinterpret_cast<const double2 *>(smraw + X##c0);                \
+        X##a1 = *reinterpret_cast<const double2 *>(smraw + t1_.x + lo);           \
+        X##b1 = *reinterpret_cast<const double2 *>(smraw + t1_.y + lo);           \
+        X##v1 = *reinterpret_cast<const double2 *>(smraw + X##c1);                \
+    } while (0)
+#define UPD_MMA(X)                                         \
+    do {                                                   \
+        if (DMMA) {                                        \
+            dmma884(X##v0.x, X##v0.y, X##a0.x, X##b0.x);   \
+            dmma884(X##v1.x, X##v1.y, X##a1.x, X##b1.x);   \
+            dmma884(X##v0.x, X##v0.y, X##a0.y, X##b0.y);   \
+            dmma884(X##v1.x, X##v1.y, X##a1.y, X##b1.y);   \
+        } else {                                           \
+            block_mma<false>(X##v0, X##a0, X##b0, lane);   \
+            block_mma<false>(X##v1, X##a1, X##b1, lane);   \
+        }                                                  \
+    } while (0)
+#define UPD_STORE(X)                                                  \
+    do {                                                              \
+        *reinterpret_cast<double2 *>(smraw + X##c0) = X##v0;          \
+        *reinterpret_cast<double2 *>(smraw + X##c1) = X##v1;          \
+    } while (0)
+                unsigned Xc0, Xc1, Yc0, Yc1;
+                double2 Xa0, Xb0, Xv0, Xa1, Xb1, Xv1, Ya0, Yb0, Yv0, Ya1, Yb1, Yv1;
+                if (cnt2 > 0) UPD_LOAD(X, 0);
+                for (int i = 0; i < cnt2; i += 4) {
+                    UPD_MMA(X);
+                    if (i + 2 < cnt2) UPD_LOAD(Y, i + 2);
+                    UPD_STORE(X);
+                    if (i + 2 >= cnt2) break;
+                    UPD_MMA(Y);
+                    if (i + 4 < cnt2) UPD_LOAD(X, i + 4);
+                    UPD_STORE(Y);
+                }
+#undef UPD_LOAD
+#undef UPD_MMA
+#undef UPD_STORE
             } else if (warp == 6) {
                 // the finished panel leaves for HBM; then block (p+1, p+1) gets its update ahead of the others and
                 // is factored at once, so that the next panel's solve can start right after the barrier
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     const double2 v1 = reinterpret_cast<const double2 *>(win + (dbase(1) + cs[1]) * 64)[lane];
                     double *Dn = win + (dbase(0) + wrap(cs[0] + 1, NB2)) * 64;
                     double2 c = reinterpret_cast<double2 *>(Dn)[lane];
-                    block_mma<DMMA>(c, make_double2(-v1.x * r2.x, -v1.y * r2.y), v1, lane);
+                    block_mma<DMMA>(c, reinterpret_cast<const double2 *>(lneg + 64)[lane], v1, lane);
                     reinterpret_cast<double2 *>(Dn)[lane] = c;
                     __syncwarp();
                     diag_factor(Dn, lst + (par ^ 1) * LPB, S.rd[par ^ 1]);
@@ -495,9 +503,6 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     mbar_wait(&S.rbar[sl], (use / kPanelRecDepth) & 1u);
                     const int4 hd = *reinterpret_cast<const int4 *>(rc);
                     rdst[lane] = reinterpret_cast<const double2 *>(rc + 16)[lane];
-                    for (int k0 = 0; k0 < hd.x; k0 += 8)
-                        element_batch(hd.z + k0, hd.z + hd.x, reinterpret_cast<const double *>(rc + Q.rec_o_coord) + 8 * k0);
-                    __syncwarp();
                     const ushort4 *src = reinterpret_cast<const ushort4 *>(rc + Q.rec_o_src);
                     const unsigned short *dstp = reinterpret_cast<const unsigned short *>(rc + Q.rec_o_dst);
                     for (int i = lane; i < hd.y; i += 32) {
@@ -508,11 +513,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                             ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
                     }
                     __syncwarp();
-                    if (lane == 0 && p + kPanelRecDepth < nrec) {  // this slot's next tenant
-                        mbar_expect_tx(&S.rbar[sl], Q.rec_stride);
-                        bulk_load(recs + sl * Q.rec_stride, Q.rec + (size_t)(q + kPanelRecDepth) * Q.rec_stride, Q.rec_stride,
-                                  &S.rbar[sl]);
-                    }
+                    if (lane == 0 && p + kPanelRecDepth < nrec) fetch_row(q + kPanelRecDepth, sl);  // this slot's next tenant
                 } else {
                     rdst[lane] = z2;
                 }
