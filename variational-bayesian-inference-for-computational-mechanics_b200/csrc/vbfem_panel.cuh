@@ -75,6 +75,7 @@ struct PanelModel {
 
 struct PanelSmem {
     double rd[2][8];    // 1/d of the diagonal block, by panel parity
+    double minv[2][64]; // inverse of the diagonal block's unit factor, row major, by panel parity
     double W[64];       // [v][a]: weight of right-hand-side row a in the right-hand side of vector v
     double nodew[16];   // [v][2]: weight of the observed node's unit vectors
     double nodeL[16];   // [2][8]: D^-1 L11^-1 e_(observed dof) inside the last panel
@@ -205,22 +206,25 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
     unsigned char *recs = smraw + Q.o_rec;
 
     for (long long s = blockIdx.x; s < A.N; s += gridDim.x) {
-        // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu)
+        // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu), recomputed where needed (three
+        //                  places) instead of being carried through the panel loop in registers
         // src/data_generation_2sam_more_loss.py:181-186
-        double x0, x1;
-        if (A.mode & kElbo) {
-            // main_custom_training.py:199-209: theta = e * sqrt(sig2) + mu, flattened [B*S]
-            const long long j = A.j_begin + s;
-            const int bb = (int)(j / A.S), ss = (int)(j % A.S);
-            x0 = A.e[2 * ss] * sqrt(A.sig2[2 * bb]) + A.mu[2 * bb];
-            x1 = A.e[2 * ss + 1] * sqrt(A.sig2[2 * bb + 1]) + A.mu[2 * bb + 1];
-        } else {
-            x0 = A.x[2 * s];
-            x1 = A.x[2 * s + 1];
-        }
-        const double E = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
-        const double nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
-        const Lame mat = lame_from_E_nu(E, nu);
+        auto sample_material = [&](double &E, double &nu) {
+            double x0, x1;
+            if (A.mode & kElbo) {
+                // main_custom_training.py:199-209: theta = e * sqrt(sig2) + mu, flattened [B*S]
+                const long long j = A.j_begin + s;
+                const int bb = (int)(j / A.S), ss = (int)(j % A.S);
+                x0 = A.e[2 * ss] * sqrt(A.sig2[2 * bb]) + A.mu[2 * bb];
+                x1 = A.e[2 * ss + 1] * sqrt(A.sig2[2 * bb + 1]) + A.mu[2 * bb + 1];
+            } else {
+                x0 = A.x[2 * s];
+                x1 = A.x[2 * s + 1];
+            }
+            E = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
+            nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
+            return lame_from_E_nu(E, nu);
+        };
         PTL_DECL;
 
         // ---------------- reset: window and rhs ring to zero, ring constants, slot tables
@@ -243,6 +247,9 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         // (src/mat_subroutine_tf.py:23-110).  The 36 lower-triangle entries go to the CTA's scratch slab in
         // first-use order; the panel loop pulls them into the shared-memory ring a few rows ahead of their use.
         double *kews = Q.kews + (size_t)blockIdx.x * Q.kews_stride;
+        {
+        double E_, nu_;
+        const Lame mat = sample_material(E_, nu_);
         for (int k = tid; k < M.nele; k += kPanelNT) {
             double xl[4], yl[4], kev[36];
 #pragma unroll
@@ -266,13 +273,14 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
 #pragma unroll
             for (int q = 0; q < 18; ++q) dst[q] = make_double2(kev[2 * q], kev[2 * q + 1]);
         }
+        }
         __threadfence_block();
         asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what was just written
         __syncthreads();
         // LDL^T of the diagonal block (p, p) and the inverse of its unit factor, by one warp: every lane
         // factors the 36 entries redundantly in registers (no exchange on the pivot chain), lane j < 8 then
         // forms column j of the inverse and stores it as row j of the transposed block stg[c][k] = Minv[k][c].
-        auto diag_factor = [&](const double *D, double *stg, double *rdo) {
+        auto diag_factor = [&](const double *D, double *stg, double *rdo, double *mro) {
             double a[36];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -313,6 +321,8 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 8; i += 2)
                     reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mro[i * 8 + j] = m[i];  // row-major copy: the solve's B fragments
             } else if (lane == 8) {
 #pragma unroll
                 for (int k = 0; k < 8; k += 2) reinterpret_cast<double2 *>(rdo)[k >> 1] = make_double2(rdv[k], rdv[k + 1]);
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         __syncthreads();
         if (tid == 7 * 32)  // ring slots of elements the first rows no longer need may now be overwritten
             for (int j = 0; j < kPanelRecDepth && j < nrec; ++j) fetch_row(NB1 + j, (int)((rec_base + j) % kPanelRecDepth));
-        if (warp == 6) diag_factor(win, lst, S.rd[0]);  // block (0, 0): diagonal 0, slot 0
+        if (warp == 6) diag_factor(win, lst, S.rd[0], S.minv[0]);  // block (0, 0): diagonal 0, slot 0
         __syncthreads();
         PTL(0);
 
@@ -368,7 +378,8 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             // ---- phase B: V = X L11^-T for the blocks below the diagonal block (in place) and the
             //      right-hand-side block; the scaled copy goes to the staging panel
             if (warp < kPanelUpdW) {
-                const double2 mi = make_double2(stg[(2 * t) * 8 + g], stg[(2 * t + 1) * 8 + g]);  // Minv[g][2t..2t+1]
+                const double2 mi = reinterpret_cast<const double2 *>(S.minv[par])[lane];  // Minv[g][2t..2t+1]
+                const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
                 for (int b = warp; b <= NB; b += kPanelUpdW) {  // b = 0: right-hand sides, else block row p+b
                     double2 *X = reinterpret_cast<double2 *>(b ? win + (dbase(b) + cs[b]) * 64 : rhs + rslot * 64);
                     const double2 xv = X[lane];
@@ -377,10 +388,12 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     X[lane] = v;
                     const double2 l = make_double2(v.x * r2.x, v.y * r2.y);
                     reinterpret_cast<double2 *>(lneg + (b ? b : NB + 1) * 64)[lane] = make_double2(-l.x, -l.y);
-                    if (MODE > 0 || b == 0) {
-                        double *Lt = stg + (b ? b : NB + 1) * 64;
-                        Lt[(2 * t) * 8 + g] = l.x;
-                        Lt[(2 * t + 1) * 8 + g] = l.y;
+                    if (MODE > 0) {
+                        // the stored panel holds L^T blocks: I * L^T on the tensor core leaves the transposed block in
+                        // the (lane-contiguous) C fragment layout -- no bank-conflicted scatter
+                        double2 lt = make_double2(0.0, 0.0);
+                        block_mma<DMMA>(lt, idf, l, lane);
+                        reinterpret_cast<double2 *>(stg + (b ? b : NB + 1) * 64)[lane] = lt;
                     }
                     if (b == 0) {  // warp 0: strain rows against the load row, G[g] += sum_c V[g][c] L[0][c]
                         const double lfx = __shfl_sync(kFull, l.x, t), lfy = __shfl_sync(kFull, l.y, t);
@@ -403,73 +416,62 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             // ---- phase C
             if (warp < kPanelUpdW) {
                 // trailing update C(I,J) -= L_I V_J^T.  Lane i works out the shared-memory offsets of this warp's
-                // i-th block into a small table (one broadcast load per block in the loop); odd counts are padded
-                // with a dummy block.  Two blocks per step with interleaved MMA chains, two steps per trip on
-                // alternating register sets: the next pair's fragments are fetched behind the MMAs, the results
-                // are stored last, and no register is ever copied.
-                const int k0 = Q.kstart[warp], cnt = Q.kstart[warp + 1] - k0, cnt2 = (cnt + 1) & ~1;
-                if (lane < cnt2) {
-                    uint4 o = make_uint4(Q.o_lneg, Q.o_lneg, Q.o_lneg + (NB + 2) * 512, 0);  // dummy: results to the spare block
-                    if (lane < cnt) {
-                        const int ub = Q.ub[k0 + lane], I = ub >> 8, J = ub & 255;
-                        o.x = Q.o_lneg + I * 512;
-                        o.y = Q.o_win + (dbase(J) + cs[J]) * 512;
-                        if (I <= NB) {
-                            const int d = I - J;
-                            o.z = Q.o_win + (dbase(d) + wrap(cs[d] + J, NB2 - d)) * 512;
-                        } else {
-                            o.z = Q.o_rhs + wrap(rslot + J, NB2) * 512;
-                        }
+                // i-th block into a small table (one broadcast load per block in the loop).  One block per step, two
+                // steps per trip on alternating register sets: the next block's fragments are fetched before the
+                // current block's two (independent) MMAs are issued, and no register is ever copied.
+                const int k0 = Q.kstart[warp], cnt = Q.kstart[warp + 1] - k0;
+                if (lane < cnt) {
+                    const int ub = Q.ub[k0 + lane], I = ub >> 8, J = ub & 255;
+                    uint4 o;
+                    o.x = Q.o_lneg + I * 512;
+                    o.y = Q.o_win + (dbase(J) + cs[J]) * 512;
+                    if (I <= NB) {
+                        const int d = I - J;
+                        o.z = Q.o_win + (dbase(d) + wrap(cs[d] + J, NB2 - d)) * 512;
+                    } else {
+                        o.z = Q.o_rhs + wrap(rslot + J, NB2) * 512;
                     }
+                    o.w = 0;
                     S.utab[warp][lane] = o;
                 }
                 __syncwarp();
                 const uint4 *tab = S.utab[warp];
                 const unsigned lo = 16u * lane;
-#define UPD_LOAD(X, k)                                                             \
-    do {                                                                           \
-        const uint4 t0_ = tab[k], t1_ = tab[(k) + 1];                              \
-        X##c0 = t0_.z + lo;                                                        \
-        X##c1 = t1_.z + lo;                                                        \
-        X##a0 = *reinterpret_cast<const double2 *>(smraw + t0_.x + lo);           \
-        X##b0 = *reinterpret_cast<const double2 *>(smraw + t0_.y + lo);           \
-        X##v0 = *reinterpret_cast<const double2 *>(smraw + X##c0);                \
-        X##a1 = *reinterpret_cast<const double2 *>(smraw + t1_.x + lo);           \
-        X##b1 = *reinterpret_cast<const double2 *>(smraw + t1_.y + lo);           \
-        X##v1 = *reinterpret_cast<const double2 *>(smraw + X##c1);                \
+#define UPD_LOAD(X, P, k)  /* set X <- block k; its A fragment is taken from set P when the block row is the same */ \
+    do {                                                                 \
+        const uint4 t0_ = tab[k];                                        \
+        X##c = t0_.z + lo;                                               \
+        X##o = t0_.x;                                                    \
+        X##a = P##a;                                                     \
+        if (X##o != P##o) X##a = *reinterpret_cast<const double2 *>(smraw + t0_.x + lo); \
+        X##b = *reinterpret_cast<const double2 *>(smraw + t0_.y + lo);   \
+        X##v = *reinterpret_cast<const double2 *>(smraw + X##c);         \
     } while (0)
-#define UPD_MMA(X)                                         \
-    do {                                                   \
-        if (DMMA) {                                        \
-            dmma884(X##v0.x, X##v0.y, X##a0.x, X##b0.x);   \
-            dmma884(X##v1.x, X##v1.y, X##a1.x, X##b1.x);   \
-            dmma884(X##v0.x, X##v0.y, X##a0.y, X##b0.y);   \
-            dmma884(X##v1.x, X##v1.y, X##a1.y, X##b1.y);   \
-        } else {                                           \
-            block_mma<false>(X##v0, X##a0, X##b0, lane);   \
-            block_mma<false>(X##v1, X##a1, X##b1, lane);   \
-        }                                                  \
+#define UPD_MMA_STORE(X)                                               \
+    do {                                                               \
+        if (DMMA) {                                                    \
+            double2 e_ = make_double2(0.0, 0.0);                       \
+            dmma884(X##v.x, X##v.y, X##a.x, X##b.x);                   \
+            dmma884(e_.x, e_.y, X##a.y, X##b.y);                       \
+            X##v.x += e_.x;                                            \
+            X##v.y += e_.y;                                            \
+        } else {                                                       \
+            block_mma<false>(X##v, X##a, X##b, lane);                  \
+        }                                                              \
+        *reinterpret_cast<double2 *>(smraw + X##c) = X##v;             \
     } while (0)
-#define UPD_STORE(X)                                                  \
-    do {                                                              \
-        *reinterpret_cast<double2 *>(smraw + X##c0) = X##v0;          \
-        *reinterpret_cast<double2 *>(smraw + X##c1) = X##v1;          \
-    } while (0)
-                unsigned Xc0, Xc1, Yc0, Yc1;
-                double2 Xa0, Xb0, Xv0, Xa1, Xb1, Xv1, Ya0, Yb0, Yv0, Ya1, Yb1, Yv1;
-                if (cnt2 > 0) UPD_LOAD(X, 0);
-                for (int i = 0; i < cnt2; i += 4) {
-                    UPD_MMA(X);
-                    if (i + 2 < cnt2) UPD_LOAD(Y, i + 2);
-                    UPD_STORE(X);
-                    if (i + 2 >= cnt2) break;
-                    UPD_MMA(Y);
-                    if (i + 4 < cnt2) UPD_LOAD(X, i + 4);
-                    UPD_STORE(Y);
+                unsigned Xc, Yc, Xo, Yo = 0xffffffffu;
+                double2 Xa, Xb, Xv, Ya = make_double2(0.0, 0.0), Yb, Yv;
+                if (cnt > 0) UPD_LOAD(X, Y, 0);
+                for (int i = 0; i < cnt; i += 2) {
+                    if (i + 1 < cnt) UPD_LOAD(Y, X, i + 1);
+                    UPD_MMA_STORE(X);
+                    if (i + 1 >= cnt) break;
+                    if (i + 2 < cnt) UPD_LOAD(X, Y, i + 2);
+                    UPD_MMA_STORE(Y);
                 }
 #undef UPD_LOAD
-#undef UPD_MMA
-#undef UPD_STORE
+#undef UPD_MMA_STORE
             } else if (warp == 6) {
                 // the finished panel leaves for HBM; then block (p+1, p+1) gets its update ahead of the others and
                 // is factored at once, so that the next panel's solve can start right after the barrier
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     block_mma<DMMA>(c, reinterpret_cast<const double2 *>(lneg + 64)[lane], v1, lane);
                     reinterpret_cast<double2 *>(Dn)[lane] = c;
                     __syncwarp();
-                    diag_factor(Dn, lst + (par ^ 1) * LPB, S.rd[par ^ 1]);
+                    diag_factor(Dn, lst + (par ^ 1) * LPB, S.rd[par ^ 1], S.minv[par ^ 1]);
                 }
             } else {
                 // block row q = p+NB+1 enters the window through the spare slots (block (q, q-d): slot of
@@ -541,6 +543,8 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         }
         __syncthreads();
         if (tid < 2) {
+            double E_, nu_;
+            const Lame mat = sample_material(E_, nu_);
             double exx = S.G[1 + 3 * tid], eyy = S.G[2 + 3 * tid], gxy = S.G[3 + 3 * tid];
             double sig[4];
             Tangent C;
@@ -735,6 +739,8 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             __syncthreads();
             if (tid == 0) {
                 // d lambda, d mu / d(E, nu), then dE/dx0 = std0 * E ; dnu/dx1 = std1 * nu (1 - 2 nu)
+                double E, nu;
+                const Lame mat = sample_material(E, nu);
                 const double tt = (1.0 + nu) * (1.0 - 2.0 * nu);
                 const double dl_dE = mat.lam / E, dm_dE = mat.mu / E;
                 const double dl_dnu = E * (1.0 + 2.0 * nu * nu) / (tt * tt);
