@@ -269,7 +269,7 @@ def test_refined_mesh_80x40(pkg):
     (23, 150, (1, 2), 2),     # node AHEAD of the element: the band order is flipped internally
     (1, 50, (3, 4), 2),       # supported node: y == 0, gradient through h only
     (116, 110, (1, 3), 0),    # node of the observed element itself: generic kernel
-    (1, 60, (3, 4), 0),       # element too close to the end of the band for two fronts: generic kernel
+    (1, 60, (3, 4), 3),       # element too close to the end of the band for two fronts: blocked panel kernel
 ])
 def test_other_observation_setups(pkg, golden_model, oracle_mesh, node_id, ele_id, nipt_id, variant):
     """The front kernel's layout (orientation, middle block, unit vectors) is derived from the
@@ -362,8 +362,9 @@ def test_elbo_step2_fused_vs_oracle(pkg, engine, torch_oracle):
 @pytest.mark.parametrize("nx,ny,variant", [
     (24, 8, 2),    # n = 432, narrower band (b = 21 < 25): front kernel with a zero-padded band
     (20, 9, 2),    # n = 400, b = 23: other front lengths
-    (16, 8, 0),    # n = 288: too small for the front kernel's shared-memory layout -> generic kernel
-    (30, 10, 0),   # n = 660: the band no longer fits twice per SM -> generic kernel, band in shared memory
+    (16, 8, 3),    # n = 288: too small for the front kernel's shared-memory layout -> blocked panel kernel
+    (30, 10, 3),   # n = 660: the band no longer fits twice per SM -> blocked panel kernel
+    (40, 20, 3),   # n = 1680, b = 45: panel kernel with a 6-block window
 ])
 def test_other_mesh_sizes(pkg, nx, ny, variant):
     """Cook membranes of other sizes through the same entry points (mesh text -> preprocessor ->

@@ -260,15 +260,15 @@ def test_plan_layout_on_host(pkg, golden_model):
     assert p2["twist_row"] + 26 + p2["bottom_cols"] == 440 and p2["twist_row"] >= 32 and p2["bottom_cols"] >= 32
     # observed node inside the observed element's rows / element too close to the end of the band
     assert pkg.fem_solver.plan_layout(golden_model, node_id=116, ele_id=110)["kernel_variant"] == 0
-    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 0
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 3  # panel kernel
     # supported observed node: no unit vectors, still the front kernel
     assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=50)["kernel_variant"] == 2
     # a smaller shared memory does not fit two samples per SM
-    assert pkg.fem_solver.plan_layout(golden_model, smem_per_sm=200000)["kernel_variant"] == 0
+    assert pkg.fem_solver.plan_layout(golden_model, smem_per_sm=200000)["kernel_variant"] == 3
 
 
-@pytest.mark.parametrize("nx,ny,variant,b", [(24, 8, 2, 21), (20, 9, 2, 23), (16, 8, 0, 21), (30, 10, 0, 25),
-                                             (80, 40, 0, 85)])
+@pytest.mark.parametrize("nx,ny,variant,b", [(24, 8, 2, 21), (20, 9, 2, 23), (16, 8, 3, 21), (30, 10, 3, 25),
+                                             (80, 40, 3, 85), (40, 20, 3, 45)])
 def test_plan_layout_other_meshes(pkg, nx, ny, variant, b):
     md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(nx, ny))
     plan = pkg.fem_solver.plan_layout(md, node_id=(nx + 1) * (ny + 1), ele_id=nx // 2 + 2)
