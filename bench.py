@@ -7,7 +7,12 @@
 One "step" = one fused forward+adjoint pass over one batch of 4096 sampled
 material-parameter sets on the Cook 20x10 mesh (BASELINE.json configs[1]);
 with N GPUs every rank processes its own 4096-sample batch (weak scaling, no
-data-path collective -- samples are independent).  Prints ONE JSON line.
+data-path collective -- samples are independent).  The same JSON line carries the
+second half of BASELINE.json's metric as a first-class object, "elbo": ELBO
+training steps/s at 8192 Monte-Carlo samples per GPU (B = 64, S = 128 N), whose
+timed region contains the NCCL all-reduce of the variational-parameter
+gradients; "config4": the refined 80x40 mesh at batch 1024; "latency": the
+one-sample-at-a-time host path; and the CPU baselines.  Prints ONE JSON line.
 """
 import argparse
 import importlib
@@ -31,6 +36,8 @@ BYTES_PER_SOLVE = 96                                                          # 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch at batch 4096 from the committed
 # `ncu --set full` capture (profiles/r01_ncu_front_kernel_final_details.txt): 328 704 B read, 0 B written
 NCU_DRAM_BYTES_PER_LAUNCH = 328704
+# config 4 (80x40): DRAM bytes per fused forward+adjoint SOLVE from the committed capture of the panel kernel
+NCU_C4_DRAM_BYTES_PER_SOLVE = int((1.871130e9 + 1.928987e9) / 296)   # 12.84 MB (read 6.32 + written 6.52)
 
 
 def golden_model():
@@ -107,6 +114,112 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU baselines beside the GPU numbers
+# ------------------------------------------------------------------------------------------------
+def tf_status():
+    """the reference TF path, if TensorFlow exists on the box."""
+    try:
+        import tensorflow  # noqa: F401
+    except Exception as exc:  # noqa: BLE001
+        return f"unavailable ({type(exc).__name__}: the reference TF path cannot be timed on this box)"
+    return "importable (not timed: the reference tree is not on this box)" if not os.path.isdir("/root/reference") \
+        else "importable"
+
+
+def _twin_worker(xs):
+    """One process: the UNMODIFIED reference NumPy twin (src/fem_solver.py + src/mat_subroutine.py) behind
+    the import shims of tests/golden/make_golden.py, one forward solve pair per sample."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden as mg
+    mg._shim()
+    work = tempfile.mkdtemp(prefix="vbfem_twin_")
+    shutil.copy(os.path.join(mg.REF, "Armero_cooksm_20x10.txt"), work)
+    os.chdir(work)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import fem_preprocess as fp
+        from src import data_generation_2sam_more_loss as dg
+        fp.PreProcessing.modeldata_initialization_topopt("Armero_cooksm_20x10.txt", "model_file.mat")
+        M = dg.MeasurementData
+        M.theta_mean, M.theta_std = np.array([np.log(20.0), 0.0]), np.array([0.1, 0.015])
+        M.node_id, M.ele_id, M.nipt_id = 231, 12, np.array([1, 3], dtype=int)
+        t0 = time.perf_counter()
+        for x in xs:
+            M.fem_f_fun(np.asarray(x))   # one solve (2 assemblies + spsolve): y; h comes from the same state
+        return time.perf_counter() - t0
+
+
+def time_numpy_twin(per_core=8):
+    """the reference's own NumPy twin on all host cores (one process per core).  The
+    reference tree does not travel to the GPU box; there this reports its absence explicitly."""
+    if not os.path.isdir("/root/reference"):
+        return "reference tree absent on this box (the statement-by-statement port stands in: " \
+               "cpu_baseline.statement_by_statement_port)"
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    x = np.random.default_rng(0).standard_normal((cores * per_core, 2))
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        inner = pool.map(_twin_worker, [x[i::cores] for i in range(cores)])
+    wall = time.perf_counter() - t0
+    return {"value": len(x) / max(inner), "unit": "forward solves/s", "cores": cores, "kind": "reference",
+            "sample": f"{len(x)} seeded samples, MeasurementData.fem_f_fun of the unmodified reference "
+                      f"(src/fem_solver.py NumPy twin), one process per core; wall incl. start-up {wall:.1f} s"}
+
+
+def _loop_worker(xs):
+    fo, _, mesh, dof = oracle()
+    lo = fo.LoopOracle(mesh, dof)
+    t0 = time.perf_counter()
+    fo.fem_fh_loop(lo, np.asarray(xs), (np.log(20.0), 0.0), (0.1, 0.015))
+    return time.perf_counter() - t0
+
+
+def time_loop_port(per_core=4):
+    """The statement-by-statement port of the reference NumPy twin (oracle LoopOracle: element and Gauss
+    loops as upstream) on all host cores, one process per core."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    x = np.random.default_rng(0).standard_normal((cores * per_core, 2))
+    with mp.get_context("spawn").Pool(cores) as pool:
+        inner = pool.map(_loop_worker, [x[i::cores] for i in range(cores)])
+    return {"value": len(x) / max(inner), "unit": "forward solves/s", "cores": cores, "kind": "port",
+            "sample": f"{len(x)} seeded samples, oracle LoopOracle (element/Gauss loops as in the reference NumPy "
+                      "twin; forward only), one process per core"}
+
+
+def cpu_elbo_step(to, fo, B=64, S=4, steps=3):
+    """One ELBO training step on the CPU port: nets -> reparameterisation -> oracle FEM (dense LU) -> loss ->
+    autograd -> Adam, on a bounded B*S."""
+    import torch
+    pkg = importlib.import_module(PKG)
+    model = pkg.elbo.make_step1_model()
+    opt = pkg.elbo.make_step1_optimizer(model)
+    yd = torch.tensor(np.random.default_rng(2).standard_normal((B, 2)) * np.array([0.53, 0.65])
+                      + np.array([-4.24, 5.71]))
+    e = torch.tensor(np.random.default_rng(5).standard_normal((S, 2)))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        mu, sig, ls = model(yd)
+        loss, *_ = fo.elbo_step1_torch(to, yd, mu, sig, e, 0.1)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"solves_per_s": B * S / dt, "B": B, "S": S, "s_per_step": dt, "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"B={B}, S={S} ({B * S} fwd+adjoint solves per step), oracle "
+                                      "elbo_step1_torch + torch autograd + Adam, torch CPU f64"}
+
+
 def run_reference(args):
     """CPU arm: the oracle's batched float64 port of the reference path (dense
     assembly + dense LU + reverse-mode gradient, torch CPU, all host threads),
@@ -115,6 +228,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core at every N
+    torch.set_num_threads(os.cpu_count() or 1)
     fo, to, mesh, dof = oracle()
     sample = 256
     x, gy, gh = inputs(0)
@@ -138,6 +253,8 @@ def run_reference(args):
                                    "(vectorised dense assembly + dense LU + autograd), torch CPU float64"},
         "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "numpy_twin": time_numpy_twin(16),
+        "tf": tf_status(),
     }
     print(json.dumps(line))
 
@@ -224,59 +341,114 @@ def run_cuda(args):
         yh, hh, gxh = eng.forward_backward_host(xh, gyh, ghh)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+
+    # ---------------- sustained figure: back-to-back fused launches for at least one second
+    n_sus = max(50, int(1.1e3 / max(b2b_ms / args.steps, 1e-3)))
+    barrier()
+    a.record()
+    for _ in range(n_sus):
+        eng.forward_backward(x, gy, gh)
+    b.record()
+    barrier()
+    sus_ms = a.elapsed_time(b)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---------------- ELBO step (config 3 at N=1; config 5 shape, 8192 samples per GPU, at N>1)
+    # ---------------- latency path: the one-sample-at-a-time callers (src/postprocess_lib.py:78-103)
+    lat = {}
+    for nb in (1, 8, 64):
+        xs = xh[:nb]
+        for _ in range(20):
+            eng.forward_host(xs)
+        reps = 300
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.forward_host(xs)
+        lat[f"forward_host_n{nb}_us_per_call"] = 1e6 * (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.forward_backward_host(xs, gyh[:nb], ghh[:nb])
+        lat[f"forward_backward_host_n{nb}_us_per_call"] = 1e6 * (time.perf_counter() - t0) / reps
+    lat["what"] = ("NumPy in / NumPy out through vbfem_forward_host / vbfem_forward_backward_host, wall clock per call "
+                   "incl. launch + synchronise; batches <= 64 run on mapped pinned memory (no staging copies)")
+
+    # ---------------- ELBO step: 8192 Monte-Carlo samples per GPU at every N (B = 64, S = 128 N; config 5 at
+    #                  N = 8), the NCCL all-reduce of the variational-parameter gradients inside the timed region
     B = 64
-    S = 100 if world == 1 else 128 * world
     yd = np.random.default_rng(2).standard_normal((10000, 2)) * np.array([0.53, 0.65]) + np.array([-4.24, 5.71])
-    e_data = torch.tensor(np.random.default_rng(3 if world == 1 else 5).standard_normal((S, 2)), device=dev)
-    model = pkg.elbo.make_step1_model(device=dev)
-    opt = pkg.elbo.make_step1_optimizer(model)
-    loss_fn = pkg.elbo.Step1Loss(eng, e_data, 0.1, rank=rank, world=world)
-    pin = torch.empty(B, 2, dtype=torch.float64).pin_memory()
 
-    def elbo_step(i):
-        pin.copy_(torch.from_numpy(yd[(i * B) % 9984:(i * B) % 9984 + B]))
-        yb = pin.to(dev, non_blocking=True)
-        opt.zero_grad(set_to_none=True)
-        mu, sig, ls = model(yb)
-        loss = loss_fn(yb, mu, sig, ls)
-        loss.backward()
-        opt.step()
-        return float(loss)  # D2H read of the loss
+    def time_elbo(S, seed, graphed=True):
+        e_data = torch.tensor(np.random.default_rng(seed).standard_normal((S, 2)), device=dev)
+        loss_fn = pkg.elbo.Step1Loss(eng, e_data, 0.1, rank=rank, world=world)
+        model = pkg.elbo.make_step1_model(device=dev)
+        if graphed:
+            step = pkg.elbo.GraphedStep1(model, pkg.elbo.make_step1_optimizer_capturable(model), loss_fn, B, dev)
+            run = lambda i: float(step.step(yd[(i * B) % 9984:(i * B) % 9984 + B]))  # batch H2D, loss D2H
+        else:
+            opt = pkg.elbo.make_step1_optimizer(model)
+            pin = torch.empty(B, 2, dtype=torch.float64).pin_memory()
 
-    elbo_steps = max(5, min(args.steps, 30))
-    for i in range(3):
-        elbo_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(elbo_steps):
-        last_loss = elbo_step(3 + i)
-    barrier()
-    elbo_eager_s = time.perf_counter() - t0
+            def run(i):
+                pin.copy_(torch.from_numpy(yd[(i * B) % 9984:(i * B) % 9984 + B]))
+                yb = pin.to(dev, non_blocking=True)
+                opt.zero_grad(set_to_none=True)
+                mu, sig, ls = model(yb)
+                loss = loss_fn(yb, mu, sig, ls)
+                loss.backward()
+                opt.step()
+                return float(loss)
+            step = None
+        n = max(10, min(args.steps, 40))
+        for i in range(3):
+            run(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            last = run(3 + i)
+        barrier()
+        dt = time.perf_counter() - t0
+        return n, dt, last, step
 
-    # the same step captured once in a CUDA graph (nets + fused FEM op + Adam) and replayed
-    gmodel = pkg.elbo.make_step1_model(device=dev)
-    gstep = pkg.elbo.GraphedStep1(gmodel, pkg.elbo.make_step1_optimizer_capturable(gmodel), loss_fn, B, dev)
+    elbo_steps, elbo_s, last_loss_g, gstep = time_elbo(128 * world, 5)
+    _, elbo_eager_s, last_loss, _ = time_elbo(128 * world, 5, graphed=False)
+    c3 = None
+    if world == 1:  # config 3 (shapes of the shipped data file: S = 100)
+        n3, c3_s, c3_loss, c3step = time_elbo(100, 3)
+        c3 = {"steps_per_s": n3 / c3_s, "B": B, "S": 100, "samples_per_step": 6400, "last_loss": c3_loss,
+              "fem_solves_per_s": 6400 * n3 / c3_s}
+        del c3step
 
-    def elbo_graph_step(i):
-        return float(gstep.step(yd[(i * B) % 9984:(i * B) % 9984 + B]))  # H2D of the batch, D2H of the loss
+    # ---------------- config 4: Cook 80x40, batch 1024 per GPU (blocked panel kernel, factor streamed to HBM)
+    md4 = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(80, 40))
+    eng4 = pkg.CookFemEngine(md4, device=local, node_id=3321, ele_id=12)
+    n4 = 1024
+    x4 = torch.tensor(np.random.default_rng(4 + 100 * rank).standard_normal((n4, 2)), device=dev)
+    g4 = np.random.default_rng(5 + 100 * rank).standard_normal((n4, 4))
+    gy4, gh4 = torch.tensor(np.ascontiguousarray(g4[:, :2]), device=dev), torch.tensor(np.ascontiguousarray(g4[:, 2:]), device=dev)
+    k4 = max(5, min(args.steps, 10))
 
-    for i in range(3):
-        elbo_graph_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(elbo_steps):
-        last_loss_g = elbo_graph_step(3 + i)
-    barrier()
-    elbo_s = time.perf_counter() - t0
+    def time4(fn):
+        for _ in range(3):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k4)]
+        barrier()
+        for ea, eb in evs:
+            flush.zero_()
+            ea.record()
+            fn()
+            eb.record()
+        barrier()
+        return float(sum(ea.elapsed_time(eb) for ea, eb in evs))
+    c4_adj_ms = time4(lambda: eng4.forward_backward(x4, gy4, gh4))
+    c4_bad = eng4.status(n4)[0]
+    c4_fwd_ms = time4(lambda: eng4.forward(x4))
+    c4_info = dict(eng4.info)
 
     # ---------------- max over ranks
-    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s = t.tolist()
+    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms = t.tolist()
 
     if rank == 0:
         import ctypes
@@ -292,24 +464,39 @@ def run_cuda(args):
         value = total / (dev_ms * 1e-3)
         launch_s = dev_ms * 1e-3 / args.steps
         tflops = FLOP_PER_SOLVE * BATCH / launch_s / 1e12
-        cpu = None
+        cpu = cpu_elbo = cpu4 = None
         if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
             fo, to, mesh, dof = oracle()
             ns = 1536
             cpu_fwd_adjoint(to, xh[:256], gyh[:256], ghh[:256])
             t0 = time.perf_counter()
             cpu_fwd_adjoint(to, xh[:ns], gyh[:ns], ghh[:ns])
             dt = time.perf_counter() - t0
-            lo = fo.LoopOracle(mesh, dof)
-            t1 = time.perf_counter()
-            fo.fem_fh_loop(lo, xh[:8], (np.log(20.0), 0.0), (0.1, 0.015))
-            dl = time.perf_counter() - t1
             cpu = {"value": ns / dt, "unit": "solves/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"first {ns} of the 4096 seeded samples, forward+adjoint, oracle TorchOracle.vjp "
                              "(vectorised dense assembly + dense LU + autograd, torch CPU f64)",
-                   "statement_by_statement_port": {"value": 8 / dl, "unit": "forward solves/s", "cores": 1,
-                                                   "sample": "8 samples, oracle LoopOracle (element/Gauss loops as "
-                                                             "in the reference NumPy twin; forward only)"}}
+                   "statement_by_statement_port": time_loop_port(),
+                   "numpy_twin": time_numpy_twin(), "tf": tf_status()}
+            cpu_elbo = cpu_elbo_step(to, fo)
+            # config 4 on the CPU: the sparse port (CSR assembly + SuperLU + discrete adjoint), one core
+            m4 = fo.read_mesh_text(fo.cook_mesh_text(80, 40))
+            so = fo.SparseOracle(m4, fo.assign_dof(m4))
+            xs4, gs4 = x4[:4].cpu().numpy(), g4[:4]
+            so.vjp(xs4[:1], gs4[:1, :2], gs4[:1, 2:], 3321, 12)
+            t0 = time.perf_counter()
+            so.vjp(xs4, gs4[:, :2], gs4[:, 2:], 3321, 12)
+            cpu4 = {"value": 4 / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "port",
+                    "sample": "4 seeded samples, forward+adjoint, oracle SparseOracle.vjp (CSR assembly + SuperLU "
+                              "+ discrete adjoint), one core"}
+        S5 = 128 * world
+        elbo_rate = elbo_steps / elbo_s
+        elbo_tflops = elbo_rate * B * S5 * FLOP_PER_SOLVE / 1e12
+        c4_rate = world * n4 * k4 / (c4_adj_ms * 1e-3)
+        c4_flop = 1600 * 3200 + 6560 * (85 * 85 + 3 * 85) + 2 * 4 * 6560 * 85       # 58.7 MFLOP
+        c4_bytes = 4 * 6560 * 86 * 8 + 96                                            # 18.05 MB if L is streamed
+        c4_tf = c4_rate / world * c4_flop / 1e12
+        c4_gbs = c4_rate / world * c4_bytes / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -325,10 +512,6 @@ def run_cuda(args):
             "roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64.value, "unit": "TFLOP/s",
                          "frac": tflops / fp64.value if fp64.value else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_unit": "bytes of DRAM traffic per launch (ncu, batch 4096): the band never leaves the SM",
-                         "other_pipes_ncu": {"fp64_pipe_active_pct": 22.8, "shared_memory_data_pipe_pct": 52.6,
-                                             "note": "profiles/r01_ncu_front_kernel_final_details.txt: the broadcast of the "
-                                                     "scaled pivot column (12 LDS.128 per column and front) keeps the "
-                                                     "shared-memory pipe busier than the FP64 pipe"},
                          "peak_source": "DFMA loop measured on this GPU by vbfem_measure_peaks "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_solve": FLOP_PER_SOLVE,
@@ -336,17 +519,47 @@ def run_cuda(args):
                                  "note": "compulsory I/O only; the band lives on chip"}},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "elbo": {"metric": "ELBO training steps/s (Cook 20x10, 8192 Monte-Carlo samples per GPU)",
+                     "value": elbo_rate, "unit": "steps/s", "n_gpus": world, "B": B, "S": S5,
+                     "samples_per_step": B * S5, "samples_per_gpu": B * S5 // world, "scaling": "weak",
+                     "fem_solves_per_s": B * S5 * elbo_rate, "last_loss": last_loss_g,
+                     "cuda_graph": bool(gstep.graphed), "eager_steps_per_s": elbo_steps / elbo_eager_s,
+                     "eager_last_loss": last_loss, "timed_steps": elbo_steps,
+                     "collective": ("one NCCL all-reduce of 3 + 4B doubles per step INSIDE the timed region "
+                                    "(a node of the captured graph)") if world > 1 else "none (one GPU)",
+                     "roofline": {"bound": "fp64", "achieved": elbo_tflops, "peak": fp64.value * world,
+                                  "unit": "TFLOP/s", "frac": elbo_tflops / (fp64.value * world) if fp64.value else None,
+                                  "note": "0.716 MFLOP per reparameterised sample (FEM forward + adjoint); the two "
+                                          "1884-parameter MLPs and Adam are < 0.1 % of the flops"},
+                     "cpu_baseline": cpu_elbo,
+                     "what": "pinned batch H2D -> NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd -> Adam "
+                             "-> loss D2H; one CUDA graph replay per step",
+                     "config3": c3},
+            "config4": {"workload": "Cook 80x40 (n=6560, half bandwidth 85), batch 1024 per GPU, fused forward+adjoint "
+                                    "(BASELINE configs[3]); x seed 4, cotangents seed 5",
+                        "value": c4_rate, "unit": "solves/s", "ms_per_step": c4_adj_ms / k4, "steps": k4,
+                        "forward_only_solves_per_s": world * n4 * k4 / (c4_fwd_ms * 1e-3), "flagged_samples": c4_bad,
+                        "l2": "flushed between timed steps", "kernel": c4_info,
+                        "roofline": {"bound": "hbm if the factor is streamed (SURVEY 8d), fp64 otherwise",
+                                     "fp64": {"achieved": c4_tf, "peak": fp64.value, "unit": "TFLOP/s",
+                                              "frac": c4_tf / fp64.value if fp64.value else None,
+                                              "flop_per_solve": c4_flop},
+                                     "hbm": {"achieved": c4_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                             "frac": c4_gbs / hbm_peak, "bytes_per_solve": c4_bytes},
+                                     "frac": min(c4_tf / fp64.value if fp64.value else 1.0, c4_gbs / hbm_peak),
+                                     "traffic": NCU_C4_DRAM_BYTES_PER_SOLVE,
+                                     "traffic_unit": "bytes of DRAM traffic per SOLVE (ncu --set full, 296 samples, "
+                                                     "profiles/r02_ncu_80x40_adj_details.txt)"},
+                        "cpu_baseline": cpu4},
+            "latency": lat,
             "extra": {"back_to_back_solves_per_s": world * BATCH * args.steps / (b2b_ms * 1e-3),
+                      "sustained": {"solves_per_s": world * BATCH * n_sus / (sus_ms * 1e-3), "launches": n_sus,
+                                    "seconds": sus_ms * 1e-3, "what": "back-to-back fused launches, no L2 flush"},
                       "forward_only_solves_per_s": world * BATCH * args.steps / (fwd_ms * 1e-3),
-                      "step_ms_min": min(step_ms), "step_ms_max": max(step_ms),
-                      "elbo": {"steps_per_s": elbo_steps / elbo_s, "B": B, "S": S, "samples_per_step": B * S,
-                               "fem_solves_per_s": B * S * elbo_steps / elbo_s, "last_loss": last_loss_g,
-                               "cuda_graph": bool(gstep.graphed),
-                               "eager_steps_per_s": elbo_steps / elbo_eager_s, "eager_last_loss": last_loss,
-                               "what": "NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd -> Adam (one CUDA graph replay per step), "
-                                       "batch H2D and loss D2H inside; one NCCL all-reduce per step when N>1"}},
+                      "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)},
         }
         print(json.dumps(line), flush=True)
+    eng4.close()
     if world > 1:
         # Tear down in a safe order: the captured graph (it holds an NCCL all-reduce node) goes first,
         # then the process group; a watchdog ends the process if the NCCL teardown does not return

@@ -394,6 +394,39 @@ class TorchOracle:
         h = t.sqrt(0.5 * t.sum(t.einsum("ij,njk->nik", self.P6, s) ** 2, dim=1))
         return y, h
 
+    def fem_fh_chunked(self, x, chunk=256):
+        """``fem_fh`` for large batches: the dense per-sample matrices of a chunk (0.9 GB per 512 samples,
+        several times that with the autograd tape) exist only while the chunk is processed; backward
+        recomputes the chunk.  Same numbers and gradients as ``fem_fh``."""
+        t = self.torch
+        oracle = self
+
+        class Chunked(t.autograd.Function):
+            @staticmethod
+            def forward(ctx, xx):
+                ctx.save_for_backward(xx)
+                ys, hs = [], []
+                with t.no_grad():
+                    for i in range(0, xx.shape[0], chunk):
+                        y, h = oracle.fem_fh(xx[i:i + chunk])
+                        ys.append(y)
+                        hs.append(h)
+                return t.cat(ys), t.cat(hs)
+
+            @staticmethod
+            def backward(ctx, gy, gh):
+                (xx,) = ctx.saved_tensors
+                out = []
+                for i in range(0, xx.shape[0], chunk):
+                    with t.enable_grad():
+                        xc = xx[i:i + chunk].detach().requires_grad_(True)
+                        y, h = oracle.fem_fh(xc)
+                        (g,) = t.autograd.grad((y * gy[i:i + chunk]).sum() + (h * gh[i:i + chunk]).sum(), xc)
+                    out.append(g)
+                return t.cat(out)
+
+        return Chunked.apply(x)
+
     def vjp(self, x_np, gy_np, gh_np):
         t = self.torch
         x = t.tensor(x_np, dtype=t.float64, requires_grad=True)
@@ -414,7 +447,7 @@ def elbo_step1_torch(torch_oracle, y_batch, mu, sig2, e_data, sig_e):
     term1 = -0.5 * t.mean(t.sum(t.log(sig2), dim=-1), dim=0) - 0.5 * d * math.log(2.0 * math.pi) - 0.5 * d
     std = t.sqrt(sig2).unsqueeze(1)
     theta = (e_data * std + mu.unsqueeze(1)).reshape(-1, d)
-    f, _ = torch_oracle.fem_fh(theta)  # [B*S, 2]
+    f, _ = torch_oracle.fem_fh(theta) if theta.shape[0] <= 512 else torch_oracle.fem_fh_chunked(theta)  # [B*S, 2]
     l1 = -0.5 * dy * math.log(2.0 * math.pi * sig_e)
     l2 = -0.5 / sig_e * t.sum((y_batch.unsqueeze(1) - f) ** 2, dim=-1)  # [B, B*S]
     term2 = l1 + t.mean(l2)
@@ -503,6 +536,65 @@ class SparseOracle:
             y[i] = u[2 * node_id - 2: 2 * node_id]
             h[i] = von_mises(stress[:, :, ele_id - 1], nipt_id)
         return y, h
+
+    def vjp(self, x, gy, gh, node_id, ele_id, nipt_id=(1, 3)):
+        """x[N,2], gy[N,2], gh[N,2] -> y, h, gx = d(sum gy*y + sum gh*h)/dx: what tape.gradient
+        (main_custom_training.py:252-256) returns, derived per sample as the discrete adjoint of the
+        sparse solve (SuperLU factor reused for K psi = w) with torch autograd for the local pieces
+        (theta -> E, nu -> lambda, mu; strain -> stress -> von Mises measure at the observed points).
+        Checked against TorchOracle.vjp (dense LU + full autograd) in tests/test_oracle.py."""
+        import scipy.sparse as sp
+        import torch as t
+        from scipy.sparse.linalg import splu
+
+        x, gy, gh = np.atleast_2d(x), np.atleast_2d(gy), np.atleast_2d(gh)
+        ndof = self.dof["ndof"]
+        free = self.dof["free_dof"] - 1
+        rows = np.repeat(self.lm[:, :, None], 8, axis=2).ravel()
+        cols = np.repeat(self.lm[:, None, :], 8, axis=1).ravel()
+        Cl = np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 0.0]])   # dC3/dlambda
+        Cm = np.array([[2.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 1.0]])   # dC3/dmu
+        if not hasattr(self, "_Kel"):
+            self._Kel = np.einsum("eg,egia,ij,egjb->eab", self.dvol, self.B, Cl, self.B)
+            self._Kem = np.einsum("eg,egia,ij,egjb->eab", self.dvol, self.B, Cm, self.B)
+        Bo = t.tensor(self.B[ele_id - 1][[g - 1 for g in nipt_id]])           # [2,3,8]
+        lmo = self.lm[ele_id - 1]
+        P6 = t.tensor(PDEV6)
+        y, h, gx = np.zeros((len(x), 2)), np.zeros((len(x), 2)), np.zeros((len(x), 2))
+        for i in range(len(x)):
+            xt = t.tensor(x[i], dtype=t.float64, requires_grad=True)
+            E = t.exp(self.theta_std[0] * xt[0] + self.theta_mean[0])
+            v = 0.5 / (1.0 + t.exp(-self.theta_std[1] * xt[1] - self.theta_mean[1]))
+            lam = v * E / ((1 + v) * (1 - 2 * v))
+            mu = 0.5 * E / (1 + v)
+            lam_f, mu_f = float(lam.detach()), float(mu.detach())
+            K = sp.csr_matrix(((lam_f * self._Kel + mu_f * self._Kem).ravel(), (rows, cols)), shape=(ndof, ndof))
+            lu = splu(K[free][:, free].tocsc())
+            u = np.zeros(ndof)
+            u[free] = lu.solve(self.dof["Pf"])
+            # local observation function of (u_e, lambda, mu)
+            ue = t.tensor(u[lmo], requires_grad=True)
+            eps = t.einsum("gia,a->gi", Bo, ue)                                   # [2,3] (xx, yy, gxy)
+            exx, eyy, gxy = eps[:, 0], eps[:, 1], eps[:, 2]
+            z = t.zeros_like(exx)
+            sig = t.stack([(lam + 2 * mu) * exx + lam * eyy, lam * exx + (lam + 2 * mu) * eyy,
+                           lam * (exx + eyy), mu * gxy, z, z])                     # [6,2]
+            hv = t.sqrt(0.5 * t.sum((P6 @ sig) ** 2, dim=0))
+            obj = (hv * t.tensor(gh[i])).sum()
+            g_ue, g_lam, g_mu = t.autograd.grad(obj, [ue, lam, mu], retain_graph=True, allow_unused=True)
+            w = np.zeros(ndof)
+            np.add.at(w, lmo, g_ue.numpy())
+            w[2 * node_id - 2: 2 * node_id] += gy[i]
+            psi = np.zeros(ndof)
+            psi[free] = lu.solve(w[free])
+            pe, uu = psi[self.lm], u[self.lm]
+            gl = -np.einsum("ea,eab,eb->", pe, self._Kel, uu) + (float(g_lam) if g_lam is not None else 0.0)
+            gm = -np.einsum("ea,eab,eb->", pe, self._Kem, uu) + (float(g_mu) if g_mu is not None else 0.0)
+            (gxi,) = t.autograd.grad(gl * lam + gm * mu, xt)
+            y[i] = u[2 * node_id - 2: 2 * node_id]
+            h[i] = hv.detach().numpy()
+            gx[i] = gxi.numpy()
+        return y, h, gx
 
 
 def read_mesh_text(text):

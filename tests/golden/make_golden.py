@@ -10,7 +10,8 @@ that are absent here (tensorflow, hdf5storage, h5py, matplotlib) and records
     the mesh/DOF interface (fem_preprocess.py:114-443),
   * config 1 (fem_test.py: E=20, nu=0.3): full u, sigma, eps, von Mises,
   * theta-parameterised solves through MeasurementData.fem_f_fun / fem_h_fun
-    (data_generation_2sam_more_loss.py:98-125) for a list of seeded x.
+    (data_generation_2sam_more_loss.py:98-125) for a list of seeded x,
+  * finite-difference Jacobians d(y, h)/dx of those same reference functions (gradient pins).
 
 Output: tests/golden/ref_numpy_twin.npz  (committed; this script is the recipe).
 Usage:  python tests/golden/make_golden.py
@@ -92,6 +93,28 @@ def main():
     out["h"] = np.stack(hs)
     out["u"] = np.stack(us)
     out["stress"] = np.stack(sigs)
+
+    # ---- gradient pins: central differences of the reference twin ITSELF (Richardson-extrapolated, two
+    #      step sizes) -> the 4x2 Jacobian d(y0, y1, h0, h1)/d(x0, x1) at a few x.  tape.gradient
+    #      (main_custom_training.py:252-256) differentiates the TF copy of these formulas; TF cannot run
+    #      here, so this is the closest reference-side pin of the gradient (good to ~1e-9 relative).
+    def yh(x):
+        return np.concatenate([np.asarray(M.fem_f_fun(x), dtype=np.float64).ravel(),
+                               np.asarray(M.fem_h_fun(x), dtype=np.float64).ravel()])
+
+    fd_x = np.array([[1.0, -1.0], [0.0, 0.0], [-2.5, 3.0], [0.3, 40.0]])
+    fd_jac = np.zeros((len(fd_x), 4, 2))
+    for i, x in enumerate(fd_x):
+        for k in range(2):
+            d = []
+            for hstep in (0.02, 0.01):
+                xp, xm = x.copy(), x.copy()
+                xp[k] += hstep
+                xm[k] -= hstep
+                d.append((yh(xp) - yh(xm)) / (2.0 * hstep))
+            fd_jac[i, :, k] = (4.0 * d[1] - d[0]) / 3.0
+    out["fd_x"] = fd_x
+    out["fd_jac"] = fd_jac
     np.savez_compressed(os.path.join(HERE, "ref_numpy_twin.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_numpy_twin.npz"))
     print("c1 y", out["c1_nodal_disp"][:, 230], "vm", out["c1_vm"], "tol", out["c1_tol"])

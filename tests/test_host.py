@@ -274,3 +274,77 @@ def test_plan_layout_other_meshes(pkg, nx, ny, variant, b):
     plan = pkg.fem_solver.plan_layout(md, node_id=(nx + 1) * (ny + 1), ele_id=nx // 2 + 2)
     assert plan["kernel_variant"] == variant and plan["half_bw"] == b
     assert plan["nfree"] == 2 * nx * (ny + 1)
+
+
+def test_h5io_roundtrip_and_layout(pkg, tmp_path):
+    """h5io: write -> read round trip of a save_data-shaped dictionary (float64, stored transposed like
+    hdf5storage's MATLAB-compatible mode), and the structural fields a libhdf5 reader checks first."""
+    import struct
+    rng = np.random.default_rng(0)
+    d = {"y_data": rng.standard_normal((50, 2)), "y_scaled_data": rng.standard_normal((50, 2)),
+         "z_data": rng.standard_normal((50, 2)), "log_z_data": rng.standard_normal((50, 2)),
+         "z_scaled_data": rng.standard_normal((50, 2)), "y_mean": rng.standard_normal((1, 2)),
+         "y_std": rng.standard_normal((1, 2)), "z_mean": rng.standard_normal((1, 2)),
+         "z_std": rng.standard_normal((1, 2)), "e_data": rng.standard_normal((7, 2))}
+    f = str(tmp_path / "data.h5")
+    pkg.h5io.write(data=d, filename=f)
+    back = pkg.h5io.read(filename=f)
+    assert sorted(back) == sorted(d)
+    for k in d:
+        assert back[k].dtype == np.float64 and np.array_equal(back[k], d[k])
+    raw = open(f, "rb").read()
+    assert raw.startswith(b"MATLAB 7.3 MAT-file") and raw[512:520] == b"\x89HDF\r\n\x1a\n" and raw[520] == 0
+    base, _, eof, _ = struct.unpack_from("<QQQQ", raw, 512 + 24)
+    assert base == 512 and base + eof == len(raw)
+    untransposed = pkg.h5io.read(filename=f, matlab_compatible=False)
+    assert untransposed["y_data"].shape == (2, 50)      # MATLAB order on disk
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.h5"
+        bad.write_bytes(b"not an hdf5 file" * 100)
+        pkg.h5io.read(filename=str(bad))
+
+
+def test_h5io_reads_a_deflate_shuffle_fletcher32_file(pkg):
+    """The committed fixture tests/golden/chunked_filters.h5 was cut from the reference's shipped
+    data_fem_test_big_noise.h5 layout by tests/golden/make_h5_fixture.py: chunked datasets with
+    shuffle + deflate + fletcher32, version-1 B-trees.  Values are the recipe's seeded arrays."""
+    f = os.path.join(ROOT, "tests", "golden", "chunked_filters.h5")
+    d = pkg.h5io.read(filename=f)
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal((300, 2))
+    b = rng.standard_normal((1, 2))
+    assert np.array_equal(d["a_data"], a) and np.array_equal(d["b_mean"], b)
+
+
+def test_generate_data_fem_is_seed_compatible(pkg, monkeypatch):
+    """generate_data_fem consumes NumPy's global generator in upstream's order (theta, err, eta, e_data;
+    src/data_generation_2sam_more_loss.py:64-73), the constructor draws nothing, save_data writes the ten
+    datasets of save_data upstream (src/data_generation_2sam_more_loss.py:256-268)."""
+    M = pkg.MeasurementData
+    calls = []
+
+    def fake_fem(x):
+        calls.append(np.array(x))
+        return [np.stack([x[:, 0], 2 * x[:, 1]], 1), np.exp(0.1 * x) + 5.0]
+    monkeypatch.setattr(M, "fem_fh_fun_loop_rev", staticmethod(fake_fem))
+    np.random.seed(123)
+    md = M(n_sam=6, ne_sam=3, d_y=2, d_z=2, d_theta=2, sig_e=0.1, sig_eta=3e-3)
+    assert md.e_data.shape == (6, 2) and not md.e_data.any()     # upstream's initial shapes, no draws
+    md.generate_data_fem()
+    np.random.seed(123)
+    theta = np.random.randn(6, 2)
+    err = np.sqrt(0.1) * np.random.randn(6, 2)
+    eta = np.sqrt(3e-3) * np.random.randn(6, 2)
+    e_data = np.random.randn(3, 2)
+    assert np.array_equal(calls[0], theta) and np.array_equal(md.e_data, e_data)
+    assert np.array_equal(md.y_data, np.stack([theta[:, 0], 2 * theta[:, 1]], 1) + err)
+    assert np.array_equal(md.z_data, np.exp(0.1 * theta) + 5.0 + eta)
+    assert np.array_equal(md.log_z_data, np.log(md.z_data)) and md.y_mean.shape == (1, 2)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "d.h5")
+        md.save_data("/", f)
+        back = M.load_data("/", f)
+    assert sorted(back) == sorted(["y_data", "y_scaled_data", "z_data", "log_z_data", "z_scaled_data", "y_mean",
+                                   "y_std", "z_mean", "z_std", "e_data"])
+    assert np.array_equal(back["y_data"], md.y_data) and np.array_equal(back["e_data"], md.e_data)

@@ -114,3 +114,36 @@ def test_elbo_broadcast_quirk(torch_oracle):
     ref = -0.5 * 2 * math.log(2 * math.pi * 0.1) - 0.5 / 0.1 * tot / (B * B * S)
     assert abs(float(t2) - float(ref)) < 1e-12 * abs(float(ref))
     assert abs(float(loss) - float(t1 - t2 - t3)) < 1e-14
+
+
+def test_sparse_oracle_vjp_equals_dense_autograd(oracle_mesh, torch_oracle):
+    """SparseOracle.vjp (discrete adjoint on the SuperLU factor, used for the 80x40 parity tests) against
+    TorchOracle.vjp (dense LU + full autograd) on the 20x10 mesh, incl. a supported observation node."""
+    import fem_oracle as fo
+    so = fo.SparseOracle(*oracle_mesh)
+    rng = np.random.default_rng(21)
+    x, gy, gh = rng.standard_normal((5, 2)), rng.standard_normal((5, 2)), rng.standard_normal((5, 2))
+    y0, h0, g0 = torch_oracle.vjp(x, gy, gh)
+    y1, h1, g1 = so.vjp(x, gy, gh, 231, 12)
+    assert relerr(y1, y0) < 1e-11 and relerr(h1, h0) < 1e-11
+    assert np.max(np.abs(g1 - g0) / np.maximum(np.abs(g0), 1e-300)) < 1e-8   # element-wise
+    to2 = fo.TorchOracle(*oracle_mesh, node_id=23, ele_id=150, nipt_id=(1, 2))
+    y0, h0, g0 = to2.vjp(x, gy, gh)
+    y1, h1, g1 = so.vjp(x, gy, gh, 23, 150, (1, 2))
+    assert relerr(g1, g0) < 1e-10
+
+
+def test_oracle_jacobian_vs_reference_finite_differences(golden, torch_oracle):
+    """Gradient pin on the reference's own code: the oracle's autograd Jacobian d(y, h)/dx against
+    Richardson-extrapolated central differences of the UNMODIFIED reference NumPy twin
+    (tests/golden/make_golden.py, arrays fd_x / fd_jac)."""
+    for x, jref in zip(golden["fd_x"], golden["fd_jac"]):
+        J = np.zeros((4, 2))
+        for r in range(4):
+            gy, gh = np.zeros((1, 2)), np.zeros((1, 2))
+            (gy if r < 2 else gh)[0, r % 2] = 1.0
+            J[r] = torch_oracle.vjp(x[None], gy, gh)[2][0]
+        # dh/dx0 is exactly 0 (stresses do not depend on E under load control); FD noise there ~3e-12
+        assert np.max(np.abs(J - jref)) < 2e-9 * np.max(np.abs(jref))
+        big = np.abs(jref) > 1e-6
+        assert np.max(np.abs(J - jref)[big] / np.abs(jref)[big]) < 2e-8

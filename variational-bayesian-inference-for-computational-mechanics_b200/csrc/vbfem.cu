@@ -197,6 +197,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 }  // namespace vbfem
 #include "vbfem_front_kernel.cuh"
 #include "vbfem_panel.cuh"
+#include "vbfem_warp.cuh"
 namespace vbfem {
 
 // ------------------------------------------------------------------------------------------
@@ -950,6 +951,7 @@ static int fail(int code, const char *fmt, ...) {
 
 typedef void (*kernel_fn)(const DevModel, const Args);
 typedef void (*panel_fn)(const DevModel, const PanelModel, const Args);
+typedef void (*warp_fn)(const DevModel, const WarpModel, const Args);
 
 struct vbfem_handle {
     int device = 0;
@@ -962,6 +964,10 @@ struct vbfem_handle {
     // blocked panel kernel (wide bands, factor streamed to HBM)
     PanelModel PM{};
     panel_fn kern_panel[3] = {nullptr, nullptr, nullptr};
+    // warp-per-sample kernel (narrow bands, window in registers)
+    WarpModel WM{};
+    warp_fn kern_warp[3] = {nullptr, nullptr, nullptr};
+    int warp_nw = 0;
     // generic kernel configuration (fields mode, meshes neither fast kernel takes)
     DevModel M_gen{};
     int gen_block = 0, gen_ctas = 0;
@@ -1225,7 +1231,11 @@ struct PanelPlan {
     std::vector<double> rhs0;
 };
 
-static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2band, int n) {
+// nb_min > 0: the window is at least nb_min blocks wide (the warp kernel's register window has a fixed shape);
+// jit_batch > 0: element matrices are computed `jit_batch` at a time straight into the ring, right before the
+// first row that needs them (the warp kernel), instead of being fetched kPanelRecDepth rows ahead.
+static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2band, int n, int nb_min = 0,
+                            int jit_batch = 0) {
     PanelPlan P;
     auto no = [&](const char *why) {
         P.ok = false;
@@ -1282,6 +1292,7 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
             NB = std::max(NB, hi / 8 - lo / 8);
         }
     }
+    NB = std::max(NB, nb_min);
     if (NB > kPanelNBMax) return no("band wider than the panel kernel's window");
     P.NB = NB;
     const int NB1 = NB + 1;
@@ -1311,9 +1322,18 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
         for (int q = P.NQ - 1; q >= 0; --q) minpos[q] = std::min(minpos[q], minpos[q + 1]);
         // the element matrices of row q are fetched into the ring kPanelRecDepth rows ahead of the gather
         int R = P.eneed[std::min(NB, P.NQ - 1)];
-        for (int q = 0; q < P.NQ; ++q) {
-            const int ahead = P.eneed[std::min(q + kPanelRecDepth, P.NQ - 1)];
-            if (minpos[q] < ahead) R = std::max(R, ahead - minpos[q]);
+        if (jit_batch > 0) {
+            R = 1;
+            int computed = 0;
+            for (int q = 0; q < P.NQ; ++q) {
+                while (computed < P.eneed[q]) computed = std::min(computed + jit_batch, ne);
+                if (minpos[q] < computed) R = std::max(R, computed - minpos[q]);
+            }
+        } else {
+            for (int q = 0; q < P.NQ; ++q) {
+                const int ahead = P.eneed[std::min(q + kPanelRecDepth, P.NQ - 1)];
+                if (minpos[q] < ahead) R = std::max(R, ahead - minpos[q]);
+            }
         }
         P.R = R;
     }
@@ -1429,6 +1449,24 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
     if (P.stages < 2) return no("window too small for the reverse pass");
     P.ok = true;
     return P;
+}
+
+// Warp-per-sample kernel (vbfem_warp.cuh): chosen for narrow bands when enabled (VBFEM_WARP=0/1 overrides the default).
+constexpr bool kWarpDefault = false;
+static bool want_warp_kernel() {
+    if (getenv("VBFEM_FORCE_GENERIC") != nullptr || getenv("VBFEM_FORCE_PANEL") != nullptr) return false;
+    if (const char *e = getenv("VBFEM_WARP")) return atoi(e) != 0;
+    return kWarpDefault;
+}
+static int warp_kernel_warps() {
+    int NW = 12;
+    if (const char *e = getenv("VBFEM_WARP_NW")) NW = atoi(e);
+    return NW;
+}
+static int warp_kernel_smem(const PanelPlan &P) { return (kWarpFixed + (P.R * 36 + 2) * 8 + 15) & ~15; }
+static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
+    return P.ok && P.NB == kWarpNB && P.NQ > kWarpNB && (NW == 8 || NW == 12 || NW == 16) &&
+           (size_t)NW * warp_kernel_smem(P) <= smem_per_block;
 }
 
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
@@ -1640,6 +1678,80 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     h->info_colors = ncolors;
     const bool force_panel = getenv("VBFEM_FORCE_PANEL") != nullptr;
 
+    // ---- warp-per-sample kernel: narrow bands (block half bandwidth <= 3), window in registers, 12 samples per SM
+    if (!force_panel && want_warp_kernel()) {
+        PanelPlan P = plan_panel(m, dof2band, n, kWarpNB, kWarpBatch);
+        const int NW = warp_kernel_warps();
+        const int warp_smem = warp_kernel_smem(P);
+        if (warp_kernel_ok(P, NW, (size_t)prop.sharedMemPerBlockOptin)) {
+            WarpModel &Q = h->WM;
+            Q.n = P.n;
+            Q.off = P.off;
+            Q.npad = P.npad;
+            Q.NQ = P.NQ;
+            Q.R = P.R;
+            Q.nele = ne;
+            Q.obs_loc[0] = P.obs_loc[0];
+            Q.obs_loc[1] = P.obs_loc[1];
+            Q.warp_smem = warp_smem;
+            warp_fn ks[3];
+            if (NW == 8) {
+                ks[0] = fem_warp_kernel<0, 8>; ks[1] = fem_warp_kernel<1, 8>; ks[2] = fem_warp_kernel<2, 8>;
+            } else if (NW == 12) {
+                ks[0] = fem_warp_kernel<0, 12>; ks[1] = fem_warp_kernel<1, 12>; ks[2] = fem_warp_kernel<2, 12>;
+            } else {
+                ks[0] = fem_warp_kernel<0, 16>; ks[1] = fem_warp_kernel<1, 16>; ks[2] = fem_warp_kernel<2, 16>;
+            }
+            bool fits = true;
+            const size_t smem = (size_t)NW * warp_smem;
+            for (int q = 0; q < 3 && fits; ++q) {
+                cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                int nb = 0;
+                if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], NW * 32, smem);
+                if (e1 != cudaSuccess || nb < 1) {
+                    fits = false;
+                    cudaGetLastError();
+                }
+                h->kern_warp[q] = ks[q];
+            }
+            if (fits) {
+                std::vector<ushort4> gsrc4(P.gdst.size());
+                for (size_t i = 0; i < P.gdst.size(); ++i)
+                    gsrc4[i] = make_ushort4(P.gsrc[4 * i], P.gsrc[4 * i + 1], P.gsrc[4 * i + 2], P.gsrc[4 * i + 3]);
+                int rc2 = 0;
+                rc2 |= upload(h, P.gptr, &Q.gptr);
+                rc2 |= upload(h, P.gdst, &Q.gdst);
+                rc2 |= upload(h, gsrc4, &Q.gsrc);
+                rc2 |= upload(h, P.rhs0, &Q.rhs0);
+                rc2 |= upload(h, P.eneed, &Q.eneed);
+                rc2 |= upload(h, P.ecoord, &Q.ecoord);
+                rc2 |= upload(h, P.elm, &Q.elm);
+                if (rc2) return -2;
+                const long long nwarps = (long long)h->num_sms * NW;
+                Q.lws_stride = (long long)P.NQ * (kWarpNB + 2) * 64;
+                Q.xws_stride = 5LL * P.npad;
+                void *pl = nullptr, *px = nullptr;
+                CU(cudaMalloc(&pl, (size_t)nwarps * Q.lws_stride * sizeof(double)));
+                h->dev_allocs.push_back(pl);
+                CU(cudaMalloc(&px, (size_t)nwarps * Q.xws_stride * sizeof(double)));
+                h->dev_allocs.push_back(px);
+                Q.lws = (double *)pl;
+                Q.xws = (double *)px;
+                h->warp_nw = NW;
+                h->block = NW * 32;
+                h->ctas_per_sm = 1;
+                h->smem_bytes = smem;
+                h->variant = 4;
+                h->n_real = n;
+                h->PM.NB = kWarpNB;
+                h->PM.R = P.R;
+                guard.p = nullptr;
+                *out = h;
+                return 0;
+            }
+        }
+    }
+
     // ---- on-chip front kernel: band (n x 26 doubles) + five vectors must fit twice per SM
     {
         constexpr int TB = kFrontB, TP = kFrontP, TNT = kFrontNT;
@@ -1834,14 +1946,25 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
         const PanelPlan Q = plan_panel(m, dof2band, n);
         if (Q.ok) variant = 3;
     }
-    out[0] = variant;
     out[1] = n;
     out[2] = b;
+    out[7] = 0;
+    if (want_warp_kernel() && m->pf) {
+        const PanelPlan Q = plan_panel(m, dof2band, n, kWarpNB, kWarpBatch);
+        // 232448: shared memory a block may opt in to on B200 (sharedMemPerBlockOptin)
+        const size_t per_block = (size_t)std::min<int64_t>(smem_per_sm > 0 ? smem_per_sm : 233472, 232448);
+        if (warp_kernel_ok(Q, warp_kernel_warps(), per_block)) {
+            out[0] = 4;
+            out[3] = out[4] = out[5] = 0;
+            out[6] = (int64_t)warp_kernel_warps() * warp_kernel_smem(Q);
+            return 0;
+        }
+    }
+    out[0] = variant;
     out[3] = P.ok ? P.pT : 0;
     out[4] = P.ok ? n - P.pT - kFrontP : 0;
     out[5] = P.ok && P.flip;
     out[6] = P.ok ? (int64_t)front_smem_bytes(n) : 0;
-    out[7] = 0;
     return 0;
 }
 
@@ -1856,7 +1979,9 @@ extern "C" int64_t vbfem_debug_panel_tables(const vbfem_mesh *m, int which, void
     for (int i = 0; i < m->nfree; ++i) is_free[m->free_dof[i] - 1] = 1;
     std::vector<int> dof2band;
     choose_numbering(m, is_free, dof2band);
-    const PanelPlan P = plan_panel(m, dof2band, m->nfree);
+    const bool warp_plan = which >= 100;   // 100 + k: table k of the warp kernel's plan
+    if (warp_plan) which -= 100;
+    const PanelPlan P = warp_plan ? plan_panel(m, dof2band, m->nfree, kWarpNB, kWarpBatch) : plan_panel(m, dof2band, m->nfree);
     std::vector<int> hdr = {P.ok, P.n, P.off, P.npad, P.NQ, P.NB, P.R, P.nub, P.obs_loc[0], P.obs_loc[1],
                             P.flip, (int)P.gdst.size(), P.smem_bytes, P.stages, P.nele, kPanelEB};
     std::vector<int> ks(P.kstart, P.kstart + kPanelNW + 1);
@@ -1908,15 +2033,15 @@ extern "C" int vbfem_info(const vbfem_t *h, int64_t *out) {
     out[VBFEM_INFO_NDOF] = h->M.ndof;
     out[VBFEM_INFO_NELE] = h->M.nele;
     out[VBFEM_INFO_NCOLORS] = h->M.ncolors;
-    out[VBFEM_INFO_BAND_IN_SMEM] = h->variant == 3 ? 0 : h->M.band_in_smem;
+    out[VBFEM_INFO_BAND_IN_SMEM] = h->variant >= 3 ? 0 : h->M.band_in_smem;
     out[VBFEM_INFO_SMEM_BYTES] = (int64_t)h->smem_bytes;
     out[VBFEM_INFO_CTAS_PER_SM] = h->ctas_per_sm;
     out[VBFEM_INFO_NUM_SMS] = h->num_sms;
     out[VBFEM_INFO_BLOCK_THREADS] = h->block;
     out[VBFEM_INFO_KERNEL_VARIANT] = h->variant;
     out[VBFEM_INFO_TWIST_ROW] = h->variant == 2 ? h->M.pT : 0;
-    out[VBFEM_INFO_PANEL_BLOCKS] = h->variant == 3 ? h->PM.NB : 0;
-    out[VBFEM_INFO_PANEL_RING] = h->variant == 3 ? h->PM.R : 0;
+    out[VBFEM_INFO_PANEL_BLOCKS] = h->variant >= 3 ? h->PM.NB : 0;
+    out[VBFEM_INFO_PANEL_RING] = h->variant >= 3 ? h->PM.R : 0;
     return 0;
 }
 
@@ -2003,6 +2128,9 @@ static int launch(vbfem_handle *h, Args &a, void *stream) {
         a.timeline = h->timeline;
 #endif
         h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M, a);
+    } else if (h->variant == 4 && !fields) {
+        const long long grid = std::min<long long>(a.N, (long long)h->num_sms);
+        h->kern_warp[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->WM, a);
     } else if (h->variant == 3 && !fields) {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);
 #ifdef VBFEM_TIMELINE

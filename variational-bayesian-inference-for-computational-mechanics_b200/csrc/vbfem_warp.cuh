@@ -1,0 +1,506 @@
+// vbfem_warp.cuh -- narrow bands (Cook 20x10: n = 440, half bandwidth 25): ONE WARP per Monte-Carlo sample,
+// a dozen samples in flight per SM, the whole elimination window in REGISTERS.
+//
+// Same mathematics as the blocked panel kernel (vbfem_panel.cuh): 8x8 blocks, per panel the diagonal block is
+// factored (LDL^T) and its unit factor inverted, the blocks below become V = X L11^-T (two FP64 tensor-core
+// MMAs m8n8k4 per block) and the trailing window takes C -= L V^T (two more per block).  What is different:
+//   * the window -- (NB+1)(NB+2)/2 = 10 blocks for NB = 3, plus NB+1 right-hand-side blocks -- never leaves
+//     the register file: an 8x8 block in the MMA's C-fragment layout (lane (g, t) holds [g][2t], [g][2t+1]) IS
+//     the A and the B fragment of the next product when the contraction index is split {0,2,4,6} / {1,3,5,7},
+//     so solve -> scale -> update chain from registers to registers;
+//   * the window slides for free: the update of block (I, J) is written to the registers of block
+//     (I-1, J-1) (the MMA's D operand), nothing is copied;
+//   * there is no block barrier and no cross-warp traffic in the sample loop.  Warps of a CTA share nothing
+//     but the read-only tables; each pulls its next sample from a shared-memory counter;
+//   * shared memory per warp is the ring of element matrices (just-in-time batches of 32, lane = element:
+//     the per-element Q4 Gauss-point kernels of src/mat_subroutine_tf.py:23-110 upstream), the staging area
+//     of the block row that enters the window (atomics-free gather, same host table as the panel kernel) and
+//     a 1.5 KB exchange area for the diagonal block: ~17 KB, so 12-13 samples are resident per SM where the
+//     on-chip two-front kernel (97 KB of factor per sample) holds two.  The latency of one sample's pivot
+//     chain is hidden by the other samples; DMMA work (tensor pipe) and the diagonal-block factorisation
+//     (FP64 pipe) of different warps overlap.
+// With an adjoint (fused or Jacobian mode) the scaled panels leave for a per-warp slab in global memory as
+// plain 16-byte stores from the fragments and come back, fragment by fragment, in ONE reverse pass that
+// back-substitutes u and the adjoint vectors together -- again registers only.
+// Replaces tf.linalg.solve (src/fem_solver_tf.py:137 upstream) and its gradient.
+#pragma once
+#include "vbfem_panel.cuh"
+
+namespace vbfem {
+
+constexpr int kWarpNB = 3;      // block half bandwidth of the register window (8x8 blocks)
+constexpr int kWarpBatch = 32;  // element matrices per just-in-time batch (lane = element)
+constexpr int kWarpFixed = 1664 + (kWarpNB + 1) * 512;  // bytes per warp ahead of the element ring
+
+struct WarpModel {
+    int n, off, npad, NQ, R, nele;
+    int obs_loc[2];              // row inside the last panel of the observed node's (x, y) dof, -1 if supported
+    int warp_smem;               // bytes of shared memory per warp
+    const int *gptr;             // [NQ+1] gather entries of block row q: [gptr[q], gptr[q+1])
+    const unsigned short *gdst;  // target d * 64 + g * 8 + c (d: block diagonal)
+    const ushort4 *gsrc;         // up to four element-ring entries slot * 36 + tri (unused: the zero entry)
+    const double *rhs0;          // [NQ][64] initial right-hand-side blocks [a][c]
+    const int *eneed;            // [NQ] elements (first-use order) block row q needs
+    const double *ecoord;        // [nele][4][2] nodal coordinates, first-use order
+    const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported
+    double *lws;                 // per-warp factor slab [NQ][NB+2][64]
+    long long lws_stride;
+    double *xws;                 // per-warp solution vectors [5][npad]
+    long long xws_stride;
+};
+
+// LDL^T of an 8x8 diagonal block and the inverse of its unit factor, every lane redundantly in registers
+// (see fem_panel_kernel's diag_factor): D in shared memory, row major, lower triangle.  Writes
+// stg[c][k] = Minv[k][c], mro[k][c] = Minv[k][c] and rdo[k] = 1 / d_k.
+__device__ __forceinline__ void warp_diag_factor(const double *D, double *stg, double *rdo, double *mro, int *flag,
+                                                 int lane) {
+    double a[36];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; j += 2) {
+            const double2 v = reinterpret_cast<const double2 *>(D + i * 8)[j >> 1];
+            a[tri(i, j)] = v.x;
+            if (j + 1 <= i) a[tri(i, j + 1)] = v.y;
+        }
+    int bad = 0;
+    double rdv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double d = a[tri(k, k)];
+        bad |= !(d > 0.0 && d < 1.0e300);
+        rdv[k] = fast_rcp3(d);
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j) {
+            const double ljk = a[tri(j, k)] * rdv[k];
+#pragma unroll
+            for (int i = j; i < 8; ++i) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
+            a[tri(j, k)] = ljk;
+        }
+    }
+    if (bad && lane == 0) *flag = 1;
+    const int j = lane & 7;
+    double m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(a[tri(i, k)], m[k], acc);
+        m[i] = (i > j) ? -acc : m[i];
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mro[i * 8 + j] = m[i];
+    } else if (lane == 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) reinterpret_cast<double2 *>(rdo)[k >> 1] = make_double2(rdv[k], rdv[k + 1]);
+    }
+}
+
+// One just-in-time batch of element matrices (lane = element, first-use order) into the ring.  Kept out of line:
+// the 36 accumulators and the shape-function state would otherwise sit on top of the register window.
+__device__ __noinline__ void warp_element_batch(const double *__restrict__ ecoord, double *__restrict__ ke, int k,
+                                                int nele, int R, double thk, double lam, double mu) {
+    if (k >= nele) return;
+    Lame mat;
+    mat.lam = lam;
+    mat.mu = mu;
+    double xl[4], yl[4], kev[36];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const double2 xy = reinterpret_cast<const double2 *>(ecoord + (size_t)8 * k)[a];
+        xl[a] = xy.x;
+        yl[a] = xy.y;
+    }
+#pragma unroll
+    for (int q = 0; q < 36; ++q) kev[q] = 0.0;
+#pragma unroll 1
+    for (int gp = 0; gp < 4; ++gp) {
+        ShapeQ4 sh;
+        shapef_q4(xl, yl, gp, thk, sh);
+        double sig[4];
+        Tangent C;
+        mat_isotropic_plane_strain(mat, 0.0, 0.0, 0.0, sig, C);
+        accumulate_kt(sh, C, kev);
+    }
+    double2 *dst = reinterpret_cast<double2 *>(ke + (k % R) * 36);
+#pragma unroll
+    for (int q = 0; q < 18; ++q) dst[q] = make_double2(kev[2 * q], kev[2 * q + 1]);
+}
+
+// MODE 0: y, h   MODE 1: y, h, gx = J^T (gy, gh)   MODE 2: y, h, J = d(y, h)/dx
+template <int MODE, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_constant__ DevModel M,
+                                                              const __grid_constant__ WarpModel Q,
+                                                              const __grid_constant__ Args A) {
+    constexpr int NB = kWarpNB, NB1 = NB + 1, LPB = (NB + 2) * 64;
+    constexpr int NV = (MODE == 2) ? 5 : 2;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int next_i;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    unsigned char *wsm = smraw + (size_t)warp * Q.warp_smem;
+    double *dg = reinterpret_cast<double *>(wsm), *stg = dg + 64, *minv = dg + 128, *rd = dg + 192;
+    int *flagp = reinterpret_cast<int *>(wsm + 1600);
+    double *stage = reinterpret_cast<double *>(wsm + 1664);  // NB+1 blocks of the entering row, by block diagonal
+    double *ke = reinterpret_cast<double *>(wsm + kWarpFixed);  // R element matrices (36 each), then 0.0, 1.0
+    // after the forward pass the staging area holds the small vectors of the observation / reverse pass
+    double *sW = stage, *nodew = stage + 64, *nodeL = stage + 80, *sG = stage + 96, *lf_last = stage + 104,
+           *obs = stage + 112;
+    const int NQ = Q.NQ;
+    const int wid = blockIdx.x * NW + warp;
+    double *lws = Q.lws + (size_t)wid * Q.lws_stride;
+    double *xws = Q.xws + (size_t)wid * Q.xws_stride;
+    const double2 z2 = make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) next_i = 0;
+    if (lane == 0) {
+        ke[Q.R * 36] = 0.0;
+        ke[Q.R * 36 + 1] = 1.0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&next_i, 1);
+        it = __shfl_sync(kFull, it, 0);
+        const long long s = blockIdx.x + (long long)gridDim.x * it;
+        if (s >= A.N) break;
+
+        // ---------------- sample parameters: theta -> (E, nu) -> (lambda, mu)  (src/data_generation_2sam_more_loss.py:181-186)
+        double E_, nu_;
+        {
+            double x0, x1;
+            if (A.mode & kElbo) {
+                // main_custom_training.py:199-209: theta = e * sqrt(sig2) + mu, flattened [B*S]
+                const long long j = A.j_begin + s;
+                const int bb = (int)(j / A.S), ss = (int)(j % A.S);
+                x0 = A.e[2 * ss] * sqrt(A.sig2[2 * bb]) + A.mu[2 * bb];
+                x1 = A.e[2 * ss + 1] * sqrt(A.sig2[2 * bb + 1]) + A.mu[2 * bb + 1];
+            } else {
+                x0 = A.x[2 * s];
+                x1 = A.x[2 * s + 1];
+            }
+            E_ = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
+            nu_ = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
+        }
+        const Lame mat = lame_from_E_nu(E_, nu_);
+        if (lane == 0) *flagp = 0;
+
+        int computed = 0;  // element matrices (first-use order) in the ring so far
+        // (a) element matrices the block row q is the first to need, (b) gather of the row into the staging area
+        auto enter_row = [&](int q) {
+            const int need = Q.eneed[q];
+            while (computed < need) {
+                warp_element_batch(Q.ecoord, ke, computed + lane, Q.nele, Q.R, M.thk, mat.lam, mat.mu);
+                computed += kWarpBatch;
+            }
+            double2 *st2 = reinterpret_cast<double2 *>(stage);
+#pragma unroll
+            for (int i = 0; i < NB1; ++i) st2[i * 32 + lane] = z2;
+            __syncwarp();
+            const int e1 = Q.gptr[q + 1];
+            for (int i = Q.gptr[q] + lane; i < e1; i += 32) {
+                const int dst = Q.gdst[i];
+                const ushort4 sr = Q.gsrc[i];
+                stage[dst] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+            }
+            __syncwarp();
+        };
+
+        // ---------------- the window: block (p+I, p+J) in W[I][J] (J <= I), right-hand sides of block column p+J in Rh[J]
+        double2 W[NB1][NB1], Rh[NB1];
+#pragma unroll
+        for (int I = 0; I < NB1; ++I) {
+            Rh[I] = z2;
+#pragma unroll
+            for (int J = 0; J < NB1; ++J) W[I][J] = z2;
+        }
+#pragma unroll
+        for (int q = 0; q < NB1; ++q) {
+            enter_row(q);
+#pragma unroll
+            for (int d = 0; d <= q; ++d) W[q][q - d] = reinterpret_cast<const double2 *>(stage)[d * 32 + lane];
+            Rh[q] = reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64)[lane];
+            __syncwarp();
+        }
+
+        // ---------------- panels
+        double gacc = 0.0;  // partial sum over this lane's columns of G[g] = q_g^T K^-1 f
+        const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
+#pragma unroll 1
+        for (int p = 0; p < NQ; ++p) {
+            // ---- diagonal block: LDL^T, inverse of the unit factor
+            reinterpret_cast<double2 *>(dg)[lane] = W[0][0];
+            __syncwarp();
+            warp_diag_factor(dg, stg, rd, minv, flagp, lane);
+            __syncwarp();
+            const double2 mi = reinterpret_cast<const double2 *>(minv)[lane];  // Minv[g][2t..2t+1]
+            const double2 r2 = reinterpret_cast<const double2 *>(rd)[t];
+            // ---- solve: V = X L11^-T for the right-hand sides (b = 0) and the blocks below; Ln = -V D^-1
+            double2 V[NB1], Ln[NB1];
+#pragma unroll
+            for (int b = 0; b < NB1; ++b) {
+                const double2 xv = b ? W[b][0] : Rh[0];
+                double2 v = z2;
+                block_mma<true>(v, xv, mi, lane);
+                V[b] = v;
+                Ln[b] = make_double2(-v.x * r2.x, -v.y * r2.y);
+            }
+            {  // strain rows against the load row: G[g] += sum_c V[g][c] L[0][c]
+                const double lfx = __shfl_sync(kFull, Ln[0].x, t), lfy = __shfl_sync(kFull, Ln[0].y, t);
+                gacc = fma(V[0].x, -lfx, fma(V[0].y, -lfy, gacc));
+                if (p == NQ - 1 && g == 0) {
+                    lf_last[2 * t] = -Ln[0].x;
+                    lf_last[2 * t + 1] = -Ln[0].y;
+                }
+            }
+            if (MODE > 0) {
+                // the scaled panel leaves for the slab: [0] Minv^T, [1..NB] L^T blocks, [NB+1] D^-1 z rows, transposed
+                // on the tensor core (I * L^T leaves the transposed block in the C-fragment layout)
+                double2 *pan = reinterpret_cast<double2 *>(lws + (size_t)p * LPB);
+                pan[lane] = reinterpret_cast<const double2 *>(stg)[lane];
+#pragma unroll
+                for (int b = 0; b < NB1; ++b) {
+                    double2 lt = z2;
+                    block_mma<true>(lt, idf, Ln[b], lane);
+                    pan[(b ? b : NB + 1) * 32 + lane] = make_double2(-lt.x, -lt.y);
+                }
+            }
+            // ---- trailing update, written one block up and one block left: the window slides with the panel
+#pragma unroll
+            for (int I = 1; I <= NB; ++I)
+#pragma unroll
+                for (int J = 1; J <= I; ++J) {
+                    double2 c = W[I][J], e = z2;
+                    dmma884(c.x, c.y, Ln[I].x, V[J].x);
+                    dmma884(e.x, e.y, Ln[I].y, V[J].y);
+                    W[I - 1][J - 1] = make_double2(c.x + e.x, c.y + e.y);
+                }
+#pragma unroll
+            for (int J = 1; J <= NB; ++J) {
+                double2 c = Rh[J], e = z2;
+                dmma884(c.x, c.y, Ln[0].x, V[J].x);
+                dmma884(e.x, e.y, Ln[0].y, V[J].y);
+                Rh[J - 1] = make_double2(c.x + e.x, c.y + e.y);
+            }
+            // ---- block row p+NB+1 enters at the bottom of the window
+            const int q = p + NB1;
+            if (q < NQ) {
+                enter_row(q);
+#pragma unroll
+                for (int d = 0; d <= NB; ++d) W[NB][NB - d] = reinterpret_cast<const double2 *>(stage)[d * 32 + lane];
+                Rh[NB] = reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64)[lane];
+            } else {
+#pragma unroll
+                for (int d = 0; d <= NB; ++d) W[NB][d] = z2;
+                Rh[NB] = z2;
+            }
+        }
+
+        // ---------------- observations: y from the last diagonal block, strains from the accumulated products,
+        //                  h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
+        __syncwarp();
+        gacc += __shfl_xor_sync(kFull, gacc, 1);
+        gacc += __shfl_xor_sync(kFull, gacc, 2);
+        if (t == 0) sG[g] = gacc;
+        if (lane < 16) {  // D^-1 L11^-1 e_j for the observed node's dofs j (their unit vectors start in the last panel)
+            const int k = lane >> 3, c = lane & 7, j = Q.obs_loc[k];
+            nodeL[lane] = (j >= 0) ? stg[j * 8 + c] * rd[c] : 0.0;
+        }
+        __syncwarp();
+        if (lane < 2) {
+            const double exx = sG[1 + 3 * lane], eyy = sG[2 + 3 * lane], gxy = sG[3 + 3 * lane];
+            double sig[4];
+            Tangent C;
+            mat_isotropic_plane_strain(mat, exx, eyy, gxy, sig, C);
+            double ds[4];
+            const double hv = von_mises_ref(sig, ds);
+            const double l2m = mat.lam + 2.0 * mat.mu;
+            double *o = obs + 8 * lane;
+            o[0] = hv;
+            o[1] = ds[0] * l2m + ds[1] * mat.lam + ds[2] * mat.lam;  // dh/d(exx)
+            o[2] = ds[0] * mat.lam + ds[1] * l2m + ds[2] * mat.lam;  // dh/d(eyy)
+            o[3] = ds[3] * mat.mu;                                   // dh/d(gxy)
+            o[4] = (ds[0] + ds[1] + ds[2]) * (exx + eyy);            // dh/d(lambda) at fixed u
+            o[5] = 2.0 * ds[0] * exx + 2.0 * ds[1] * eyy + ds[3] * gxy;
+            if (A.h) A.h[2 * s + lane] = hv;
+            // y_k = (L11^-T D^-1 z_f)[j] = sum_c Minv[c][j] lf[c]
+            const int j = Q.obs_loc[lane];
+            double yv = 0.0;
+            if (j >= 0)
+                for (int c = 0; c < 8; ++c) yv = fma(stg[j * 8 + c], lf_last[c], yv);
+            obs[16 + lane] = yv;
+            if (A.y) A.y[2 * s + lane] = yv;
+            if (A.f_out) A.f_out[2 * s + lane] = yv;
+            if (!(fabs(yv) < 1.0e300) || !(hv < 1.0e300)) *flagp = 1;
+        }
+        __syncwarp();
+        if (MODE > 0) {
+            // ---------------- right-hand sides of the reverse pass: v = 0 is u (row 0 = D^-1 z_f); the adjoint
+            //                  vectors combine the strain rows and the observed node's unit vectors
+            sW[lane] = 0.0;
+            sW[32 + lane] = 0.0;
+            if (lane < 16) nodew[lane] = 0.0;
+            __syncwarp();
+            if (lane == 0) {
+                sW[0] = 1.0;
+                if (MODE == 1) {
+                    double gy0, gy1, gh0 = 0.0, gh1 = 0.0;
+                    if (A.mode & kElbo) {
+                        // d(loss)/d f_j through term2 with the [B, B*S] broadcast (main_custom_training.py:205-214)
+                        gy0 = A.gcoef * ((double)A.B * obs[16] - A.ysum[0]);
+                        gy1 = A.gcoef * ((double)A.B * obs[17] - A.ysum[1]);
+                    } else {
+                        gy0 = A.gy[2 * s];
+                        gy1 = A.gy[2 * s + 1];
+                        gh0 = A.gh[2 * s];
+                        gh1 = A.gh[2 * s + 1];
+                    }
+                    obs[20] = gh0;
+                    obs[21] = gh1;
+                    for (int i = 0; i < 3; ++i) {
+                        sW[8 + 1 + i] = gh0 * obs[1 + i];
+                        sW[8 + 4 + i] = gh1 * obs[8 + 1 + i];
+                    }
+                    nodew[2] = gy0;
+                    nodew[3] = gy1;
+                } else {
+                    // vectors 1, 2: adjoints of y0, y1; 3, 4: adjoints of h0, h1
+                    nodew[2 * 1] = 1.0;
+                    nodew[2 * 2 + 1] = 1.0;
+                    for (int i = 0; i < 3; ++i) {
+                        sW[3 * 8 + 1 + i] = obs[1 + i];
+                        sW[4 * 8 + 4 + i] = obs[8 + 1 + i];
+                    }
+                }
+            }
+            __syncwarp();
+            // ---------------- reverse pass: x_p = (W Lrhs_p - sum_b x_(p+b) L_(p+b,p)) Minv_p, panels descending,
+            //                  fragments straight from the slab (each lane reads back what it stored)
+            const double2 Wf = reinterpret_cast<const double2 *>(sW)[lane];
+            const double nw0 = nodew[2 * g], nw1 = nodew[2 * g + 1];
+            const double2 nl0 = make_double2(nodeL[2 * t], nodeL[2 * t + 1]),
+                          nl1 = make_double2(nodeL[8 + 2 * t], nodeL[8 + 2 * t + 1]);
+            double2 X[NB1];  // X[b] = -x_(p+b), b = 1..NB
+#pragma unroll
+            for (int b = 0; b < NB1; ++b) X[b] = z2;
+            double2 cur[NB + 2], nxt[NB + 2];
+            {
+                const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 1) * LPB);
+#pragma unroll
+                for (int b = 0; b < NB + 2; ++b) nxt[b] = pan[b * 32 + lane];
+            }
+#pragma unroll 1
+            for (int p = NQ - 1; p >= 0; --p) {
+#pragma unroll
+                for (int b = 0; b < NB + 2; ++b) cur[b] = nxt[b];
+                if (p > 0) {
+                    const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 1) * LPB);
+#pragma unroll
+                    for (int b = 0; b < NB + 2; ++b) nxt[b] = pan[b * 32 + lane];
+                }
+                double2 d = z2;
+                block_mma<true>(d, Wf, cur[NB + 1], lane);
+#pragma unroll
+                for (int b = 1; b <= NB; ++b) {
+                    double2 c = z2;
+                    block_mma<true>(c, X[b], cur[b], lane);
+                    d.x += c.x;
+                    d.y += c.y;
+                }
+                if (p == NQ - 1) {
+                    d.x += nw0 * nl0.x + nw1 * nl1.x;
+                    d.y += nw0 * nl0.y + nw1 * nl1.y;
+                }
+                double2 x = z2;
+                block_mma<true>(x, d, cur[0], lane);
+                if (g < NV) *reinterpret_cast<double2 *>(xws + (size_t)g * Q.npad + 8 * p + 2 * t) = x;
+#pragma unroll
+                for (int b = NB; b > 1; --b) X[b] = X[b - 1];
+                X[1] = make_double2(-x.x, -x.y);
+            }
+            __syncwarp();
+
+            // ---------------- element-wise contraction -psi^T (dK/dp) u + explicit dh/dp, chained to x
+            constexpr int NADJ = NV - 1;
+            double sl[NADJ], sm[NADJ];
+#pragma unroll
+            for (int v = 0; v < NADJ; ++v) sl[v] = sm[v] = 0.0;
+            for (int e = lane; e < M.nele; e += 32) {
+                double xl[4], yl[4], ue[8];
+                int lm[8];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int nd = M.ien[4 * e + a];
+                    const double2 xy = *reinterpret_cast<const double2 *>(M.coord + 2 * nd);
+                    xl[a] = xy.x;
+                    yl[a] = xy.y;
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    lm[a] = Q.elm[8 * e + a];
+                    ue[a] = (lm[a] >= 0) ? xws[lm[a]] : 0.0;
+                }
+#pragma unroll 1
+                for (int gp = 0; gp < 4; ++gp) {
+                    ShapeQ4 sh;
+                    shapef_q4(xl, yl, gp, M.thk, sh);
+                    double uxx, uyy, uxy;
+                    strain_q4(sh, ue, uxx, uyy, uxy);
+#pragma unroll
+                    for (int v = 0; v < NADJ; ++v) {
+                        const double *pv = xws + (size_t)(v + 1) * Q.npad;
+                        double pe[8], pxx, pyy, pxy, cl, cm;
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) pe[a] = (lm[a] >= 0) ? pv[lm[a]] : 0.0;
+                        strain_q4(sh, pe, pxx, pyy, pxy);
+                        mat_tangent_param_contract(pxx, pyy, pxy, uxx, uyy, uxy, cl, cm);
+                        sl[v] = fma(sh.dvol, cl, sl[v]);
+                        sm[v] = fma(sh.dvol, cm, sm[v]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NADJ; ++v)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sl[v] += __shfl_down_sync(kFull, sl[v], o);
+                    sm[v] += __shfl_down_sync(kFull, sm[v], o);
+                }
+            if (lane == 0) {
+                // d lambda, d mu / d(E, nu), then dE/dx0 = std0 * E ; dnu/dx1 = std1 * nu (1 - 2 nu)
+                const double E = E_, nu = nu_;
+                const double tt = (1.0 + nu) * (1.0 - 2.0 * nu);
+                const double dl_dE = mat.lam / E, dm_dE = mat.mu / E;
+                const double dl_dnu = E * (1.0 + 2.0 * nu * nu) / (tt * tt);
+                const double dm_dnu = -0.5 * E / ((1.0 + nu) * (1.0 + nu));
+                const double dE_dx0 = M.theta_std[0] * E, dnu_dx1 = M.theta_std[1] * nu * (1.0 - 2.0 * nu);
+                if (MODE == 1) {
+                    const double gh0 = obs[20], gh1 = obs[21];
+                    const double gl = -sl[0] + gh0 * obs[4] + gh1 * obs[8 + 4];
+                    const double gm = -sm[0] + gh0 * obs[5] + gh1 * obs[8 + 5];
+                    A.gx[2 * s] = (gl * dl_dE + gm * dm_dE) * dE_dx0;
+                    A.gx[2 * s + 1] = (gl * dl_dnu + gm * dm_dnu) * dnu_dx1;
+                } else {
+                    // adjoint vectors v = 0, 1: y0, y1; v = 2, 3: h0, h1 -- the storage order of J
+                    double *J = A.ws + (size_t)s * A.ws_stride;
+#pragma unroll
+                    for (int v = 0; v < NADJ; ++v) {
+                        const double gl = -sl[v] + (v >= 2 ? obs[8 * (v - 2) + 4] : 0.0);
+                        const double gm = -sm[v] + (v >= 2 ? obs[8 * (v - 2) + 5] : 0.0);
+                        J[2 * v] = (gl * dl_dE + gm * dm_dE) * dE_dx0;
+                        J[2 * v + 1] = (gl * dl_dnu + gm * dm_dnu) * dnu_dx1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && A.status) A.status[s] = *flagp;
+        __syncwarp();
+    }
+}
+
+}  // namespace vbfem

@@ -65,10 +65,19 @@ class MeasurementData:
     device = None            # CUDA device index (None = torch's current device)
 
     def __init__(self, n_sam, ne_sam, d_y, d_z, d_theta, sig_e, sig_eta):
+        # same attributes and initial values as upstream (src/data_generation_2sam_more_loss.py:22-39); no random
+        # draws here, so a seeded generate_data_fem consumes the generator exactly like upstream's
         self.n_sam, self.ne_sam = n_sam, ne_sam
         self.d_y, self.d_theta, self.d_z = d_y, d_theta, d_z
         self.sig_e, self.sig_eta = sig_e, sig_eta
-        self.e_data = np.random.randn(self.ne_sam, self.d_theta)
+        self.e_data = np.zeros((n_sam, d_theta))
+        self.y_data = np.zeros((n_sam, d_y))
+        self.y_scaled_data = np.zeros((n_sam, d_y))
+        self.z_data = np.zeros((n_sam, d_z))
+        self.log_z_data = np.zeros((n_sam, d_z))
+        self.z_scaled_data = np.zeros((n_sam, d_z))
+        self.y_mean, self.y_std = np.zeros((1, d_y)), np.zeros((1, d_y))
+        self.z_mean, self.z_std = np.zeros((1, d_z)), np.zeros((1, d_z))
 
     # ------------------------------------------------------------------ engine
     @classmethod
@@ -120,13 +129,15 @@ class MeasurementData:
 
     # ------------------------------------------------------------ data generation
     def generate_data_fem(self, rng=None):
-        """Synthetic observations (src/data_generation_2sam_more_loss.py:64-96)."""
-        rng = np.random.default_rng() if rng is None else rng
-        theta = rng.standard_normal((self.n_sam, self.d_theta))
-        err = math.sqrt(self.sig_e) * rng.standard_normal((self.n_sam, self.d_y))
-        eta = math.sqrt(self.sig_eta) * rng.standard_normal((self.n_sam, self.d_z))
-        self.e_data = rng.standard_normal((self.ne_sam, self.d_theta))
-        f, h = MeasurementData.fem_fh_fun_loop_rev(theta)
+        """Synthetic observations (src/data_generation_2sam_more_loss.py:64-96).  The random draws come from
+        NumPy's global generator in upstream's order -- theta, measurement noise, prediction noise, e_data -- so
+        ``np.random.seed(k)`` reproduces upstream's draws; ``rng`` (a ``RandomState`` / ``Generator``) overrides."""
+        randn = np.random.randn if rng is None else (lambda *s: rng.standard_normal(s))
+        theta = randn(self.n_sam, self.d_theta)
+        err = math.sqrt(self.sig_e) * randn(self.n_sam, self.d_y)
+        eta = math.sqrt(self.sig_eta) * randn(self.n_sam, self.d_z)
+        self.e_data = randn(self.ne_sam, self.d_theta)
+        f, h = MeasurementData.fem_fh_fun_loop_rev(theta)   # one batched launch instead of tf.map_fn
         self.theta_data = theta
         self.y_data = f + err
         self.y_mean = np.mean(self.y_data, axis=0, keepdims=True)
@@ -135,3 +146,19 @@ class MeasurementData:
         self.log_z_data = np.log(self.z_data)
         self.z_mean = np.mean(self.z_data, axis=0, keepdims=True)
         self.z_std = np.std(self.z_data, axis=0, keepdims=True)
+
+    def save_data(self, file_path, file_name):
+        """The ten datasets of src/data_generation_2sam_more_loss.py:256-268, written as the same kind of
+        MATLAB-7.3 / HDF5 file ``hdf5storage.write`` produces (h5io.write; upstream passes path= and
+        filename= the same way)."""
+        from . import h5io
+        data_dic = {"y_data": self.y_data, "y_scaled_data": self.y_data, "z_data": self.z_data,
+                    "log_z_data": self.log_z_data, "z_scaled_data": self.z_data, "y_mean": self.y_mean,
+                    "y_std": self.y_std, "z_mean": self.z_mean, "z_std": self.z_std, "e_data": self.e_data}
+        h5io.write(data=data_dic, path=file_path, filename=file_name)
+
+    @staticmethod
+    def load_data(file_path, file_name):
+        """``hdf5storage.read(path=..., filename=...)`` as main_custom_training.py:76 calls it: name -> array."""
+        from . import h5io
+        return h5io.read(path=file_path, filename=file_name)

@@ -2,10 +2,12 @@
 library, installed over ``MeasurementData.fem_fh_fun_loop_rev`` so that
 upstream's ``main_custom_training.py`` trains through the CUDA solver.
 
-TensorFlow is not part of this image, so this module is import-guarded and is
-exercised only where TF exists; the torch ``autograd.Function`` in
-``data_generation_2sam_more_loss`` is the tested twin with identical
-semantics.  Graph mode (``tf.function``) cannot hand device pointers to
+TensorFlow is not part of this image: the module is import-guarded, and CI drives
+it end to end against a minimal stand-in for the handful of TF entry points it
+uses (tests/fake_tf.py: custom_gradient contract, py_function, DLPack round trip
+through torch) -- real graph-mode TF remains untested here.  The torch
+``autograd.Function`` in ``data_generation_2sam_more_loss`` is the twin with
+identical semantics.  Graph mode (``tf.function``) cannot hand device pointers to
 ctypes, so the op body runs in a ``tf.py_function`` eager island and moves
 tensors by DLPack (zero-copy on the same GPU).
 """
@@ -33,26 +35,27 @@ def make_fem_fh_op():
         eng = _engine()
         with tf.device(f"/GPU:{eng.device_index}"):
             xt = to_torch(tf.identity(x))
-        y, h = eng.forward(xt, keep_factor=True)
+        # the closure owns its state: the per-sample 4x2 Jacobians travel with THIS call's gradient function
+        y, h, jac = eng.forward_jac(xt)
         torch.cuda.current_stream(eng.device).synchronize()
-        return to_tf(y), to_tf(h)
+        return to_tf(y), to_tf(h), to_tf(jac.reshape(-1, 8))
 
-    def _bwd(gy, gh):
+    def _bwd(jac, gy, gh):
         eng = _engine()
         with tf.device(f"/GPU:{eng.device_index}"):
-            gyt, ght = to_torch(tf.identity(gy)), to_torch(tf.identity(gh))
-        gx = eng.backward(gyt, ght)
+            jt, gyt, ght = to_torch(tf.identity(jac)), to_torch(tf.identity(gy)), to_torch(tf.identity(gh))
+        gx = eng.jac_vjp(jt.reshape(-1, 4, 2), gyt, ght)
         torch.cuda.current_stream(eng.device).synchronize()
         return to_tf(gx)
 
     @tf.custom_gradient
     def fem_fh(x):
-        y, h = tf.py_function(_fwd, [x], [tf.float64, tf.float64])
+        y, h, jac = tf.py_function(_fwd, [x], [tf.float64, tf.float64, tf.float64])
         y.set_shape(x.shape)
         h.set_shape(x.shape)
 
         def grad(gy, gh):
-            gx = tf.py_function(_bwd, [gy, gh], tf.float64)
+            gx = tf.py_function(_bwd, [jac, gy, gh], tf.float64)
             gx.set_shape(x.shape)
             return gx
 
