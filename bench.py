@@ -117,6 +117,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baselines beside the GPU numbers
 # ------------------------------------------------------------------------------------------------
+def host_cores():
+    """Host cores this process may use: affinity mask, capped by the cgroup CPU quota (the GPU boxes expose
+    every core of the machine to os.cpu_count() but give the container a slice) and by 32."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))
+
+
 def tf_status():
     """the reference TF path, if TensorFlow exists on the box."""
     try:
@@ -160,9 +173,10 @@ def time_numpy_twin(per_core=8):
         return "reference tree absent on this box (the statement-by-statement port stands in: " \
                "cpu_baseline.statement_by_statement_port)"
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     x = np.random.default_rng(0).standard_normal((cores * per_core, 2))
     t0 = time.perf_counter()
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"   # one core per worker process
     with mp.get_context("spawn").Pool(cores) as pool:
         inner = pool.map(_twin_worker, [x[i::cores] for i in range(cores)])
     wall = time.perf_counter() - t0
@@ -183,8 +197,9 @@ def time_loop_port(per_core=4):
     """The statement-by-statement port of the reference NumPy twin (oracle LoopOracle: element and Gauss
     loops as upstream) on all host cores, one process per core."""
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     x = np.random.default_rng(0).standard_normal((cores * per_core, 2))
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"   # one core per worker process
     with mp.get_context("spawn").Pool(cores) as pool:
         inner = pool.map(_loop_worker, [x[i::cores] for i in range(cores)])
     return {"value": len(x) / max(inner), "unit": "forward solves/s", "cores": cores, "kind": "port",
@@ -227,9 +242,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core at every N.  The thread count must be
+    # fixed through the environment BEFORE torch is imported (torch.set_num_threads breaks MKL's batched LU here:
+    # "Parameter 6 was incorrect on entry to DLASWP").
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(host_cores())
     import torch
-    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core at every N
-    torch.set_num_threads(os.cpu_count() or 1)
     fo, to, mesh, dof = oracle()
     sample = 256
     x, gy, gh = inputs(0)
@@ -466,7 +483,6 @@ def run_cuda(args):
         tflops = FLOP_PER_SOLVE * BATCH / launch_s / 1e12
         cpu = cpu_elbo = cpu4 = None
         if world == 1 and not args.no_cpu_baseline:
-            torch.set_num_threads(os.cpu_count() or 1)
             fo, to, mesh, dof = oracle()
             ns = 1536
             cpu_fwd_adjoint(to, xh[:256], gyh[:256], ghh[:256])

@@ -574,3 +574,38 @@ def test_tf_bridge_contract_with_stand_in_tf(pkg, engine, golden, torch_oracle, 
     assert relerr(gxa.numpy(), torch_oracle.vjp(golden["x"][:8], gy, gh)[2]) < TOL
     assert relerr(gxb.numpy(), torch_oracle.vjp(golden["x"][8:], gy, gh)[2]) < TOL
     assert tuple(M.nipt_id) == (1, 3) and M.node_id == 231   # install keeps the class attributes in sync
+
+
+def test_small_batch_host_path_and_mcmc_log_posterior(pkg, engine, golden, torch_oracle):
+    """The one-sample-at-a-time callers (src/postprocess_lib.py:78-103): batches of 1, 8 and 64 on mapped
+    pinned memory give the device path's numbers bit for bit; logp_y_2d equals upstream's expression on the
+    oracle's f; a short Metropolis chain runs through it; the large-batch KDE sampler agrees with the oracle."""
+    import torch
+    for n in (1, 8, 64, 65):
+        x = np.random.default_rng(n).standard_normal((n, 2))
+        gy, gh = np.random.default_rng(n + 1).standard_normal((n, 2)), np.random.default_rng(n + 2).standard_normal((n, 2))
+        y, h, gx = engine.forward_backward(_t(x, engine), _t(gy, engine), _t(gh, engine))
+        yh, hh, gxh = engine.forward_backward_host(x, gy, gh)
+        yf, hf = engine.forward_host(x)
+        assert np.array_equal(yh, y.cpu().numpy()) and np.array_equal(gxh, gx.cpu().numpy())
+        assert np.array_equal(yf, yh) and np.array_equal(hf, hh) and np.array_equal(hh, h.cpu().numpy())
+    M, PP = pkg.MeasurementData, pkg.postprocess_lib.PostProcess
+    pkg.PreProcessing.reset()
+    pkg.PreProcessing.model_data = golden_model_of(engine)
+    M.theta_mean, M.theta_std = np.array([math.log(20.0), 0.0]), np.array([0.1, 0.015])
+    M.node_id, M.ele_id, M.nipt_id = 231, 12, np.array([1, 3], dtype=int)
+    y_obs, sig_e = np.array([-4.1, 5.6]), 0.1
+    logp = PP.logp_y_2d(y_obs, sig_e)
+    for th in golden["x"][:4]:
+        f = torch_oracle.fem_fh(torch.tensor(th[None]))[0].numpy()
+        ref = -0.5 / sig_e * np.sum((y_obs - f) ** 2) - np.log(2 * np.pi * sig_e) - 0.5 * np.sum(th ** 2) - np.log(2 * np.pi)
+        assert abs(logp(th) - ref) < 1e-9 * abs(ref)
+    chain = pkg.postprocess_lib.metropolis_chain(logp, np.zeros(2), 60, burn=20, thin=2, scale=0.5,
+                                                 rng=np.random.default_rng(0))
+    assert chain.shape == (20, 2) and np.isfinite(chain).all() and len(np.unique(chain[:, 0])) > 3
+    zm, zv = PP.moments_2d_case4_method1(np.zeros((3, 2)), np.ones((3, 2)), 3e-3, 50, rng=np.random.default_rng(1))
+    rng = np.random.default_rng(1)
+    theta = rng.standard_normal((50, 2))            # std = 1, mean = 0: the same draw for every observation
+    eta = np.sqrt(3e-3) * rng.standard_normal((50, 2))
+    z = torch_oracle.fem_fh(torch.tensor(theta))[1].numpy() + eta
+    assert relerr(zm, np.tile(z.mean(0), (3, 1))) < TOL and relerr(zv, np.tile(z.var(0), (3, 1))) < 1e-8

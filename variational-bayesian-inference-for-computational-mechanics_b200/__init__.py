@@ -8,7 +8,7 @@ The directory name contains hyphens; import it with
 or through the ``vbfem_b200`` alias at the repository root.
 """
 from . import _lib  # noqa: F401
-from . import fem_preprocess, fem_postprocess, fem_solver, data_generation_2sam_more_loss, elbo, h5io  # noqa: F401
+from . import fem_preprocess, fem_postprocess, fem_solver, data_generation_2sam_more_loss, elbo, h5io, postprocess_lib  # noqa: F401
 from ._lib import VbfemError, build, load  # noqa: F401
 from .fem_preprocess import PreProcessing, cook_membrane_feap  # noqa: F401
 from .fem_solver import CookFemEngine, FemSolver  # noqa: F401
