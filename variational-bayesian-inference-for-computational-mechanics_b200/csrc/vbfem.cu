@@ -1463,10 +1463,17 @@ static int warp_kernel_warps() {
     if (const char *e = getenv("VBFEM_WARP_NW")) NW = atoi(e);
     return NW;
 }
+static int warp_kernel_batch() {
+    int b = 30;  // 30 instead of 32 elements per batch: ring of 44 instead of 46 matrices on Cook 20x10 -> 14 warps fit
+    if (const char *e = getenv("VBFEM_WARP_BATCH")) b = atoi(e);
+    return std::min(std::max(b, 1), kWarpBatch);
+}
 static int warp_kernel_smem(const PanelPlan &P) { return (kWarpFixed + (P.R * 36 + 2) * 8 + 15) & ~15; }
+static int warp_kernel_tab_bytes(const PanelPlan &P) { return (int)((P.gdst.size() * 8 + (size_t)(P.NQ + 1) * 8 + 15) & ~(size_t)15); }
 static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
-    return P.ok && P.NB == kWarpNB && P.NQ > kWarpNB && (NW == 8 || NW == 12 || NW == 16) &&
-           (size_t)NW * warp_kernel_smem(P) <= smem_per_block;
+    // 11-bit ring indices and 8-bit targets in the packed gather table
+    return P.ok && P.NB == kWarpNB && P.NQ > kWarpNB && P.R * 36 + 2 <= 2048 && (NW == 8 || NW == 12 || NW == 16) &&
+           (size_t)NW * warp_kernel_smem(P) + warp_kernel_tab_bytes(P) <= smem_per_block;
 }
 
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
@@ -1680,7 +1687,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
 
     // ---- warp-per-sample kernel: narrow bands (block half bandwidth <= 3), window in registers, 12 samples per SM
     if (!force_panel && want_warp_kernel()) {
-        PanelPlan P = plan_panel(m, dof2band, n, kWarpNB, kWarpBatch);
+        PanelPlan P = plan_panel(m, dof2band, n, kWarpNB, warp_kernel_batch());
         const int NW = warp_kernel_warps();
         const int warp_smem = warp_kernel_smem(P);
         if (warp_kernel_ok(P, NW, (size_t)prop.sharedMemPerBlockOptin)) {
@@ -1691,6 +1698,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             Q.NQ = P.NQ;
             Q.R = P.R;
             Q.nele = ne;
+            Q.batch = warp_kernel_batch();
             Q.obs_loc[0] = P.obs_loc[0];
             Q.obs_loc[1] = P.obs_loc[1];
             Q.warp_smem = warp_smem;
@@ -1703,7 +1711,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                 ks[0] = fem_warp_kernel<0, 16>; ks[1] = fem_warp_kernel<1, 16>; ks[2] = fem_warp_kernel<2, 16>;
             }
             bool fits = true;
-            const size_t smem = (size_t)NW * warp_smem;
+            const size_t smem = (size_t)NW * warp_smem + warp_kernel_tab_bytes(P);
             for (int q = 0; q < 3 && fits; ++q) {
                 cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 int nb = 0;
@@ -1715,17 +1723,31 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                 h->kern_warp[q] = ks[q];
             }
             if (fits) {
-                std::vector<ushort4> gsrc4(P.gdst.size());
-                for (size_t i = 0; i < P.gdst.size(); ++i)
-                    gsrc4[i] = make_ushort4(P.gsrc[4 * i], P.gsrc[4 * i + 1], P.gsrc[4 * i + 2], P.gsrc[4 * i + 3]);
+                std::vector<unsigned long long> gpack(P.gdst.size());
+                for (size_t i = 0; i < P.gdst.size(); ++i) {
+                    unsigned long long w = (unsigned long long)P.gdst[i] << 44;
+                    for (int k = 0; k < 4; ++k) w |= (unsigned long long)P.gsrc[4 * i + k] << (11 * k);
+                    gpack[i] = w;
+                }
+                std::vector<int2> rowtab(P.NQ + 1);
+                for (int q = 0; q <= P.NQ; ++q) {
+                    int flag = 0;
+                    if (q < P.NQ)
+                        for (int i = 0; i < 64; ++i) flag |= P.rhs0[(size_t)q * 64 + i] != 0.0;
+                    rowtab[q] = make_int2(P.gptr[q], (q < P.NQ ? P.eneed[q] : ne) | (flag << 30));
+                }
+                Q.nent = (int)gpack.size();
+                Q.tab_bytes = warp_kernel_tab_bytes(P);
                 int rc2 = 0;
-                rc2 |= upload(h, P.gptr, &Q.gptr);
-                rc2 |= upload(h, P.gdst, &Q.gdst);
-                rc2 |= upload(h, gsrc4, &Q.gsrc);
+                rc2 |= upload(h, gpack, &Q.gpack);
+                rc2 |= upload(h, rowtab, &Q.rowtab);
                 rc2 |= upload(h, P.rhs0, &Q.rhs0);
-                rc2 |= upload(h, P.eneed, &Q.eneed);
                 rc2 |= upload(h, P.ecoord, &Q.ecoord);
-                rc2 |= upload(h, P.elm, &Q.elm);
+                std::vector<int> elm_fu((size_t)8 * ne);  // band rows of the element dofs, elements in first-use order
+                for (int k = 0; k < ne; ++k)
+                    for (int a = 0; a < 8; ++a) elm_fu[8 * k + a] = P.elm[8 * P.eord[k] + a];
+                rc2 |= upload(h, elm_fu, &Q.elm);
+                Q.x_in_smem = (size_t)2 * P.npad <= (size_t)P.R * 36;
                 if (rc2) return -2;
                 const long long nwarps = (long long)h->num_sms * NW;
                 Q.lws_stride = (long long)P.NQ * (kWarpNB + 2) * 64;
@@ -1950,13 +1972,13 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
     out[2] = b;
     out[7] = 0;
     if (want_warp_kernel() && m->pf) {
-        const PanelPlan Q = plan_panel(m, dof2band, n, kWarpNB, kWarpBatch);
+        const PanelPlan Q = plan_panel(m, dof2band, n, kWarpNB, warp_kernel_batch());
         // 232448: shared memory a block may opt in to on B200 (sharedMemPerBlockOptin)
         const size_t per_block = (size_t)std::min<int64_t>(smem_per_sm > 0 ? smem_per_sm : 233472, 232448);
         if (warp_kernel_ok(Q, warp_kernel_warps(), per_block)) {
             out[0] = 4;
             out[3] = out[4] = out[5] = 0;
-            out[6] = (int64_t)warp_kernel_warps() * warp_kernel_smem(Q);
+            out[6] = (int64_t)warp_kernel_warps() * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
             return 0;
         }
     }
@@ -1981,7 +2003,7 @@ extern "C" int64_t vbfem_debug_panel_tables(const vbfem_mesh *m, int which, void
     choose_numbering(m, is_free, dof2band);
     const bool warp_plan = which >= 100;   // 100 + k: table k of the warp kernel's plan
     if (warp_plan) which -= 100;
-    const PanelPlan P = warp_plan ? plan_panel(m, dof2band, m->nfree, kWarpNB, kWarpBatch) : plan_panel(m, dof2band, m->nfree);
+    const PanelPlan P = warp_plan ? plan_panel(m, dof2band, m->nfree, kWarpNB, warp_kernel_batch()) : plan_panel(m, dof2band, m->nfree);
     std::vector<int> hdr = {P.ok, P.n, P.off, P.npad, P.NQ, P.NB, P.R, P.nub, P.obs_loc[0], P.obs_loc[1],
                             P.flip, (int)P.gdst.size(), P.smem_bytes, P.stages, P.nele, kPanelEB};
     std::vector<int> ks(P.kstart, P.kstart + kPanelNW + 1);
@@ -2130,6 +2152,13 @@ static int launch(vbfem_handle *h, Args &a, void *stream) {
         h->kern_front[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M, a);
     } else if (h->variant == 4 && !fields) {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms);
+#ifdef VBFEM_TIMELINE
+        if (!h->timeline) {
+            CU(cudaMalloc(&h->timeline, (size_t)h->num_sms * 2 * 4 * 16 * sizeof(long long)));
+        }
+        CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * 4 * 16 * sizeof(long long), st));
+        a.timeline = h->timeline;
+#endif
         h->kern_warp[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->WM, a);
     } else if (h->variant == 3 && !fields) {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);

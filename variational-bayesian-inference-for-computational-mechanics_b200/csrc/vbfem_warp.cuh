@@ -29,32 +29,39 @@
 namespace vbfem {
 
 constexpr int kWarpNB = 3;      // block half bandwidth of the register window (8x8 blocks)
-constexpr int kWarpBatch = 32;  // element matrices per just-in-time batch (lane = element)
+constexpr int kWarpBatch = 32;  // element matrices per just-in-time batch (lane = element); WarpModel::batch may be smaller
 constexpr int kWarpFixed = 1664 + (kWarpNB + 1) * 512;  // bytes per warp ahead of the element ring
 
 struct WarpModel {
     int n, off, npad, NQ, R, nele;
+    int batch;                   // element matrices per just-in-time batch (<= 32: lanes >= batch idle)
     int obs_loc[2];              // row inside the last panel of the observed node's (x, y) dof, -1 if supported
     int warp_smem;               // bytes of shared memory per warp
-    const int *gptr;             // [NQ+1] gather entries of block row q: [gptr[q], gptr[q+1])
-    const unsigned short *gdst;  // target d * 64 + g * 8 + c (d: block diagonal)
-    const ushort4 *gsrc;         // up to four element-ring entries slot * 36 + tri (unused: the zero entry)
+    int nent, tab_bytes;         // gather entries; bytes of the CTA-shared tables ahead of the per-warp areas
+    // Gather table, one 64-bit word per target entry of the lower band: bits [0, 44) four 11-bit element-ring
+    // entries slot * 36 + tri (unused: the zero entry), bits [44, 52) the target d * 64 + g * 8 + c (d: block
+    // diagonal).  Row table: {first gather entry of block row q, elements (first-use order) the row needs
+    // | 1 << 30 if the row has a non-zero initial right-hand-side block}.  Both are copied to shared memory once
+    // per CTA.
+    const unsigned long long *gpack;
+    const int2 *rowtab;          // [NQ+1]
     const double *rhs0;          // [NQ][64] initial right-hand-side blocks [a][c]
-    const int *eneed;            // [NQ] elements (first-use order) block row q needs
     const double *ecoord;        // [nele][4][2] nodal coordinates, first-use order
-    const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported
+    const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported; first-use order
+    int x_in_smem;               // fused adjoint: u and psi live in the (then idle) element ring instead of xws
     double *lws;                 // per-warp factor slab [NQ][NB+2][64]
     long long lws_stride;
     double *xws;                 // per-warp solution vectors [5][npad]
     long long xws_stride;
 };
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // LDL^T of an 8x8 diagonal block and the inverse of its unit factor, every lane redundantly in registers
 // (see fem_panel_kernel's diag_factor): D in shared memory, row major, lower triangle.  Writes
 // stg[c][k] = Minv[k][c], mro[k][c] = Minv[k][c] and rdo[k] = 1 / d_k.
-__device__ __forceinline__ void warp_diag_factor(const double *D, double *stg, double *rdo, double *mro, int *flag,
-                                                 int lane) {
-    double a[36];
+__device__ __forceinline__ void warp_diag_load(const double *D, double (&a)[36]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -63,6 +70,9 @@ __device__ __forceinline__ void warp_diag_factor(const double *D, double *stg, d
             a[tri(i, j)] = v.x;
             if (j + 1 <= i) a[tri(i, j + 1)] = v.y;
         }
+}
+__device__ __forceinline__ void warp_diag_compute(double (&a)[36], double *stg, double *rdo, double *mro, int *flag,
+                                                  int lane) {
     int bad = 0;
     double rdv[8];
 #pragma unroll
@@ -79,17 +89,15 @@ __device__ __forceinline__ void warp_diag_factor(const double *D, double *stg, d
         }
     }
     if (bad && lane == 0) *flag = 1;
+    // column j of the inverse of the unit factor, column oriented (dependency depth 7 instead of 28)
     const int j = lane & 7;
     double m[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 1; i < 8; ++i) {
-        double acc = 0.0;
+    for (int k = 0; k < 7; ++k)
 #pragma unroll
-        for (int k = 0; k < i; ++k) acc = fma(a[tri(i, k)], m[k], acc);
-        m[i] = (i > j) ? -acc : m[i];
-    }
+        for (int i = k + 1; i < 8; ++i) m[i] = fma(-a[tri(i, k)], m[k], m[i]);  // m[k] = 0 for k < j: rows above j stay 0
     if (lane < 8) {
 #pragma unroll
         for (int i = 0; i < 8; i += 2) reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
@@ -132,6 +140,25 @@ __device__ __noinline__ void warp_element_batch(const double *__restrict__ ecoor
     for (int q = 0; q < 18; ++q) dst[q] = make_double2(kev[2 * q], kev[2 * q + 1]);
 }
 
+#ifdef VBFEM_TIMELINE
+#define WTL_DECL long long wtl[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, wtl_t = clock64()
+#define WTL(i)                            \
+    do {                                  \
+        const long long now_ = clock64(); \
+        wtl[i] += now_ - wtl_t;           \
+        wtl_t = now_;                     \
+    } while (0)
+#define WTL_FLUSH                                                                   \
+    do {                                                                            \
+        if (A.timeline && lane == 0 && warp < 4)                                    \
+            for (int i_ = 0; i_ < 16; ++i_) A.timeline[(blockIdx.x * 4 + warp) * 16 + i_] = wtl[i_]; \
+    } while (0)
+#else
+#define WTL_DECL ((void)0)
+#define WTL(i) ((void)0)
+#define WTL_FLUSH ((void)0)
+#endif
+
 // MODE 0: y, h   MODE 1: y, h, gx = J^T (gy, gh)   MODE 2: y, h, J = d(y, h)/dx
 template <int MODE, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_constant__ DevModel M,
@@ -142,7 +169,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int next_i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    unsigned char *wsm = smraw + (size_t)warp * Q.warp_smem;
+    const unsigned long long *gtab = reinterpret_cast<const unsigned long long *>(smraw);
+    const int2 *rowtab = reinterpret_cast<const int2 *>(smraw + (size_t)Q.nent * 8);
+    unsigned char *wsm = smraw + Q.tab_bytes + (size_t)warp * Q.warp_smem;
     double *dg = reinterpret_cast<double *>(wsm), *stg = dg + 64, *minv = dg + 128, *rd = dg + 192;
     int *flagp = reinterpret_cast<int *>(wsm + 1600);
     double *stage = reinterpret_cast<double *>(wsm + 1664);  // NB+1 blocks of the entering row, by block diagonal
@@ -156,6 +185,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
     double *xws = Q.xws + (size_t)wid * Q.xws_stride;
     const double2 z2 = make_double2(0.0, 0.0);
     if (threadIdx.x == 0) next_i = 0;
+    for (int i = threadIdx.x; i < Q.nent; i += NW * 32) reinterpret_cast<unsigned long long *>(smraw)[i] = Q.gpack[i];
+    for (int i = threadIdx.x; i <= Q.NQ; i += NW * 32) reinterpret_cast<int2 *>(smraw + (size_t)Q.nent * 8)[i] = Q.rowtab[i];
     if (lane == 0) {
         ke[Q.R * 36] = 0.0;
         ke[Q.R * 36 + 1] = 1.0;
@@ -188,26 +219,37 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
         }
         const Lame mat = lame_from_E_nu(E_, nu_);
         if (lane == 0) *flagp = 0;
+        WTL_DECL;
 
         int computed = 0;  // element matrices (first-use order) in the ring so far
-        // (a) element matrices the block row q is the first to need, (b) gather of the row into the staging area
-        auto enter_row = [&](int q) {
-            const int need = Q.eneed[q];
+        // Block row q enters the window in two steps around a warp barrier: (a) the element matrices the row is the
+        // first to need (just-in-time batch) and a cleared staging area, (b) the atomics-free gather of the row's
+        // lower-band entries from the ring (at most 96 per row: three predicated trips, no loop, so that the
+        // scheduler can interleave them with the diagonal block's factorisation).
+        auto row_prepare = [&](int q) {
+            const int need = rowtab[q].y & 0x3fffffff;
             while (computed < need) {
-                warp_element_batch(Q.ecoord, ke, computed + lane, Q.nele, Q.R, M.thk, mat.lam, mat.mu);
-                computed += kWarpBatch;
+                warp_element_batch(Q.ecoord, ke, lane < Q.batch ? computed + lane : Q.nele, Q.nele, Q.R, M.thk, mat.lam,
+                                   mat.mu);
+                computed += Q.batch;
             }
             double2 *st2 = reinterpret_cast<double2 *>(stage);
 #pragma unroll
             for (int i = 0; i < NB1; ++i) st2[i * 32 + lane] = z2;
-            __syncwarp();
-            const int e1 = Q.gptr[q + 1];
-            for (int i = Q.gptr[q] + lane; i < e1; i += 32) {
-                const int dst = Q.gdst[i];
-                const ushort4 sr = Q.gsrc[i];
-                stage[dst] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+        };
+        auto row_gather = [&](int q) {
+            const int e0 = rowtab[q].x, e1 = rowtab[q + 1].x;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int i = e0 + lane + 32 * r;
+                if (i < e1) {
+                    const unsigned long long w = gtab[i];
+                    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+                    const double v = ((ke[lo & 2047u] + ke[(lo >> 11) & 2047u]) + ke[(unsigned)(w >> 22) & 2047u]) +
+                                     ke[(hi >> 1) & 2047u];
+                    stage[(hi >> 12) & 255u] = v;
+                }
             }
-            __syncwarp();
         };
 
         // ---------------- the window: block (p+I, p+J) in W[I][J] (J <= I), right-hand sides of block column p+J in Rh[J]
@@ -220,23 +262,31 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
         }
 #pragma unroll
         for (int q = 0; q < NB1; ++q) {
-            enter_row(q);
+            row_prepare(q);
+            __syncwarp();
+            row_gather(q);
+            __syncwarp();
 #pragma unroll
             for (int d = 0; d <= q; ++d) W[q][q - d] = reinterpret_cast<const double2 *>(stage)[d * 32 + lane];
-            Rh[q] = reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64)[lane];
+            if (rowtab[q].y >> 30) Rh[q] = __ldg(reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64) + lane);
             __syncwarp();
         }
 
+        WTL(0);
         // ---------------- panels
         double gacc = 0.0;  // partial sum over this lane's columns of G[g] = q_g^T K^-1 f
         const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
-#pragma unroll 1
-        for (int p = 0; p < NQ; ++p) {
-            // ---- diagonal block: LDL^T, inverse of the unit factor
+        {   // diagonal block of panel 0: LDL^T, inverse of the unit factor
             reinterpret_cast<double2 *>(dg)[lane] = W[0][0];
             __syncwarp();
-            warp_diag_factor(dg, stg, rd, minv, flagp, lane);
+            double a[36];
+            warp_diag_load(dg, a);
+            warp_diag_compute(a, stg, rd, minv, flagp, lane);
             __syncwarp();
+        }
+#pragma unroll 1
+        for (int p = 0; p < NQ; ++p) {
+            WTL(1);
             const double2 mi = reinterpret_cast<const double2 *>(minv)[lane];  // Minv[g][2t..2t+1]
             const double2 r2 = reinterpret_cast<const double2 *>(rd)[t];
             // ---- solve: V = X L11^-T for the right-hand sides (b = 0) and the blocks below; Ln = -V D^-1
@@ -261,45 +311,61 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 // the scaled panel leaves for the slab: [0] Minv^T, [1..NB] L^T blocks, [NB+1] D^-1 z rows, transposed
                 // on the tensor core (I * L^T leaves the transposed block in the C-fragment layout)
                 double2 *pan = reinterpret_cast<double2 *>(lws + (size_t)p * LPB);
-                pan[lane] = reinterpret_cast<const double2 *>(stg)[lane];
+                __stcs(pan + lane, reinterpret_cast<const double2 *>(stg)[lane]);
 #pragma unroll
                 for (int b = 0; b < NB1; ++b) {
                     double2 lt = z2;
                     block_mma<true>(lt, idf, Ln[b], lane);
-                    pan[(b ? b : NB + 1) * 32 + lane] = make_double2(-lt.x, -lt.y);
+                    __stcs(pan + (b ? b : NB + 1) * 32 + lane, make_double2(-lt.x, -lt.y));
                 }
             }
+            WTL(3);
             // ---- trailing update, written one block up and one block left: the window slides with the panel
 #pragma unroll
             for (int I = 1; I <= NB; ++I)
 #pragma unroll
                 for (int J = 1; J <= I; ++J) {
-                    double2 c = W[I][J], e = z2;
+                    double2 c = W[I][J];
                     dmma884(c.x, c.y, Ln[I].x, V[J].x);
-                    dmma884(e.x, e.y, Ln[I].y, V[J].y);
-                    W[I - 1][J - 1] = make_double2(c.x + e.x, c.y + e.y);
+                    dmma884(c.x, c.y, Ln[I].y, V[J].y);
+                    W[I - 1][J - 1] = c;
                 }
 #pragma unroll
             for (int J = 1; J <= NB; ++J) {
-                double2 c = Rh[J], e = z2;
+                double2 c = Rh[J];
                 dmma884(c.x, c.y, Ln[0].x, V[J].x);
-                dmma884(e.x, e.y, Ln[0].y, V[J].y);
-                Rh[J - 1] = make_double2(c.x + e.x, c.y + e.y);
+                dmma884(c.x, c.y, Ln[0].y, V[J].y);
+                Rh[J - 1] = c;
             }
-            // ---- block row p+NB+1 enters at the bottom of the window
+            WTL(4);
+            // ---- the diagonal block of panel p+1 is factored WHILE block row p+NB+1 is gathered into the staging area:
+            //      one instruction stream, two independent dependency chains
             const int q = p + NB1;
+            if (p + 1 < NQ) {
+                reinterpret_cast<double2 *>(dg)[lane] = W[0][0];
+                if (q < NQ) row_prepare(q);
+                __syncwarp();
+                double a[36];
+                warp_diag_load(dg, a);
+                if (q < NQ) row_gather(q);
+                warp_diag_compute(a, stg, rd, minv, flagp, lane);
+                __syncwarp();
+            }
+            WTL(2);
             if (q < NQ) {
-                enter_row(q);
 #pragma unroll
                 for (int d = 0; d <= NB; ++d) W[NB][NB - d] = reinterpret_cast<const double2 *>(stage)[d * 32 + lane];
-                Rh[NB] = reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64)[lane];
+                Rh[NB] = z2;
+                if (rowtab[q].y >> 30) Rh[NB] = __ldg(reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64) + lane);
             } else {
 #pragma unroll
                 for (int d = 0; d <= NB; ++d) W[NB][d] = z2;
                 Rh[NB] = z2;
             }
+            WTL(8);
         }
 
+        WTL(1);
         // ---------------- observations: y from the last diagonal block, strains from the accumulated products,
         //                  h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
         __syncwarp();
@@ -378,6 +444,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 }
             }
             __syncwarp();
+            WTL(5);
             // ---------------- reverse pass: x_p = (W Lrhs_p - sum_b x_(p+b) L_(p+b,p)) Minv_p, panels descending,
             //                  fragments straight from the slab (each lane reads back what it stored)
             const double2 Wf = reinterpret_cast<const double2 *>(sW)[lane];
@@ -387,20 +454,34 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
             double2 X[NB1];  // X[b] = -x_(p+b), b = 1..NB
 #pragma unroll
             for (int b = 0; b < NB1; ++b) X[b] = z2;
-            double2 cur[NB + 2], nxt[NB + 2];
+            // u and the adjoint vectors: in the element ring (idle after the forward pass) when they fit, else global
+            double *xv = (MODE == 1 && Q.x_in_smem) ? ke : xws;
+            double2 cur[NB + 2], nxt[NB + 2], nx2[NB + 2];  // panels p, p-1, p-2: loads two panels ahead of their use
+            constexpr int kAhead = 4;  // panels on their way into L2 ahead of the register buffers
+            if (lane < (NB + 2) * 4)
+                for (int i = 2; i <= 1 + kAhead && NQ - 1 - i >= 0; ++i)
+                    prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(NQ - 1 - i) * LPB) + 128 * lane);
             {
                 const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 1) * LPB);
 #pragma unroll
-                for (int b = 0; b < NB + 2; ++b) nxt[b] = pan[b * 32 + lane];
+                for (int b = 0; b < NB + 2; ++b) nxt[b] = __ldcs(pan + b * 32 + lane);
+                const double2 *pa2 = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 2) * LPB);
+#pragma unroll
+                for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pa2 + b * 32 + lane);
             }
 #pragma unroll 1
             for (int p = NQ - 1; p >= 0; --p) {
 #pragma unroll
-                for (int b = 0; b < NB + 2; ++b) cur[b] = nxt[b];
-                if (p > 0) {
-                    const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 1) * LPB);
+                for (int b = 0; b < NB + 2; ++b) {
+                    cur[b] = nxt[b];
+                    nxt[b] = nx2[b];
+                }
+                if (p > 1) {
+                    const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 2) * LPB);
 #pragma unroll
-                    for (int b = 0; b < NB + 2; ++b) nxt[b] = pan[b * 32 + lane];
+                    for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pan + b * 32 + lane);
+                    if (p - 2 - kAhead >= 0 && lane < (NB + 2) * 4)
+                        prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(p - 2 - kAhead) * LPB) + 128 * lane);
                 }
                 double2 d = z2;
                 block_mma<true>(d, Wf, cur[NB + 1], lane);
@@ -417,33 +498,38 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 }
                 double2 x = z2;
                 block_mma<true>(x, d, cur[0], lane);
-                if (g < NV) *reinterpret_cast<double2 *>(xws + (size_t)g * Q.npad + 8 * p + 2 * t) = x;
+                if (g < NV) *reinterpret_cast<double2 *>(xv + (size_t)g * Q.npad + 8 * p + 2 * t) = x;
 #pragma unroll
                 for (int b = NB; b > 1; --b) X[b] = X[b - 1];
                 X[1] = make_double2(-x.x, -x.y);
             }
             __syncwarp();
 
+            WTL(6);
             // ---------------- element-wise contraction -psi^T (dK/dp) u + explicit dh/dp, chained to x
             constexpr int NADJ = NV - 1;
             double sl[NADJ], sm[NADJ];
 #pragma unroll
             for (int v = 0; v < NADJ; ++v) sl[v] = sm[v] = 0.0;
-            for (int e = lane; e < M.nele; e += 32) {
+            for (int e = lane; e < Q.nele; e += 32) {  // first-use order: coordinates and band rows are contiguous records
                 double xl[4], yl[4], ue[8];
                 int lm[8];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    const int nd = M.ien[4 * e + a];
-                    const double2 xy = *reinterpret_cast<const double2 *>(M.coord + 2 * nd);
+                    const double2 xy = __ldg(reinterpret_cast<const double2 *>(Q.ecoord + (size_t)8 * e) + a);
                     xl[a] = xy.x;
                     yl[a] = xy.y;
                 }
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    lm[a] = Q.elm[8 * e + a];
-                    ue[a] = (lm[a] >= 0) ? xws[lm[a]] : 0.0;
+                for (int a = 0; a < 2; ++a) {
+                    const int4 r4 = __ldg(reinterpret_cast<const int4 *>(Q.elm + (size_t)8 * e) + a);
+                    lm[4 * a] = r4.x;
+                    lm[4 * a + 1] = r4.y;
+                    lm[4 * a + 2] = r4.z;
+                    lm[4 * a + 3] = r4.w;
                 }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) ue[a] = (lm[a] >= 0) ? xv[lm[a]] : 0.0;
 #pragma unroll 1
                 for (int gp = 0; gp < 4; ++gp) {
                     ShapeQ4 sh;
@@ -452,7 +538,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                     strain_q4(sh, ue, uxx, uyy, uxy);
 #pragma unroll
                     for (int v = 0; v < NADJ; ++v) {
-                        const double *pv = xws + (size_t)(v + 1) * Q.npad;
+                        const double *pv = xv + (size_t)(v + 1) * Q.npad;
                         double pe[8], pxx, pyy, pxy, cl, cm;
 #pragma unroll
                         for (int a = 0; a < 8; ++a) pe[a] = (lm[a] >= 0) ? pv[lm[a]] : 0.0;
@@ -500,6 +586,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
         __syncwarp();
         if (lane == 0 && A.status) A.status[s] = *flagp;
         __syncwarp();
+        WTL(7);
+        WTL_FLUSH;
     }
 }
 
