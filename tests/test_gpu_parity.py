@@ -34,7 +34,7 @@ def test_native_library_is_loaded(engine, pkg):
     maps = open("/proc/self/maps").read()
     assert "libvbfem.so" in maps
     assert engine.info["nfree"] == 440 and engine.info["half_bw"] == 25  # short-side numbering
-    assert engine.info["band_in_smem"] == 1
+    assert engine.info["kernel_variant"] == 4 and engine.info["block_threads"] == 384   # warp-per-sample kernel, 12 warps
     # the host-only plan (vbfem_plan, unit-tested without a GPU) is what vbfem_create built
     plan = pkg.fem_solver.plan_layout(golden_model_of(engine))
     for k in ("kernel_variant", "nfree", "half_bw", "twist_row", "smem_bytes"):
@@ -111,6 +111,23 @@ def test_forward_adjoint_vs_oracle_full_batch(engine, torch_oracle):
     gx2 = engine.backward(_t(gy, engine), _t(gh, engine))
     assert relerr(y2.cpu().numpy(), y) < 1e-13
     assert relerr(gx2.cpu().numpy(), g) < 1e-11
+
+
+def test_front_kernel_full_batch_vs_warp_kernel(pkg, engine, golden_model, monkeypatch):
+    """The on-chip two-front kernel (VBFEM_WARP=0) and the warp-per-sample kernel are independent
+    implementations of the same solve: all 4096 benchmark samples agree to 1e-11."""
+    import bench
+    monkeypatch.setenv("VBFEM_WARP", "0")
+    front = pkg.CookFemEngine(golden_model, device=0)
+    assert front.info["kernel_variant"] == 2 and engine.info["kernel_variant"] == 4
+    x, gy, gh = (_t(a, engine) for a in bench.inputs(0))
+    a = engine.forward_backward(x, gy, gh)
+    b = front.forward_backward(x, gy, gh)
+    for u, v in zip(a, b):
+        assert relerr(u.cpu().numpy(), v.cpu().numpy()) < 1e-11
+    ja, jb = engine.forward_jac(x)[2], front.forward_jac(x)[2]
+    assert relerr(ja.cpu().numpy(), jb.cpu().numpy()) < 1e-11
+    front.close()
 
 
 def test_jacobian_vs_reference_finite_differences(engine, golden):
@@ -412,18 +429,22 @@ def test_refined_mesh_80x40(pkg):
     eng.close()
 
 
-@pytest.mark.parametrize("node_id,ele_id,nipt_id,variant", [
-    (231, 12, (1, 3), 2),     # the reference's set-up: node behind the element in band order
-    (21, 12, (2, 4), 2),      # tip of the bottom edge, other Gauss points
-    (23, 150, (1, 2), 2),     # node AHEAD of the element: the band order is flipped internally
-    (1, 50, (3, 4), 2),       # supported node: y == 0, gradient through h only
-    (116, 110, (1, 3), 0),    # node of the observed element itself: generic kernel
-    (1, 60, (3, 4), 3),       # element too close to the end of the band for two fronts: blocked panel kernel
+@pytest.mark.parametrize("node_id,ele_id,nipt_id,variant,warp", [
+    (231, 12, (1, 3), 4, "1"),    # the reference's set-up: observed node at the end of the band order -> warp kernel
+    (231, 12, (1, 3), 2, "0"),    # the same on the on-chip two-front kernel: node behind the element in band order
+    (21, 12, (2, 4), 2, "1"),     # tip of the bottom edge (middle of the band order), other Gauss points: front kernel
+    (23, 150, (1, 2), 2, "1"),    # node AHEAD of the element: the band order is flipped internally
+    (1, 50, (3, 4), 4, "1"),      # supported node: y == 0, gradient through h only
+    (1, 50, (3, 4), 2, "0"),
+    (116, 110, (1, 3), 0, "1"),   # node of the observed element itself: generic kernel
+    (1, 60, (3, 4), 4, "1"),
+    (1, 60, (3, 4), 3, "0"),      # element too close to the end of the band for two fronts: blocked panel kernel
 ])
-def test_other_observation_setups(pkg, golden_model, oracle_mesh, node_id, ele_id, nipt_id, variant):
-    """The front kernel's layout (orientation, middle block, unit vectors) is derived from the
+def test_other_observation_setups(pkg, golden_model, oracle_mesh, node_id, ele_id, nipt_id, variant, warp, monkeypatch):
+    """Every kernel's layout (orientation, middle block, unit vectors, right-hand-side rows) is derived from the
     observation set-up; every choice must agree with the oracle."""
     import fem_oracle as fo
+    monkeypatch.setenv("VBFEM_WARP", warp)
     eng = pkg.CookFemEngine(golden_model, device=0, node_id=node_id, ele_id=ele_id, nipt_id=nipt_id)
     assert eng.info["kernel_variant"] == variant
     to = fo.TorchOracle(*oracle_mesh, node_id=node_id, ele_id=ele_id, nipt_id=nipt_id)
@@ -508,18 +529,23 @@ def test_elbo_step2_fused_vs_oracle(pkg, engine, torch_oracle):
     assert relerr(res[0][1], res[1][1]) < TOL and relerr(res[0][2], res[1][2]) < TOL
 
 
-@pytest.mark.parametrize("nx,ny,variant", [
-    (24, 8, 2),    # n = 432, narrower band (b = 21 < 25): front kernel with a zero-padded band
-    (20, 9, 2),    # n = 400, b = 23: other front lengths
-    (16, 8, 3),    # n = 288: too small for the front kernel's shared-memory layout -> blocked panel kernel
-    (30, 10, 3),   # n = 660: the band no longer fits twice per SM -> blocked panel kernel
-    (40, 20, 3),   # n = 1680, b = 45: panel kernel with a 6-block window
+@pytest.mark.parametrize("nx,ny,variant,warp", [
+    (24, 8, 4, "1"),    # n = 432, narrower band (b = 21 < 25): warp kernel, window padded to three blocks
+    (24, 8, 2, "0"),    #          front kernel with a zero-padded band
+    (20, 9, 4, "1"),    # n = 400, b = 23
+    (20, 9, 2, "0"),    #          other front lengths
+    (16, 8, 4, "1"),    # n = 288
+    (16, 8, 3, "0"),    #          too small for the front kernel's shared-memory layout -> blocked panel kernel
+    (30, 10, 4, "1"),   # n = 660: the larger gather table leaves room for eight warps
+    (30, 10, 3, "0"),   #          the band no longer fits twice per SM -> blocked panel kernel
+    (40, 20, 3, "1"),   # n = 1680, b = 45: panel kernel with a 6-block window
 ])
-def test_other_mesh_sizes(pkg, nx, ny, variant):
+def test_other_mesh_sizes(pkg, nx, ny, variant, warp, monkeypatch):
     """Cook membranes of other sizes through the same entry points (mesh text -> preprocessor ->
     engine), against the oracle built from the same text: forward, fused adjoint, Jacobian mode."""
     import torch
     import fem_oracle as fo
+    monkeypatch.setenv("VBFEM_WARP", warp)
     md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(nx, ny))
     node_id, ele_id = (nx + 1) * (ny + 1), nx // 2 + 2
     eng = pkg.CookFemEngine(md, device=0, node_id=node_id, ele_id=ele_id)

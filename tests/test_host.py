@@ -247,10 +247,21 @@ def test_step2_loss_sharded_over_gloo_ranks(tmp_path):
         assert "ERR" in o
 
 
-def test_plan_layout_on_host(pkg, golden_model):
-    """vbfem_plan: the numbering / orientation / front split vbfem_create would choose, computed
-    without a GPU.  Cook 20x10 with the reference's observation set-up: short-side numbering
-    (b = 25 instead of 43), middle block on the observed element, observed node in the bottom front."""
+def test_plan_layout_on_host(pkg, golden_model, monkeypatch):
+    """vbfem_plan: the kernel choice / numbering / orientation / front split vbfem_create would make, computed
+    without a GPU.  Cook 20x10 with the reference's observation set-up: short-side numbering (b = 25 instead of
+    43); the warp-per-sample kernel by default, the on-chip two-front kernel when it is disabled or cannot take
+    the observation set-up (middle block on the observed element, observed node in the bottom front)."""
+    plan = pkg.fem_solver.plan_layout(golden_model)
+    assert plan["kernel_variant"] == 4 and plan["nfree"] == 440 and plan["half_bw"] == 25
+    assert plan["smem_bytes"] == 12 * 16400 + 3816 * 8 + 56 * 8   # twelve warps + the packed gather table + row table
+    # a supported observed node has no unit vectors: warp kernel; a node in the middle of the band order: front kernel
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=50)["kernel_variant"] == 4
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 4
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=21, ele_id=12)["kernel_variant"] == 2
+    # less shared memory: eight warps instead of twelve
+    assert pkg.fem_solver.plan_layout(golden_model, smem_per_sm=200000)["smem_bytes"] == 8 * 16400 + 3816 * 8 + 56 * 8
+    monkeypatch.setenv("VBFEM_WARP", "0")
     plan = pkg.fem_solver.plan_layout(golden_model)
     assert plan == {"kernel_variant": 2, "nfree": 440, "half_bw": 25, "twist_row": 220, "bottom_cols": 194,
                     "flipped": 0, "smem_bytes": 109888}
@@ -258,22 +269,25 @@ def test_plan_layout_on_host(pkg, golden_model):
     p2 = pkg.fem_solver.plan_layout(golden_model, node_id=23, ele_id=150)
     assert p2["kernel_variant"] == 2 and p2["flipped"] == 1
     assert p2["twist_row"] + 26 + p2["bottom_cols"] == 440 and p2["twist_row"] >= 32 and p2["bottom_cols"] >= 32
-    # observed node inside the observed element's rows / element too close to the end of the band
+    # observed node inside the observed element's rows: generic kernel; element too close to the end of the band
+    # for two fronts: blocked panel kernel
     assert pkg.fem_solver.plan_layout(golden_model, node_id=116, ele_id=110)["kernel_variant"] == 0
-    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 3  # panel kernel
+    assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 3
     # supported observed node: no unit vectors, still the front kernel
     assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=50)["kernel_variant"] == 2
     # a smaller shared memory does not fit two samples per SM
     assert pkg.fem_solver.plan_layout(golden_model, smem_per_sm=200000)["kernel_variant"] == 3
 
 
-@pytest.mark.parametrize("nx,ny,variant,b", [(24, 8, 2, 21), (20, 9, 2, 23), (16, 8, 3, 21), (30, 10, 3, 25),
-                                             (80, 40, 3, 85), (40, 20, 3, 45)])
-def test_plan_layout_other_meshes(pkg, nx, ny, variant, b):
+@pytest.mark.parametrize("nx,ny,variant,b,variant_no_warp", [(24, 8, 4, 21, 2), (20, 9, 4, 23, 2), (16, 8, 4, 21, 3),
+                                                            (30, 10, 4, 25, 3), (80, 40, 3, 85, 3), (40, 20, 3, 45, 3)])
+def test_plan_layout_other_meshes(pkg, nx, ny, variant, b, variant_no_warp, monkeypatch):
     md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(nx, ny))
     plan = pkg.fem_solver.plan_layout(md, node_id=(nx + 1) * (ny + 1), ele_id=nx // 2 + 2)
     assert plan["kernel_variant"] == variant and plan["half_bw"] == b
     assert plan["nfree"] == 2 * nx * (ny + 1)
+    monkeypatch.setenv("VBFEM_WARP", "0")
+    assert pkg.fem_solver.plan_layout(md, node_id=(nx + 1) * (ny + 1), ele_id=nx // 2 + 2)["kernel_variant"] == variant_no_warp
 
 
 def test_h5io_roundtrip_and_layout(pkg, tmp_path):

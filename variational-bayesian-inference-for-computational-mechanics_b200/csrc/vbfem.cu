@@ -1452,17 +1452,13 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
 }
 
 // Warp-per-sample kernel (vbfem_warp.cuh): chosen for narrow bands when enabled (VBFEM_WARP=0/1 overrides the default).
-constexpr bool kWarpDefault = false;
+constexpr bool kWarpDefault = true;
 static bool want_warp_kernel() {
     if (getenv("VBFEM_FORCE_GENERIC") != nullptr || getenv("VBFEM_FORCE_PANEL") != nullptr) return false;
     if (const char *e = getenv("VBFEM_WARP")) return atoi(e) != 0;
     return kWarpDefault;
 }
-static int warp_kernel_warps() {
-    int NW = 12;
-    if (const char *e = getenv("VBFEM_WARP_NW")) NW = atoi(e);
-    return NW;
-}
+
 static int warp_kernel_batch() {
     int b = 30;  // 30 instead of 32 elements per batch: ring of 44 instead of 46 matrices on Cook 20x10 -> 14 warps fit
     if (const char *e = getenv("VBFEM_WARP_BATCH")) b = atoi(e);
@@ -1470,6 +1466,12 @@ static int warp_kernel_batch() {
 }
 static int warp_kernel_smem(const PanelPlan &P) { return (kWarpFixed + (P.R * 36 + 2) * 8 + 15) & ~15; }
 static int warp_kernel_tab_bytes(const PanelPlan &P) { return (int)((P.gdst.size() * 8 + (size_t)(P.NQ + 1) * 8 + 15) & ~(size_t)15); }
+static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block);
+// Warps (= samples in flight) per CTA: twelve when the per-warp areas and the shared tables fit, else eight.
+static int warp_kernel_warps(const PanelPlan &P, size_t smem_per_block) {
+    if (const char *e = getenv("VBFEM_WARP_NW")) return atoi(e);
+    return warp_kernel_ok(P, 12, smem_per_block) ? 12 : 8;
+}
 static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
     // 11-bit ring indices and 8-bit targets in the packed gather table
     return P.ok && P.NB == kWarpNB && P.NQ > kWarpNB && P.R * 36 + 2 <= 2048 && (NW == 8 || NW == 12 || NW == 16) &&
@@ -1688,7 +1690,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     // ---- warp-per-sample kernel: narrow bands (block half bandwidth <= 3), window in registers, 12 samples per SM
     if (!force_panel && want_warp_kernel()) {
         PanelPlan P = plan_panel(m, dof2band, n, kWarpNB, warp_kernel_batch());
-        const int NW = warp_kernel_warps();
+        const int NW = warp_kernel_warps(P, (size_t)prop.sharedMemPerBlockOptin);
         const int warp_smem = warp_kernel_smem(P);
         if (warp_kernel_ok(P, NW, (size_t)prop.sharedMemPerBlockOptin)) {
             WarpModel &Q = h->WM;
@@ -1975,10 +1977,11 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
         const PanelPlan Q = plan_panel(m, dof2band, n, kWarpNB, warp_kernel_batch());
         // 232448: shared memory a block may opt in to on B200 (sharedMemPerBlockOptin)
         const size_t per_block = (size_t)std::min<int64_t>(smem_per_sm > 0 ? smem_per_sm : 233472, 232448);
-        if (warp_kernel_ok(Q, warp_kernel_warps(), per_block)) {
+        const int NW = warp_kernel_warps(Q, per_block);
+        if (warp_kernel_ok(Q, NW, per_block)) {
             out[0] = 4;
             out[3] = out[4] = out[5] = 0;
-            out[6] = (int64_t)warp_kernel_warps() * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
+            out[6] = (int64_t)NW * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
             return 0;
         }
     }
