@@ -78,6 +78,18 @@ enum {
  * in fem_preprocess.py:291-443 + fem_solver_tf.py:378-396 (host side). */
 int vbfem_create(vbfem_t **out, const vbfem_mesh *mesh, int device);
 
+/* Options beyond the reference's default cards.  stype = section['stype'] (model_property_cards.py:28): 2 = plane
+ * strain (what the TF path executes unconditionally, src/mat_subroutine_tf.py:54-56), 1 = plane stress (the NumPy
+ * twin's other branch, src/mat_subroutine.py:283-290: Ce = E/(1-v^2) [[1,v,0],[v,1,0],[0,0,(1-v)/2]], sigma_zz = 0,
+ * eps_33 = -v/(1-v)(eps_xx+eps_yy)).  Plane stress runs on the generic kernel (all modes incl. the adjoint).
+ * Body forces (part['body'], src/mat_subroutine_tf.py:157-158) need no option: they are sample-independent and
+ * enter through the load vector `pf` (see fem_solver.body_force_vector). */
+typedef struct vbfem_options {
+    int32_t stype;
+    int32_t reserved[7];
+} vbfem_options;
+int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *mesh, const vbfem_options *opt /* NULL: defaults */, int device);
+
 /* The host-side plan vbfem_create would make for this mesh and observation set-up, WITHOUT touching
  * a GPU (unit tests of the numbering / orientation / front split): out[0] = kernel variant (2 = on-chip
  * two-front kernel, 3 = blocked panel kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
@@ -142,6 +154,12 @@ int vbfem_forward_backward(vbfem_t *h, int64_t n_samples, const double *x_dev,
  * sample [N][2] and x_dev is ignored (fem_test.py uses the card values). */
 int vbfem_fields(vbfem_t *h, int64_t n_samples, const double *x_dev, const double *emat_dev,
                  double *u_dev, double *sig_dev, double *eps_dev, double *fint_dev, void *stream);
+
+/* Heterogeneous material: full fields (and the observations y, h) with ONE (E, nu) PER ELEMENT and sample,
+ * emat_dev [N][nele][2] -- the generality the reference's cards only hint at (material per part,
+ * src/mat_subroutine.py:24-25).  Forward only.  Any output pointer may be NULL. */
+int vbfem_fields_elementwise(vbfem_t *h, int64_t n_samples, const double *emat_dev, double *y_dev, double *h_dev,
+                             double *u_dev, double *sig_dev, double *eps_dev, double *fint_dev, void *stream);
 
 /* Step-1 ELBO pieces (main_custom_training.py:183-235) for the flat sample
  * range [j_begin, j_end) of the B*S reparameterised samples

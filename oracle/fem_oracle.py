@@ -186,31 +186,40 @@ def shapef(s, xl):
     return shp, xsj
 
 
-def isotropic_elasticity(eps, E, v):
-    """mat_subroutine_tf.py:333-390 (plane-strain branch that the TF file
-    executes unconditionally): lambda/mu, 4x4 Ce, sig[0:4] = Ce @ eps[0:4],
-    Ct[{0,1,3}^2] = Ce[{0,1,3}^2]."""
-    l = v * E / ((1 + v) * (1 - 2 * v))
-    mu = 0.5 * E / (1 + v)
-    Ce = np.array([[l + 2 * mu, l, l, 0], [l, l + 2 * mu, l, 0], [l, l, l + 2 * mu, 0], [0, 0, 0, mu]])
+def isotropic_elasticity(eps, E, v, stype=2):
+    """mat_subroutine_tf.py:333-390 (the plane-strain branch, which the TF file executes unconditionally):
+    lambda/mu, 4x4 Ce, sig[0:4] = Ce @ eps[0:4], Ct[{0,1,3}^2] = Ce[{0,1,3}^2]; with stype = 1 the NumPy
+    twin's plane-stress branch (mat_subroutine.py:283-290).  Returns sig, Ct, eps33."""
     sig = np.zeros(6)
-    sig[0:4] = Ce @ eps[0:4]
     Ct = np.zeros((6, 6))
     idx = [0, 1, 3]
-    Ct[np.ix_(idx, idx)] = Ce[np.ix_(idx, idx)]
-    return sig, Ct
+    eps33 = None
+    if stype == 1:
+        Ce = E / (1 - v ** 2) * np.array([[1, v, 0], [v, 1, 0], [0, 0, (1 - v) / 2]])
+        sig[idx] = Ce @ eps[idx]
+        eps33 = -v / (1 - v) * (eps[0] + eps[1])
+        Ct[np.ix_(idx, idx)] = Ce
+    else:
+        l = v * E / ((1 + v) * (1 - 2 * v))
+        mu = 0.5 * E / (1 + v)
+        Ce = np.array([[l + 2 * mu, l, l, 0], [l, l + 2 * mu, l, 0], [l, l, l + 2 * mu, 0], [0, 0, 0, mu]])
+        sig[0:4] = Ce @ eps[0:4]
+        Ct[np.ix_(idx, idx)] = Ce[np.ix_(idx, idx)]
+    return sig, Ct, eps33
 
 
-def solid_2d(ul, xl, E, v, thk):
+def solid_2d(ul, xl, E, v, thk, stype=2, body=(0.0, 0.0)):
     """mat_subroutine_tf.py:23-110: 2x2 Gauss loop, strain (112-145), plane
     strain eps[2]=0 (54-56), material, Ct -> [0,1,3]^2 (75-76), dvol=thk*jac,
-    p += dvol*Bm^T sig[0,1,3] (147-159, zero body force), kt += dvol*Bm^T Ct Bm,
-    Bm rows (dNx | dNy | dNy,dNx) (161-227)."""
+    p += dvol*Bm^T sig[0,1,3] - dvol*Nm^T body (147-159), kt += dvol*Bm^T Ct Bm,
+    Bm rows (dNx | dNy | dNy,dNx), Nm rows (N at x dofs | N at y dofs) (161-227).  stype = 1: plane stress,
+    eps[2] = eps33 after the material call (mat_subroutine.py:51-52)."""
     sg = gauss_2x2()
     p = np.zeros(8)
     kt = np.zeros((8, 8))
     eps_out = np.zeros((6, 4))
     sig_out = np.zeros((6, 4))
+    body = np.asarray(body, dtype=np.float64)
     for ipt in range(4):
         shp, xsj = shapef(sg[0:2, ipt], xl)
         jac = xsj * sg[2, ipt]
@@ -219,16 +228,21 @@ def solid_2d(ul, xl, E, v, thk):
         eps[1] = shp[1] @ ul[1]
         eps[3] = shp[0] @ ul[1] + shp[1] @ ul[0]
         eps[2] = 0.0
-        sig, Ct = isotropic_elasticity(eps, E, v)
+        sig, Ct, eps33 = isotropic_elasticity(eps, E, v, stype)
+        if stype == 1:
+            eps[2] = eps33
         Ct3 = Ct[np.ix_([0, 1, 3], [0, 1, 3])]
         dvol = thk * jac
         Bm = np.zeros((3, 8))
+        Nm = np.zeros((2, 8))
         for i in range(4):
             Bm[0, 2 * i] = shp[0, i]
             Bm[1, 2 * i + 1] = shp[1, i]
             Bm[2, 2 * i] = shp[1, i]
             Bm[2, 2 * i + 1] = shp[0, i]
-        p += dvol * (Bm.T @ sig[[0, 1, 3]])
+            Nm[0, 2 * i] = shp[2, i]
+            Nm[1, 2 * i + 1] = shp[2, i]
+        p += dvol * (Bm.T @ sig[[0, 1, 3]]) - dvol * (Nm.T @ body)
         kt += dvol * (Bm.T @ Ct3 @ Bm)
         eps_out[:, ipt] = eps
         sig_out[:, ipt] = sig
@@ -239,8 +253,9 @@ def solid_2d(ul, xl, E, v, thk):
 class LoopOracle:
     """Statement-by-statement restatement of fem_solver_tf.py:86-185,229-341."""
 
-    def __init__(self, mesh, dof, thk=10.0):
+    def __init__(self, mesh, dof, thk=10.0, stype=2, body=(0.0, 0.0)):
         self.mesh, self.dof, self.thk = mesh, dof, thk
+        self.stype, self.body = stype, body
         self.xy = mesh["coord"][:, 1:3]
 
     def assemble(self, u, E, v):
@@ -256,7 +271,8 @@ class LoopOracle:
             lm = d["LM"][:, e] - 1
             ul = u[lm].reshape(4, 2).T
             xl = self.xy[d["IEN"][e] - 1].T
-            p, kt, eps, sig = solid_2d(ul, xl, E, v, self.thk)
+            Ee, ve = (E[e], v[e]) if np.ndim(E) else (E, v)   # one material, or one per element
+            p, kt, eps, sig = solid_2d(ul, xl, Ee, ve, self.thk, self.stype, self.body)
             Fint[lm] += p
             Kg[np.ix_(lm, lm)] += kt
             strain[:, :, e], stress[:, :, e] = eps, sig

@@ -8,7 +8,7 @@ that are absent here (tensorflow, hdf5storage, h5py, matplotlib) and records
 
   * the pre-processor state (coord, IEN, LM, ID, free/supp dof, Pf) that pins
     the mesh/DOF interface (fem_preprocess.py:114-443),
-  * config 1 (fem_test.py: E=20, nu=0.3): full u, sigma, eps, von Mises,
+  * config 1 (fem_test.py: E=20, nu=0.3): full u, sigma, eps, von Mises; the same with a body force in the part card (bf_*),
   * theta-parameterised solves through MeasurementData.fem_f_fun / fem_h_fun
     (data_generation_2sam_more_loss.py:98-125) for a list of seeded x,
   * finite-difference Jacobians d(y, h)/dx of those same reference functions (gradient pins).
@@ -68,11 +68,28 @@ def main():
     od, sd = fp.PreProcessing.out_data, fp.PreProcessing.sol_data
     out["c1_u"] = np.asarray(sd["u_n1"].toarray(), dtype=np.float64).ravel()
     out["c1_Fint"] = np.asarray(sd["F_int"].toarray(), dtype=np.float64).ravel()
-    out["c1_stress"] = np.asarray(od["ele_stress"][:, :, :, 1], dtype=np.float64)
-    out["c1_strain"] = np.asarray(od["ele_strain"][:, :, :, 1], dtype=np.float64)
+    out["c1_stress"] = np.asarray(od["ele_stress"][:, :, :, 1], dtype=np.float64).copy()
+    out["c1_strain"] = np.asarray(od["ele_strain"][:, :, :, 1], dtype=np.float64).copy()
     out["c1_nodal_disp"] = np.asarray(od["step"][1]["nodal_disp"], dtype=np.float64)
     out["c1_vm"] = np.asarray(fpp.PostProcessing.von_mises_stress(2, 12, np.array([1, 3])), dtype=np.float64)
     out["c1_tol"] = np.asarray(od["step"][1]["tol_vec"], dtype=np.float64)
+
+    # ---- the cards' other branches, still on the unmodified reference: plane stress (section stype = 1,
+    #      src/mat_subroutine.py:283-290) and a constant body force (part body, src/mat_subroutine.py:113-116)
+    def solve_variant(tag):
+        fp.PreProcessing.out_data["step"] = fp.PreProcessing.out_data["step"][:1]
+        fs.FemSolver.fea_solution(input_data=None)
+        out[tag + "_u"] = np.asarray(sd["u_n1"].toarray(), dtype=np.float64).ravel()
+        out[tag + "_Fint"] = np.asarray(sd["F_int"].toarray(), dtype=np.float64).ravel()
+        out[tag + "_stress"] = np.asarray(od["ele_stress"][:, :, :, 1], dtype=np.float64).copy()
+        out[tag + "_strain"] = np.asarray(od["ele_strain"][:, :, :, 1], dtype=np.float64).copy()
+        out[tag + "_vm"] = np.asarray(fpp.PostProcessing.von_mises_stress(2, 12, np.array([1, 3])), dtype=np.float64)
+
+    # (the plane-stress branch itself cannot be run unmodified under numpy >= 2: src/mat_subroutine.py:52 assigns the
+    #  size-1 array eps33 to a scalar slot and raises; it is pinned through the oracle's restatement only)
+    md["part"][0]["body"] = np.array([[0.01], [-0.02], [0.0]])
+    solve_variant("bf")
+    md["part"][0]["body"] = np.array([[0], [0], [0]])
 
     # ---- theta-parameterised solves (main_custom_training.py:32-38) -----------
     M = dg.MeasurementData

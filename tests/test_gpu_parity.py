@@ -635,3 +635,68 @@ def test_small_batch_host_path_and_mcmc_log_posterior(pkg, engine, golden, torch
     eta = np.sqrt(3e-3) * rng.standard_normal((50, 2))
     z = torch_oracle.fem_fh(torch.tensor(theta))[1].numpy() + eta
     assert relerr(zm, np.tile(z.mean(0), (3, 1))) < TOL and relerr(zv, np.tile(z.var(0), (3, 1))) < 1e-8
+
+
+def test_generality_plane_stress_body_force_elementwise(pkg, golden, golden_model, oracle_mesh):
+    """SURVEY 8(f) row 4 -- the card options the reference stubs out, on the generic kernel: plane stress
+    (section stype 1), a body force (part body; pinned to the reference twin's own run), one (E, nu) per
+    element, and the Newton-Raphson solver option."""
+    import copy
+    import torch
+    import fem_oracle as fo
+    # ---- body force through FemSolver.fea_solution with the part card set, against the reference golden
+    P = pkg.PreProcessing
+    P.modeldata_initialization_topopt(pkg.cook_membrane_feap(20, 10))
+    P.model_data["part"][0]["body"] = np.array([[0.01], [-0.02], [0.0]])
+    P.model_data["solution_control"]["solver"] = 2      # Newton-Raphson option: converges in the first iteration
+    pkg.FemSolver.fea_solution(input_data=None)
+    assert relerr(P.sol_data["u_n1"].ravel(), golden["bf_u"]) < TOL
+    assert relerr(P.out_data["ele_stress"][:, :, :, 1], golden["bf_stress"]) < TOL
+    assert relerr(P.sol_data["F_int"].ravel(), golden["bf_Fint"]) < 1e-8
+    assert relerr(pkg.PostProcessing.von_mises_stress(2, 12, np.array([1, 3])), golden["bf_vm"]) < TOL
+    assert int(P.out_data["step"][1]["iter_vec"][0, 0]) == 1
+    # the batched theta path with the same body force: fast kernel (the load vector is all that changes)
+    eng = pkg.CookFemEngine(P.model_data, device=0)
+    assert eng.info["kernel_variant"] == 4
+    lo = fo.LoopOracle(*oracle_mesh, body=(0.01, -0.02))
+    x = golden["x"][:3]
+    yo, ho = fo.fem_fh_loop(lo, x, (math.log(20.0), 0.0), (0.1, 0.015))
+    y, h = eng.forward(_t(x, eng))
+    assert relerr(y.cpu().numpy(), yo) < TOL and relerr(h.cpu().numpy(), ho) < TOL
+    eng.close()
+    # ---- plane stress: forward, fields and the adjoint (finite differences of the oracle), generic kernel
+    eng = pkg.CookFemEngine(golden_model, device=0, stype=1)
+    assert eng.info["kernel_variant"] == 0
+    lo = fo.LoopOracle(*oracle_mesh, stype=1)
+    u, fint, strain, stress = lo.solve(20.0, 0.3)
+    out = eng.fields(emat=_t([[20.0, 0.3]], eng))
+    assert relerr(out["u"][0].cpu().numpy(), u) < TOL and relerr(out["stress"][0].cpu().numpy(), stress) < TOL
+    assert relerr(out["strain"][0].cpu().numpy(), strain) < TOL
+    x = golden["x"][:4]
+    yo, ho = fo.fem_fh_loop(lo, x, (math.log(20.0), 0.0), (0.1, 0.015))
+    gy, gh = np.random.default_rng(51).standard_normal((4, 2)), np.random.default_rng(52).standard_normal((4, 2))
+    y, h, gx = eng.forward_backward(_t(x, eng), _t(gy, eng), _t(gh, eng))
+    assert relerr(y.cpu().numpy(), yo) < TOL and relerr(h.cpu().numpy(), ho) < TOL
+    eps = 1e-5
+    for k in range(2):
+        xp, xm = x.copy(), x.copy()
+        xp[:, k] += eps
+        xm[:, k] -= eps
+        yp, hp = eng.forward(_t(xp, eng))
+        ym, hm = eng.forward(_t(xm, eng))
+        fd = (((yp - ym).cpu().numpy() * gy).sum(1) + ((hp - hm).cpu().numpy() * gh).sum(1)) / (2 * eps)
+        assert np.max(np.abs(fd - gx.cpu().numpy()[:, k])) < 2e-6 * max(1.0, np.abs(fd).max())
+    eng.close()
+    # ---- one (E, nu) per element
+    eng = pkg.CookFemEngine(golden_model, device=0)
+    rng = np.random.default_rng(53)
+    Ee, ve = 20.0 * np.exp(0.2 * rng.standard_normal(200)), 0.2 + 0.2 * rng.random(200)
+    lo = fo.LoopOracle(*oracle_mesh)
+    u, fint, strain, stress = lo.solve(Ee, ve)
+    emat = _t(np.stack([Ee, ve], 1)[None], eng)
+    out = eng.fields_elementwise(emat)
+    assert relerr(out["u"][0].cpu().numpy(), u) < TOL and relerr(out["stress"][0].cpu().numpy(), stress) < TOL
+    assert relerr(out["fint"][0].cpu().numpy(), fint) < 1e-8
+    assert relerr(out["y"][0].cpu().numpy(), u[460:462]) < TOL
+    assert relerr(out["h"][0].cpu().numpy(), fo.von_mises(stress[:, :, 11], (1, 3))) < TOL
+    eng.close()

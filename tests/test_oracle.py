@@ -147,3 +147,28 @@ def test_oracle_jacobian_vs_reference_finite_differences(golden, torch_oracle):
         assert np.max(np.abs(J - jref)) < 2e-9 * np.max(np.abs(jref))
         big = np.abs(jref) > 1e-6
         assert np.max(np.abs(J - jref)[big] / np.abs(jref)[big]) < 2e-8
+
+
+def test_loop_oracle_body_force_matches_reference(golden, oracle_mesh):
+    """The part card's body force (src/mat_subroutine.py:113-116): the oracle's restatement against the
+    unmodified reference twin run with body = (0.01, -0.02) (golden bf_*)."""
+    lo = fo.LoopOracle(*oracle_mesh, body=(0.01, -0.02))
+    u, fint, strain, stress = lo.solve(20.0, 0.3)
+    assert relerr(u, golden["bf_u"]) < 1e-11 and relerr(stress, golden["bf_stress"]) < 1e-11
+    assert relerr(fint, golden["bf_Fint"]) < 1e-10
+    assert relerr(fo.von_mises(stress[:, :, 11], (1, 3)), golden["bf_vm"]) < 1e-11
+
+
+def test_loop_oracle_plane_stress_branch(oracle_mesh):
+    """Plane stress (src/mat_subroutine.py:283-290; not runnable on the reference itself under numpy >= 2):
+    known properties of the restatement -- sigma_zz = 0, eps_33 = -v/(1-v)(eps_xx+eps_yy), softer than plane
+    strain, equilibrium with the load."""
+    ps = fo.LoopOracle(*oracle_mesh, stype=1)
+    pe = fo.LoopOracle(*oracle_mesh, stype=2)
+    u1, f1, e1, s1 = ps.solve(20.0, 0.3)
+    u2, _, _, _ = pe.solve(20.0, 0.3)
+    assert np.all(s1[2] == 0.0)
+    assert relerr(e1[2], -0.3 / 0.7 * (e1[0] + e1[1])) < 1e-14
+    assert np.abs(u1).sum() > 1.05 * np.abs(u2).sum()
+    free = oracle_mesh[1]["free_dof"] - 1
+    assert relerr(f1[free], oracle_mesh[1]["Pf"]) < 1e-9

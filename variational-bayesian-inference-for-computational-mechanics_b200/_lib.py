@@ -18,7 +18,7 @@ REPO = os.path.dirname(_HERE)
 INCLUDE = os.path.join(REPO, "include")
 LIB_PATH = os.environ.get("VBFEM_LIB", os.path.join(CSRC, "libvbfem.so"))  # VBFEM_LIB: profiling builds
 SOURCES = ["vbfem.cu"]
-HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", "vbfem_panel.cuh",
+HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", "vbfem_panel.cuh", "vbfem_warp.cuh",
            os.path.join(INCLUDE, "vbfem.h")]
 
 NVCC_FLAGS = [
@@ -32,7 +32,7 @@ INFO_NAMES = ["nfree", "half_bw", "ndof", "nele", "ncolors", "band_in_smem", "sm
 
 # every symbol include/vbfem.h declares
 SYMBOLS = [
-    "vbfem_create", "vbfem_plan", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_reserve", "vbfem_forward",
+    "vbfem_create", "vbfem_create_ex", "vbfem_fields_elementwise", "vbfem_plan", "vbfem_destroy", "vbfem_last_error", "vbfem_info", "vbfem_reserve", "vbfem_forward",
     "vbfem_backward", "vbfem_keep_ticket", "vbfem_backward_ticket", "vbfem_forward_jac", "vbfem_jac_vjp",
     "vbfem_debug_panel_tables", "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
     "vbfem_forward_backward_host", "vbfem_measure_peaks",
@@ -60,6 +60,11 @@ class VbfemMesh(ctypes.Structure):
         ("theta_mean", ctypes.c_double * 2),
         ("theta_std", ctypes.c_double * 2),
     ]
+
+
+class VbfemOptions(ctypes.Structure):
+    """struct vbfem_options (include/vbfem.h)."""
+    _fields_ = [("stype", ctypes.c_int32), ("reserved", ctypes.c_int32 * 7)]
 
 
 def _stale() -> bool:
@@ -106,6 +111,11 @@ def load():
     i64 = ctypes.c_int64
     lib.vbfem_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(VbfemMesh), ctypes.c_int]
     lib.vbfem_create.restype = ctypes.c_int
+    lib.vbfem_create_ex.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(VbfemMesh),
+                                    ctypes.POINTER(VbfemOptions), ctypes.c_int]
+    lib.vbfem_create_ex.restype = ctypes.c_int
+    lib.vbfem_fields_elementwise.argtypes = [ctypes.c_void_p, i64] + [c_dp] * 8
+    lib.vbfem_fields_elementwise.restype = ctypes.c_int
     lib.vbfem_plan.argtypes = [ctypes.POINTER(VbfemMesh), i64, ctypes.POINTER(i64)]
     lib.vbfem_plan.restype = ctypes.c_int
     lib.vbfem_destroy.argtypes = [ctypes.c_void_p]

@@ -53,6 +53,7 @@ struct DevModel {
     int color_start[kMaxColors + 1];
     double obs_x[4], obs_y[4];
     double thk, theta_mean[2], theta_std[2];
+    int stype;            // 1 plane stress, 2 plane strain (section['stype'], model_property_cards.py:28)
     const double *coord;  // [nnodes][2]
     const int *ien;       // [nele][4] 0-based
     const short *lmb;     // [nele][8] band row of each element dof, -1 if supported
@@ -84,6 +85,7 @@ struct Args {
     long long N;
     int mode;
     const double *x, *emat;
+    int emat_per_ele;  // emat is [N][nele][2] (heterogeneous material, fields / forward only) instead of [N][2]
     double *y, *h;
     const double *gy, *gh;
     double *gx;
@@ -170,8 +172,8 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
     const double h = von_mises_ref(sig, dhdu ? ds : nullptr);
     if (dhdu) {
         const double l2m = mat.lam + 2.0 * mat.mu;
-        const double dexx = ds[0] * l2m + ds[1] * mat.lam + ds[2] * mat.lam;
-        const double deyy = ds[0] * mat.lam + ds[1] * l2m + ds[2] * mat.lam;
+        const double dexx = ds[0] * l2m + ds[1] * mat.lam + ds[2] * mat.szz;
+        const double deyy = ds[0] * mat.lam + ds[1] * l2m + ds[2] * mat.szz;
         const double dgxy = ds[3] * mat.mu;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -179,7 +181,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
             dhdu[2 * a + 1] = deyy * s.ny[a] + dgxy * s.nx[a];
         }
         const double tr = exx + eyy;
-        *dhdl = (ds[0] + ds[1] + ds[2]) * tr;
+        *dhdl = (ds[0] + ds[1] + (mat.szz != 0.0 ? ds[2] : 0.0)) * tr;  // sigma_zz carries lambda only in plane strain
         *dhdm = 2.0 * ds[0] * exx + 2.0 * ds[1] * eyy + ds[3] * gxy;
     }
     return h;
@@ -393,14 +395,24 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
             x1 = A.x[2 * s + 1];
         }
         double *ws_s = A.ws ? A.ws + (size_t)blockIdx.x * A.ws_stride : nullptr;  // per-CTA scratch (band in HBM)
-        if (A.emat) {
+        if (A.emat && !A.emat_per_ele) {
             E = A.emat[2 * s];
             nu = A.emat[2 * s + 1];
         } else {
             E = exp(M.theta_std[0] * x0 + M.theta_mean[0]);
             nu = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
         }
-        const Lame mat = lame_from_E_nu(E, nu);
+        auto make_mat = [&](double Ee, double ve) { return M.stype == 1 ? lame_plane_stress(Ee, ve) : lame_from_E_nu(Ee, ve); };
+        // heterogeneous material: (E, nu) of element e of this sample; the observation uses the observed element's
+        auto ele_mat = [&](int e) {
+            const double *em = A.emat + ((size_t)s * M.nele + e) * 2;
+            return make_mat(em[0], em[1]);
+        };
+        if (A.emat && A.emat_per_ele) {
+            E = A.emat[((size_t)s * M.nele + M.obs_ele) * 2];
+            nu = A.emat[((size_t)s * M.nele + M.obs_ele) * 2 + 1];
+        }
+        const Lame mat = make_mat(E, nu);
         double *band = M.band_in_smem ? smem : ws_s;
         if (tid == 0) s_flag = 0;
 
@@ -439,7 +451,7 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                         // zero predictor (src/fem_solver_tf.py:105-124): strain = 0, only the tangent matters
                         double sig[4];
                         Tangent C;
-                        mat_isotropic_plane_strain(mat, 0.0, 0.0, 0.0, sig, C);
+                        mat_isotropic_plane_strain(A.emat_per_ele ? ele_mat(e) : mat, 0.0, 0.0, 0.0, sig, C);
                         accumulate_kt(sh, C, ke);
                     }
                 }
@@ -666,7 +678,7 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                         double exx, eyy, gxy, sig[4];
                         Tangent C;
                         strain_q4(sh, ue, exx, eyy, gxy);
-                        mat_isotropic_plane_strain(mat, exx, eyy, gxy, sig, C);
+                        mat_isotropic_plane_strain(A.emat_per_ele ? ele_mat(e) : mat, exx, eyy, gxy, sig, C);
                         // p += dvol * Bm^T sig[0,1,3]   (src/mat_subroutine_tf.py:147-159)
 #pragma unroll
                         for (int a = 0; a < 4; ++a) {
@@ -686,7 +698,13 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                         if (A.eps_out) {
                             A.eps_out[o] = exx;
                             A.eps_out[o + cs] = eyy;
-                            A.eps_out[o + 2 * cs] = 0.0;
+                            // plane stress: eps33 = -v / (1 - v) (eps_xx + eps_yy)  (src/mat_subroutine.py:289, :51-52)
+                            double e33 = 0.0;
+                            if (M.stype == 1) {
+                                const double ve = A.emat_per_ele ? A.emat[((size_t)s * M.nele + e) * 2 + 1] : nu;
+                                e33 = -ve / (1.0 - ve) * (exx + eyy);
+                            }
+                            A.eps_out[o + 2 * cs] = e33;
                             A.eps_out[o + 3 * cs] = gxy;
                             A.eps_out[o + 4 * cs] = 0.0;
                             A.eps_out[o + 5 * cs] = 0.0;
@@ -809,7 +827,9 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
                 const double gm = -tm + gh0 * obs_s[10] + gh1 * obs_s[12 + 10];
                 const double t = (1.0 + nu) * (1.0 - 2.0 * nu);
                 const double dl_dE = mat.lam / E, dm_dE = mat.mu / E;
-                const double dl_dnu = E * (1.0 + 2.0 * nu * nu) / (t * t);
+                // plane strain: lambda = v E / ((1 + v)(1 - 2 v)); plane stress: lambda' = v E / (1 - v^2)
+                const double u2 = 1.0 - nu * nu;
+                const double dl_dnu = M.stype == 1 ? E * (1.0 + nu * nu) / (u2 * u2) : E * (1.0 + 2.0 * nu * nu) / (t * t);
                 const double dm_dnu = -0.5 * E / ((1.0 + nu) * (1.0 + nu));
                 const double gE = gl * dl_dE + gm * dm_dE;
                 const double gnu = gl * dl_dnu + gm * dm_dnu;
@@ -1077,10 +1097,22 @@ static std::vector<int> rcm_order(const vbfem_mesh *m) {
     return order;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel FUNCTION, not to a handle: two engines (two
+// meshes) share it, and the one created last would cap the other's launches.  Always opt in to the device maximum.
+static int g_smem_optin = 232448;
+template <typename F>
+static cudaError_t allow_max_smem(F k) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin - (int)fa.sharedSizeBytes);
+}
+
 template <int NT, int EPT, int MINB, bool HBM>
 static int configure(vbfem_handle *h, size_t smem) {
     kernel_fn k = fem_kernel<NT, EPT, MINB, HBM>;
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > (size_t)g_smem_optin) return fail(-3, "kernel does not fit: %zu bytes of shared memory", smem);
+    CU(allow_max_smem(k));
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NT, smem));
     if (nb < 1) return fail(-3, "kernel does not fit: %zu bytes of shared memory", smem);
@@ -1481,7 +1513,13 @@ static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
+    return vbfem_create_ex(out, m, nullptr, device);
+}
+
+extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_options *opt, int device) {
     if (!out || !m) return fail(-1, "null argument");
+    const int stype = opt ? opt->stype : 2;
+    if (stype != 1 && stype != 2) return fail(-1, "section stype %d not supported (1 plane stress, 2 plane strain)", stype);
     if (m->nnodes <= 0 || m->nele <= 0 || m->nfree <= 0 || !m->coord || !m->ien || !m->free_dof || !m->pf)
         return fail(-1, "incomplete mesh description");
     int ndev = 0;
@@ -1571,6 +1609,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     M.ncolors = ncolors;
     M.nitems = b * (b + 1) / 2 + b;
     M.thk = m->thk;
+    M.stype = stype;
     for (int k = 0; k < 2; ++k) {
         M.theta_mean[k] = m->theta_mean[k];
         M.theta_std[k] = m->theta_std[k];
@@ -1636,6 +1675,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    g_smem_optin = (int)prop.sharedMemPerBlockOptin;
     {
         int NT = (M.nitems <= 352) ? 352 : (M.nitems <= 512 ? 256 : (M.nitems <= 4096 ? 512 : 1024));
         {   // band in HBM: 256 threads (255 registers, no spills: the per-column loop must not touch local memory)
@@ -1686,6 +1726,11 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
     CU(cudaMalloc(&h->elbo_ysum, 8 * sizeof(double)));
     h->info_colors = ncolors;
     const bool force_panel = getenv("VBFEM_FORCE_PANEL") != nullptr;
+    if (stype != 2) {  // plane stress: the generic kernel serves every mode (the fast kernels are plane strain only)
+        guard.p = nullptr;
+        *out = h;
+        return 0;
+    }
 
     // ---- warp-per-sample kernel: narrow bands (block half bandwidth <= 3), window in registers, 12 samples per SM
     if (!force_panel && want_warp_kernel()) {
@@ -1715,7 +1760,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             bool fits = true;
             const size_t smem = (size_t)NW * warp_smem + warp_kernel_tab_bytes(P);
             for (int q = 0; q < 3 && fits; ++q) {
-                cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e1 = allow_max_smem(ks[q]);
                 int nb = 0;
                 if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], NW * 32, smem);
                 if (e1 != cudaSuccess || nb < 1) {
@@ -1842,7 +1887,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
                                fem_front_kernel<TB, TNT, 2>};
             int nbmin = 1 << 30;
             for (int q = 0; q < 3; ++q) {
-                cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr_smem);
+                cudaError_t e1 = allow_max_smem(ks[q]);
                 int nb = 0;
                 if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], TNT, fr_smem);
                 if (e1 != cudaSuccess || nb < 1) {
@@ -1896,7 +1941,7 @@ extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
             int nbmin = 1 << 30;
             bool fits = true;
             for (int q = 0; q < 3 && fits; ++q) {
-                cudaError_t e1 = cudaFuncSetAttribute(ks[q], cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
+                cudaError_t e1 = allow_max_smem(ks[q]);
                 int nb = 0;
                 if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], kPanelNT, P.smem_bytes);
                 if (e1 != cudaSuccess || nb < 1) {
@@ -2284,6 +2329,23 @@ extern "C" int vbfem_fields(vbfem_t *h, int64_t N, const double *x, const double
     a.mode = kFields;
     a.x = x;
     a.emat = emat;
+    a.u_out = u;
+    a.sig_out = sig;
+    a.eps_out = eps;
+    a.fint_out = fint;
+    return launch(h, a, stream);
+}
+
+extern "C" int vbfem_fields_elementwise(vbfem_t *h, int64_t N, const double *emat, double *y, double *hh, double *u,
+                                        double *sig, double *eps, double *fint, void *stream) {
+    if (!h || (N > 0 && !emat)) return fail(-1, "null argument");
+    Args a{};
+    a.N = N;
+    a.mode = kFields;
+    a.emat = emat;
+    a.emat_per_ele = 1;
+    a.y = y;
+    a.h = hh;
     a.u_out = u;
     a.sig_out = sig;
     a.eps_out = eps;

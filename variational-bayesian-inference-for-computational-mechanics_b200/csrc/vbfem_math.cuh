@@ -100,11 +100,23 @@ struct Tangent {
 // (src/mat_subroutine_tf.py:75-76).
 struct Lame {
     double lam, mu;
+    double szz;  // sigma_zz = szz * (eps_xx + eps_yy): lambda in plane strain, 0 in plane stress
 };
 __device__ __forceinline__ Lame lame_from_E_nu(double E, double v) {
     Lame m;
     m.lam = v * E / ((1.0 + v) * (1.0 - 2.0 * v));
     m.mu = 0.5 * E / (1.0 + v);
+    m.szz = m.lam;
+    return m;
+}
+// Plane stress (src/mat_subroutine.py:283-290): Ce = E / (1 - v^2) [[1, v, 0], [v, 1, 0], [0, 0, (1 - v) / 2]] is
+// the plane-strain tangent with lambda replaced by lambda' = v E / (1 - v^2) (lambda' + 2 mu = E / (1 - v^2),
+// (1 - v) / 2 * E / (1 - v^2) = mu); sigma_zz = 0.
+__device__ __forceinline__ Lame lame_plane_stress(double E, double v) {
+    Lame m;
+    m.lam = v * E / (1.0 - v * v);
+    m.mu = 0.5 * E / (1.0 + v);
+    m.szz = 0.0;
     return m;
 }
 __device__ __forceinline__ void mat_isotropic_plane_strain(const Lame &m, double exx, double eyy, double gxy,
@@ -112,7 +124,7 @@ __device__ __forceinline__ void mat_isotropic_plane_strain(const Lame &m, double
     const double l2m = m.lam + 2.0 * m.mu;
     sig[0] = l2m * exx + m.lam * eyy;    // + lam*0 + 0*gxy
     sig[1] = m.lam * exx + l2m * eyy;
-    sig[2] = m.lam * exx + m.lam * eyy;  // sigma_zz
+    sig[2] = m.szz * exx + m.szz * eyy;  // sigma_zz
     sig[3] = m.mu * gxy;
     C.c11 = l2m;
     C.c12 = m.lam;

@@ -117,6 +117,7 @@ __device__ __noinline__ void warp_element_batch(const double *__restrict__ ecoor
     Lame mat;
     mat.lam = lam;
     mat.mu = mu;
+    mat.szz = lam;
     double xl[4], yl[4], kev[36];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {

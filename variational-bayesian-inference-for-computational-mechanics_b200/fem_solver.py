@@ -51,6 +51,30 @@ def mesh_struct(md, theta_mean=(math.log(20.0), 0.0), theta_std=(0.1, 0.015), no
     return mesh, keep
 
 
+def body_force_vector(md, body):
+    """Consistent nodal forces of a constant body force b = (bx, by) per unit volume: sum over the 2x2 Gauss
+    points of dvol * Nm^T b (src/mat_subroutine_tf.py:157-158; upstream subtracts this term from the element
+    residual p, which is the same as adding it to the external load).  Returns a dense [ndof] vector."""
+    mi, di = md["mesh_info"], md["dof_info"]
+    xy = np.asarray(mi["coord"], dtype=np.float64)[:, 1:3]
+    ien = np.asarray(di["IEN"], dtype=np.int64) - 1
+    thk = float(md["section"][0]["thk"]) if "section" in md else 10.0
+    g = 0.577350269189626                           # src/fem_preprocess.py:19
+    pts = [(-g, -g), (g, -g), (g, g), (-g, g)]      # src/fem_preprocess.py:553-558
+    f = np.zeros(int(di["ndof"]))
+    b = np.asarray(body, dtype=np.float64).reshape(-1)[:2]
+    for xi, eta in pts:
+        N = 0.25 * np.array([(1 - xi) * (1 - eta), (1 + xi) * (1 - eta), (1 + xi) * (1 + eta), (1 - xi) * (1 + eta)])
+        dN = 0.25 * np.array([[-(1 - eta), (1 - eta), (1 + eta), -(1 + eta)],
+                              [-(1 - xi), -(1 + xi), (1 + xi), (1 - xi)]])
+        X = xy[ien]                                  # [nele, 4, 2]
+        J = np.einsum("ia,eaj->eij", dN, X)
+        dvol = thk * (J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0])
+        for c in range(2):
+            np.add.at(f, 2 * ien + c, dvol[:, None] * N[None, :] * b[c])
+    return f
+
+
 def plan_layout(md, node_id=231, ele_id=12, nipt_id=(1, 3), smem_per_sm=0):
     """What ``vbfem_create`` would decide for this mesh and observation set-up, computed on the host
     without a GPU (``vbfem_plan``): kernel variant, order, half bandwidth, front split, orientation."""
@@ -65,7 +89,10 @@ class CookFemEngine:
     """One libvbfem handle (= one GPU).  Not re-entrant."""
 
     def __init__(self, model_data=None, device=None, theta_mean=(math.log(20.0), 0.0), theta_std=(0.1, 0.015),
-                 node_id=231, ele_id=12, nipt_id=(1, 3)):
+                 node_id=231, ele_id=12, nipt_id=(1, 3), stype=None, body=None):
+        """``stype``: 1 plane stress / 2 plane strain (default: section[0]['stype'] of the model, else 2);
+        ``body``: constant body force (bx, by) (default: part[0]['body'] of the model, else none) -- added to the
+        load vector as consistent nodal forces."""
         import torch
 
         self.torch = torch
@@ -79,9 +106,25 @@ class CookFemEngine:
         mi, di = md["mesh_info"], md["dof_info"]
         self.nnodes, self.nele, self.ndof = int(mi["nnodes"]), int(mi["nele"]), int(di["ndof"])
         self.nfree = int(di["nfree"])
+        if stype is None:
+            stype = int(md["section"][0].get("stype", 2)) if "section" in md else 2
+        if body is None and "part" in md:
+            body = np.asarray(md["part"][0].get("body", np.zeros(3)), dtype=np.float64).reshape(-1)[:2]
+        self.stype = int(stype)
+        self.body_force = None
+        if body is not None and np.any(np.asarray(body) != 0.0):
+            self.body_force = body_force_vector(md, body)
+            md = dict(md)
+            pf = md["loading"]["Pf"]
+            pf = pf.toarray() if hasattr(pf, "toarray") else np.asarray(pf)
+            free = np.asarray(di["free_dof"], dtype=np.int64) - 1
+            md["loading"] = dict(md["loading"], Pf=pf.reshape(-1) + self.body_force[free])
         mesh, keep = mesh_struct(md, theta_mean, theta_std, node_id, ele_id, nipt_id)
+        opt = _lib.VbfemOptions()
+        opt.stype = self.stype
         h = ctypes.c_void_p()
-        _lib.check(self.lib.vbfem_create(ctypes.byref(h), ctypes.byref(mesh), self.device_index), "vbfem_create")
+        _lib.check(self.lib.vbfem_create_ex(ctypes.byref(h), ctypes.byref(mesh), ctypes.byref(opt), self.device_index),
+                   "vbfem_create_ex")
         self._h = h
         self.device = torch.device("cuda", self.device_index)
         info = (ctypes.c_int64 * _lib.INFO_COUNT)()
@@ -212,6 +255,29 @@ class CookFemEngine:
                 self._chk(emat, n, "emat") if emat is not None else null,
                 p("u"), p("stress"), p("strain"), p("fint"), self._stream()), "vbfem_fields")
             self.launches += 1
+        if "fint" in out and self.body_force is not None:
+            # upstream's element residual is Bm^T sigma - Nm^T b (src/mat_subroutine_tf.py:157-158)
+            out["fint"] -= self.torch.as_tensor(self.body_force, device=self.device)
+        return out
+
+    def fields_elementwise(self, emat, want=("y", "h", "u", "stress", "strain", "fint")):
+        """Heterogeneous material: emat[N, nele, 2] = (E, nu) per sample AND element -> observations and full
+        fields (forward only; ``vbfem_fields_elementwise``)."""
+        n = emat.shape[0]
+        if emat.device != self.device or emat.dtype != self.torch.float64 or not emat.is_contiguous() \
+                or tuple(emat.shape) != (n, self.nele, 2):
+            raise ValueError(f"emat must be a contiguous float64 [{n},{self.nele},2] tensor on {self.device}")
+        shapes = {"y": (n, 2), "h": (n, 2), "u": (n, self.ndof), "stress": (n, 6, 4, self.nele),
+                  "strain": (n, 6, 4, self.nele), "fint": (n, self.ndof)}
+        out = {k: self._new(*shapes[k]) for k in want}
+        p = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else ctypes.c_void_p(0)
+        if n:
+            _lib.check(self.lib.vbfem_fields_elementwise(self._h, n, ctypes.c_void_p(emat.data_ptr()), p("y"), p("h"),
+                                                         p("u"), p("stress"), p("strain"), p("fint"), self._stream()),
+                       "vbfem_fields_elementwise")
+            self.launches += 1
+        if "fint" in out and self.body_force is not None:
+            out["fint"] -= self.torch.as_tensor(self.body_force, device=self.device)
         return out
 
     def elbo_step1_partials(self, mu, sig2, e_data, y_batch, sig_e, j_begin=0, j_end=None, want_f=False):
@@ -289,10 +355,22 @@ def default_engine(device=None, **obs):
 
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    key = (id(PreProcessing.model_data.get("dof_info")), int(device), repr(sorted(obs.items())))
+    md = PreProcessing.model_data
+    import hashlib
+    hsh = hashlib.sha1()
+    for a in (md["dof_info"]["IEN"], np.asarray(md["mesh_info"]["coord"])[:, 1:3], md["dof_info"]["free_dof"]):
+        hsh.update(np.ascontiguousarray(a).tobytes())
+    pf = md["loading"]["Pf"]
+    hsh.update(np.ascontiguousarray(pf.toarray() if hasattr(pf, "toarray") else pf).tobytes())
+    sec = md.get("section", [{}])[0]
+    body = np.asarray(md["part"][0].get("body", np.zeros(3)), dtype=np.float64).reshape(-1) if "part" in md else np.zeros(3)
+    key = (hsh.hexdigest(), int(device), repr(sorted(obs.items())), int(sec.get("stype", 2)), float(sec.get("thk", 10.0)),
+           body.tobytes())
     eng = _engines.get(key)
     if eng is None:
-        eng = CookFemEngine(PreProcessing.model_data, device, **obs)
+        if len(_engines) >= 8:   # bounded cache: the oldest engine (and its GPU workspace) goes
+            _engines.pop(next(iter(_engines))).close()
+        eng = CookFemEngine(md, device, **obs)
         _engines[key] = eng
     return eng
 
@@ -303,7 +381,7 @@ class FemSolver:
     @classmethod
     def fea_solution(cls, input_data=None, device=None):
         md = PreProcessing.model_data
-        if md["solution_control"]["solver"] != 1:
+        if md["solution_control"]["solver"] not in (1, 2):
             raise ValueError("Illegal solver option")  # src/fem_solver_tf.py:27-28
         cls.global_linear_solver(device)
 
@@ -336,12 +414,26 @@ class FemSolver:
         react = np.zeros(di["ndof"])
         react[supp] = sd["F_int"][supp, 0]
         duf = sd["u_n1"][free, 0]
-        resid = sd["F_int"][free, 0] - np.asarray(md["loading"]["Pf"]).reshape(-1)
+        pf_dense = md["loading"]["Pf"]
+        pf_dense = (pf_dense.toarray() if hasattr(pf_dense, "toarray") else np.asarray(pf_dense)).reshape(-1)
+        resid = sd["F_int"][free, 0] - pf_dense
         step = {"Pf": md["loading"]["Pf"], "Us": md["loading"]["Us"], "Uf": sd["u_n1"][free],
                 "Ps": sd["F_int"][supp, 0].copy(), "nodal_disp": u.reshape(2, nn, order="F"),
                 "nodal_react": react.reshape(2, nn, order="F"),
                 "tol_vec": np.array([abs(float(duf @ resid))]),  # energy norm, src/fem_solver.py:106-113
                 "iter_vec": np.array([[1]]), "load_ratio": np.array([[1.0]])}
+        if md["solution_control"]["solver"] == 2:
+            # Newton-Raphson with the cards' nr_param (model_property_cards.py:57; src/fem_solver.py:106-124): the
+            # batched solve is iteration 1 from the zero predictor; the energy norm |du . R| of the re-assembled
+            # residual is then checked against tol_cr.  The material is linear, so iteration 2 would add a
+            # displacement of the size of that residual: it converges here or the factorisation failed.
+            nr = md["solution_control"].get("nr_param", {"max_iter": 10, "tol_cr": 1.0e-10})
+            ref = abs(float(duf @ pf_dense)) or 1.0
+            if step["tol_vec"][0] > nr["tol_cr"] * ref and nr["max_iter"] <= 1:
+                raise ValueError("Newton-Raphson did not converge within max_iter")
+            if step["tol_vec"][0] > max(nr["tol_cr"] * ref, 1e-6 * ref):
+                raise ValueError("Illegal exiting flag")
+            step["iter_vec"] = np.array([[1 if step["tol_vec"][0] <= nr["tol_cr"] * ref else 2]])
         if len(od["step"]) > 1:
             od["step"][1] = step
         else:
