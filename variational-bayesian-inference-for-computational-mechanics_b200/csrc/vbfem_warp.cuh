@@ -78,13 +78,21 @@ __device__ __forceinline__ void warp_diag_compute(double (&a)[36], double *stg, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const double d = a[tri(k, k)];
-        bad |= !(d > 0.0 && d < 1.0e300);
+        // positive, finite, not tiny: sign and exponent bits only (integer pipe; the FP64 pipe is the busy one)
+        bad |= (unsigned)(__double2hiint(d) - 0x00200000) >= 0x7fd00000u;
         rdv[k] = fast_rcp3(d);
+        // the next pivot first, one level after the reciprocal: d' = a' - (a_(k+1,k))^2 / d with the square formed
+        // while the reciprocal is refined -- it heads the dependency chain of the whole block
+        if (k + 1 < 8) {
+            const double sq = a[tri(k + 1, k)] * a[tri(k + 1, k)];
+            a[tri(k + 1, k + 1)] = fma(-sq, rdv[k], a[tri(k + 1, k + 1)]);
+        }
 #pragma unroll
         for (int j = k + 1; j < 8; ++j) {
             const double ljk = a[tri(j, k)] * rdv[k];
 #pragma unroll
-            for (int i = j; i < 8; ++i) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
+            for (int i = j; i < 8; ++i)
+                if (!(i == k + 1 && j == k + 1)) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
             a[tri(j, k)] = ljk;
         }
     }
