@@ -128,10 +128,11 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
     // lane stores, everybody reads the broadcast back
     double zj[NRA];
 #pragma unroll
-    for (int r = 0; r < NRA; ++r) {
-        sts_if(zp + r * vs, st.zr[r], k == 0);
+    for (int r = 0; r < NRA; ++r) sts_if(zp + r * vs, st.zr[r], k == 0);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < NRA; ++r)
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(zj[r]) : "r"(zp + r * vs) : "memory");
-    }
 #pragma unroll 1
     for (int j = j0; j < j1; ++j) {
         const bool sub = (unsigned)(k - 1) < (unsigned)B;  // 1 <= k <= B: a sub-diagonal row of column j
@@ -153,6 +154,7 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
         const double w = vm * rd;
         sts_if(pk, w, sub);
         sts_if(colp, rd, k == 0);
+        __syncwarp();  // the scaled column is read back by every lane: order the exchange (CUDA memory model)
         // ... the rest is interleaved with the broadcast loads of column j's scaled entries (each
         // load overwrites a pair the late update has just consumed), so that the FP64 pipe and
         // the shared-memory pipe work at the same time
@@ -200,10 +202,11 @@ __device__ __forceinline__ void front_eliminate(FrontState<B> &st, unsigned band
         for (int r = 0; r < NRA; ++r) lds_if(st.zr[r], zs + r * vs + 8u * (unsigned)R, wrap);
         const bool pst = (k == 0) && (j + 1 < j1);  // nothing to publish behind the last column
 #pragma unroll
-        for (int r = 0; r < NRA; ++r) {
-            sts_if(zp + r * vs, st.zr[r], pst);
+        for (int r = 0; r < NRA; ++r) sts_if(zp + r * vs, st.zr[r], pst);
+        __syncwarp();  // the pivot lane's right-hand-side entries are read by every lane
+#pragma unroll
+        for (int r = 0; r < NRA; ++r)
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(zj[r]) : "r"(zp + r * vs) : "memory");
-        }
         v = vn;
         d = dn;
         v1 = v1n;
