@@ -66,10 +66,11 @@ enum {
     VBFEM_INFO_NUM_SMS = 8,
     VBFEM_INFO_BLOCK_THREADS = 9,
     VBFEM_INFO_KERNEL_VARIANT = 10, /* 0 = generic per-column kernel, 2 = on-chip two-front kernel,
-                                       3 = blocked panel kernel (wide bands, factor streamed to HBM) */
+                                       3 = blocked panel kernel (wide bands, factor streamed to HBM),
+                                       4 = warp-per-sample kernel (narrow bands, window in registers) */
     VBFEM_INFO_TWIST_ROW = 11,      /* first middle row of the twisted factorisation */
-    VBFEM_INFO_PANEL_BLOCKS = 12,   /* panel kernel: block half bandwidth (8x8 blocks below the diagonal block) */
-    VBFEM_INFO_PANEL_RING = 13,     /* panel kernel: capacity of the element-matrix ring */
+    VBFEM_INFO_PANEL_BLOCKS = 12,   /* panel / warp kernel: block half bandwidth (8x8 blocks below the diagonal block) */
+    VBFEM_INFO_PANEL_RING = 13,     /* panel / warp kernel: capacity of the element-matrix ring */
     VBFEM_INFO_COUNT = 16
 };
 
@@ -91,8 +92,8 @@ typedef struct vbfem_options {
 int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *mesh, const vbfem_options *opt /* NULL: defaults */, int device);
 
 /* The host-side plan vbfem_create would make for this mesh and observation set-up, WITHOUT touching
- * a GPU (unit tests of the numbering / orientation / front split): out[0] = kernel variant (2 = on-chip
- * two-front kernel, 3 = blocked panel kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
+ * a GPU (unit tests of the numbering / orientation / front split): out[0] = kernel variant (4 = warp-per-sample
+ * kernel, 2 = on-chip two-front kernel, 3 = blocked panel kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
  * middle row pT, out[4] = bottom-front columns nB, out[5] = 1 if the band order was reversed so that
  * it ends at the observed node, out[6] = shared memory per CTA in bytes, out[7] reserved.
  * smem_per_sm: shared memory per SM assumed for the fit test (<= 0: 233472, B200). */

@@ -12,9 +12,11 @@
 //   (d) fused displacement / von Mises observation [src/fem_postprocess.py:172-185]
 //   (e) adjoint: reuse the factor for K psi = dJ/du, contract -psi^T (dK/dp) u element
 //       by element, chain to x [what tape.gradient derives, main_custom_training.py:252-256]
-// Two kernels: fem_front_kernel (vbfem_front_kernel.cuh; band on chip, two warp-synchronous
-// elimination fronts -- the production path for Cook 20x10) and fem_kernel below (any
-// bandwidth, band in shared memory or HBM, full fields).
+// Four kernels: fem_warp_kernel (vbfem_warp.cuh; one warp per sample, the elimination
+// window in registers, 8x8 blocks on FP64 tensor-core MMAs -- the production path for Cook 20x10),
+// fem_panel_kernel (vbfem_panel.cuh; one CTA per sample, wide bands, factor streamed to HBM -- Cook 80x40),
+// fem_front_kernel (vbfem_front_kernel.cuh; band on chip, two warp-synchronous column fronts) and fem_kernel
+// below (any bandwidth, band in shared memory or HBM, full fields, plane stress, per-element materials).
 // Paths are relative to nfeng2022/Variational-Bayesian-Inference-for-Computational-Mechanics.
 #include <cuda_runtime.h>
 
