@@ -34,8 +34,10 @@ METRIC = "FEM forward+adjoint solves/s (Cook 20x10, batch 4096 per GPU)"
 FLOP_PER_SOLVE = 1600 * 200 + 440 * (25 * 25 + 3 * 25) + 2 * 4 * 440 * 25   # = 0.716 MFLOP
 BYTES_PER_SOLVE = 96                                                          # x, gy, gh in; y, h, gx out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch at batch 4096 from the committed
-# `ncu --set full` capture (profiles/r01_ncu_front_kernel_final_details.txt): 328 704 B read, 0 B written
-NCU_DRAM_BYTES_PER_LAUNCH = 328704
+# `ncu --set full` capture of the warp-per-sample kernel (profiles/r02_ncu_warp_adj_raw_selected.txt):
+# 366.5 MB read + 533.3 MB written -- the factor slab of the adjoint (141 KB per sample, written once, read once);
+# the forward-only launch moves the compulsory 48 B per sample.
+NCU_DRAM_BYTES_PER_LAUNCH = 366493184 + 533329152
 # config 4 (80x40): DRAM bytes per fused forward+adjoint SOLVE from the committed capture of the panel kernel
 NCU_C4_DRAM_BYTES_PER_SOLVE = int((1.871130e9 + 1.928987e9) / 296)   # 12.84 MB (read 6.32 + written 6.52)
 
@@ -527,12 +529,18 @@ def run_cuda(args):
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64.value, "unit": "TFLOP/s",
                          "frac": tflops / fp64.value if fp64.value else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_unit": "bytes of DRAM traffic per launch (ncu, batch 4096): the band never leaves the SM",
+                         "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, batch 4096, fused forward+adjoint): "
+                                         "220 KB per sample = the scaled factor panels streamed to a per-warp slab and read "
+                                         "back once by the reverse pass (SURVEY 8d counts 4 n (b+1) 8 = 366 KB per sample for "
+                                         "a streamed factor); compulsory I/O is 96 B per sample",
                          "peak_source": "DFMA loop measured on this GPU by vbfem_measure_peaks "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_solve": FLOP_PER_SOLVE,
                          "hbm": {"achieved_gbs": BYTES_PER_SOLVE * BATCH / launch_s / 1e9, "peak_gbs": hbm_peak,
-                                 "note": "compulsory I/O only; the band lives on chip"}},
+                                 "measured_dram_gbs": NCU_DRAM_BYTES_PER_LAUNCH / launch_s / 1e9,
+                                 "note": "achieved_gbs = compulsory I/O only; measured_dram_gbs = the ncu traffic of one "
+                                         "launch over this run's launch time (factor slab): well below the HBM peak, the "
+                                         "kernel is bound by the FP64 / DMMA pipe and its dependency chains"}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "elbo": {"metric": "ELBO training steps/s (Cook 20x10, 8192 Monte-Carlo samples per GPU)",
