@@ -1,192 +1,31 @@
-// vbfem_panel.cuh -- blocked banded LDL^T for wide bands (Cook 80x40: n = 6560, half bandwidth 85):
-// one CTA per Monte-Carlo sample, two CTAs per SM, the factor streamed to HBM with bulk copies.
-//
-// The matrix is cut into 8x8 blocks.  A "panel" is one block column: the diagonal block and the
-// NB blocks below it (NB = 11 for b = 85) plus ONE extra block row that carries up to eight
-// right-hand sides through the elimination (row 0: the load vector, rows 1..6: the six strain
-// functionals B^T of the two observed Gauss points).  Per panel:
-//   diag   the 8x8 diagonal block is factored (LDL^T) and its unit lower factor inverted, in
-//          registers, by one warp;
-//   solve  every block below becomes V = X * L11^-T (two FP64 tensor-core MMAs m8n8k4 per block);
-//   update the trailing window, (NB+1) NB/2 + NB blocks, takes its rank-8 update C -= L V^T, again
-//          two DMMAs per block.  Fragments are read and written as ONE 16-byte access per lane at
-//          (block base + 16 * lane): the 8x8 row-major block is exactly the C fragment layout,
-//          and with the contraction index split {0,2,4,6} / {1,3,5,7} over the two MMAs it is
-//          the A and B fragment layout too -- no shuffles, no bank conflicts;
-//   fresh  the block row entering the window is assembled on the fly by an atomics-free GATHER
-//          (host table: target entry <- up to four element-matrix entries) from a ring of element
-//          matrices that the per-element Q4 kernels fill a batch ahead (src/mat_subroutine_tf.py:23-110,
-//          src/fem_solver_tf.py:229-341 upstream).  K itself never exists in HBM.
-// Only the lower triangle of the window is kept: diagonal d of the window is a ring of NB+2-d block
-// slots (NB+1-d live blocks and one spare), the slot of block (I, J) is J mod (NB+2-d); 46 KB for NB = 11.
-// The spare slot lets the block row entering the window be assembled WHILE the current panel is
-// being applied.  Warp roles inside a panel step (two block barriers per panel):
-//   solve   warps 0..5: the blocks below the (already factored) diagonal block
-//   update  warps 0..5: the trailing blocks, software pipelined (the next block's fragments are in
-//           flight while the current block's two MMAs run);
-//           warp 6: updates the NEXT diagonal block first and factors it at once (look-ahead), and
-//           sends the finished panel to HBM;  warp 7: element matrices + gather of the entering row.
-//
-// The band order ENDS at the observed node, so its displacement y falls out of the last diagonal
-// block; the observed strains are eps_i = q_i^T K^-1 f = sum_c z_qi[c] z_f[c] / d_c, accumulated from
-// the right-hand-side rows while they are eliminated: forward mode needs no back substitution and
-// writes nothing to HBM.  With an adjoint (fused or Jacobian mode) the scaled panels (L^T blocks, the
-// INVERSE of the diagonal block's unit factor, D^-1 z rows) go to a per-CTA HBM slab by
-// cp.async.bulk, and ONE reverse pass (bulk loads through an mbarrier ring) back-substitutes u and
-// up to four adjoint vectors together: the right-hand side of psi = K^-1 w is a combination of the
-// stored rows, since w lies in the span of the strain functionals and the observed node.
-// Replaces tf.linalg.solve (src/fem_solver_tf.py:137 upstream) and its gradient on wide bands.
+// vbfem_panel2.cuh -- second generation of the blocked panel kernel for wide bands (Cook 80x40): the same
+// mathematics, warp roles, element ring, row records and reverse pass as vbfem_panel.cuh, but the TRAILING WINDOW
+// LIVES IN REGISTERS.  The (NB+1) NB / 2 + ... off-diagonal window blocks and the right-hand-side ring -- 90 ring
+// slots for NB = 11 -- are dealt to the six update warps, 15 slots (30 doubles per lane) each.  A slot keeps its
+// place in its diagonal's ring (slot r of diagonal d holds the block whose column is congruent to r modulo the
+// ring length), so its ROLE changes from panel to panel -- J = (r - p) mod len: 0 = in the panel column (solve,
+// publish V and -L to shared memory), 1..len-2 = trailing block (update), len-1 = spare (the entering row's
+// block is being assembled for it) -- while its REGISTERS never move.  The update is then two MMAs on two
+// fragment loads: no accumulator load, no store, no load-to-use chain through shared memory per block (the first
+// generation spent 47 % of its stall samples there).  Only the diagonal ring stays in shared memory (the
+// look-ahead warp factors from it).
 #pragma once
-#include "vbfem_front.cuh"
+#include "vbfem_panel.cuh"
 
 namespace vbfem {
 
-constexpr int kPanelNT = 256, kPanelNW = kPanelNT / 32, kPanelNBMax = 15, kPanelStagesMax = 8;
-constexpr int kPanelUpdW = 6;   // warps 0..5 solve and update; warp 6: diagonal look-ahead; warp 7: assembly
-constexpr int kPanelEB = 8;     // element matrices per pass of one warp (lane = element x Gauss point)
-constexpr int kPanelRecDepth = 4;  // row records in flight to the assembling warp (bulk copies into a shared-memory ring)
-
-struct PanelModel {
-    int n, off, npad, NQ, NB;  // order, leading pad rows, padded order, panels, block half bandwidth
-    int R;                     // capacity of the element-matrix ring
-    int nub;                   // blocks of one trailing update
-    int obs_loc[2];            // row inside the last panel of the observed node's (x, y) dof, -1 if supported
-    int o_win, o_rhs, o_lst, o_ke, smem_bytes;  // shared-memory offsets in bytes
-    int stages;                // bulk-load ring of the reverse pass
-    int o_lneg;                // NB+2 blocks: -L of the current panel, row major (block b: block row p+b; NB+1: rhs), then a dummy block
-    int o_rec, rec_stride, rec_o_src, rec_o_dst;  // row-record ring in shared memory / record layout (bytes)
-    // second generation (vbfem_panel2.cuh): shared-memory offsets of the diagonal ring, the entering-row staging area,
-    // the V blocks, the region the reverse pass re-uses as its bulk-load ring; ring slots (diagonal d, position r)
-    // of update warp w, d = 0: unused, d = NB+1: right-hand-side ring
-    int o_wdiag, o_fresh, o_vst, o_big;
-    unsigned char slot_d[kPanelUpdW][16], slot_r[kPanelUpdW][16];
-    int kstart[kPanelNW + 1];  // update blocks [kstart[w], kstart[w+1]) belong to warp w < kPanelUpdW
-    unsigned short ub[kPanelNBMax * (kPanelNBMax + 1) / 2 + kPanelNBMax];  // (I << 8) | J
-    // Row record of block row q (rec_stride bytes, what the row needs to enter the window): int32 header
-    // {new elements, gather entries, first new element (first-use order)}, the 8x8 right-hand-side block,
-    // gather sources (ushort4: element-ring entries slot * 36 + tri, unused -> the zero entry) and gather
-    // targets (u16: d * 64 + g * 8 + c)
-    const unsigned char *rec;
-    const int *eneed;            // [NQ] elements (first-use order) block row q needs
-    const double *ecoord;        // [nele][4][2] nodal coordinates of the elements in first-use order
-    double *kews;                // per-CTA scratch: the sample's element matrices [nele][36], first-use order
-    long long kews_stride;
-    const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported
-    double *lws;                 // per-CTA factor slab
-    long long lws_stride;        // doubles
-    double *xws;                 // per-CTA solution vectors [5][npad]
-    long long xws_stride;
-};
-
-struct PanelSmem {
-    double rd[2][8];    // 1/d of the diagonal block, by panel parity
-    double minv[2][64]; // inverse of the diagonal block's unit factor, row major, by panel parity
-    double W[64];       // [v][a]: weight of right-hand-side row a in the right-hand side of vector v
-    double nodew[16];   // [v][2]: weight of the observed node's unit vectors
-    double nodeL[16];   // [2][8]: D^-1 L11^-1 e_(observed dof) inside the last panel
-    double G[8];        // q_a^T K^-1 f
-    double lf_last[8];  // D^-1 z_f of the last panel
-    double obs[32];
-    double red[2 * 5 * kPanelNW];
-    unsigned long long bar[kPanelStagesMax];
-    unsigned long long rbar[kPanelRecDepth];
-    uint4 utab[kPanelUpdW][32];  // per update warp: shared-memory byte offsets (A, B, C) of its blocks in this panel
-    int colslot[2][kPanelNBMax + 2];
-    int flag;
-};
-
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-// One 8x8x8 block product C += A * B^T on fragments (a = A[g][2t..2t+1], b = B[g][2t..2t+1], c = C[g][2t..2t+1]).
-// DMMA: two tensor-core MMAs.  The alternative distributes the operands by shuffles and runs 16 DFMAs
-// per lane -- the same arithmetic on the FP64 pipe, kept for the ncu comparison the design notes quote.
-template <bool DMMA>
-__device__ __forceinline__ void block_mma(double2 &c, const double2 a, const double2 b, int lane) {
-    if (DMMA) {
-        dmma884(c.x, c.y, a.x, b.x);
-        dmma884(c.x, c.y, a.y, b.y);
-    } else {
-        const int g4 = lane & ~3, t = lane & 3;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double ax = __shfl_sync(kFull, a.x, g4 + k), ay = __shfl_sync(kFull, a.y, g4 + k);
-            const int r0 = 8 * t + k;  // lane holding B[2t][2k..2k+1], the next row is 4 lanes up
-            const double b0x = __shfl_sync(kFull, b.x, r0), b0y = __shfl_sync(kFull, b.y, r0);
-            const double b1x = __shfl_sync(kFull, b.x, r0 + 4), b1y = __shfl_sync(kFull, b.y, r0 + 4);
-            c.x = fma(ax, b0x, c.x);
-            c.x = fma(ay, b0y, c.x);
-            c.y = fma(ax, b1x, c.y);
-            c.y = fma(ay, b1y, c.y);
-        }
-    }
-}
-
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
-#ifdef VBFEM_TIMELINE
-#define PTL_DECL long long ptl[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ptl_t = clock64()
-#define PTL(i)                          \
-    do {                                \
-        const long long now_ = clock64(); \
-        ptl[i] += now_ - ptl_t;         \
-        ptl_t = now_;                   \
-    } while (0)
-#define PTL_FLUSH                                                                                  \
-    do {                                                                                           \
-        if (A.timeline && lane == 0 && (warp < 2 || warp >= 6))                                    \
-            for (int i_ = 0; i_ < 16; ++i_)                                                        \
-                A.timeline[(blockIdx.x * 4 + (warp < 2 ? warp : warp - 4)) * 16 + i_] = ptl[i_];   \
-    } while (0)
-#else
-#define PTL_DECL ((void)0)
-#define PTL(i) ((void)0)
-#define PTL_FLUSH ((void)0)
-#endif
+constexpr int kPanel2Slots = 15;  // register slots per update warp (6 x 15 = 90 ring slots for NB = 11)
 
 // MODE 0: y, h   MODE 1: y, h, gx = J^T (gy, gh)   MODE 2: y, h, J = d(y, h)/dx
 template <int MODE, bool DMMA>
-__global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_constant__ DevModel M,
+__global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_constant__ DevModel M,
                                                                 const __grid_constant__ PanelModel Q,
                                                                 const __grid_constant__ Args A) {
     extern __shared__ __align__(16) unsigned char smraw[];
     PanelSmem &S = *reinterpret_cast<PanelSmem *>(smraw);
-    double *win = reinterpret_cast<double *>(smraw + Q.o_win);  // window blocks, then (contiguous) the rhs ring
-    double *rhs = reinterpret_cast<double *>(smraw + Q.o_rhs);  // NB+2 right-hand-side blocks
+    double *wdiag = reinterpret_cast<double *>(smraw + Q.o_wdiag);  // ring of NB+2 diagonal blocks (block (c, c): slot c mod (NB+2))
+    double *fresh = reinterpret_cast<double *>(smraw + Q.o_fresh);  // the entering block row by diagonal d = 0..NB, then its rhs block
+    double *vst = reinterpret_cast<double *>(smraw + Q.o_vst);      // V blocks of the current panel (block row p+J at J), C layout
     double *lst = reinterpret_cast<double *>(smraw + Q.o_lst);  // two staging panels (transposed, scaled)
     double *ke = reinterpret_cast<double *>(smraw + Q.o_ke);    // R element matrices (36 each), then 0.0, 1.0
     double *lneg = reinterpret_cast<double *>(smraw + Q.o_lneg);  // -L blocks of the current panel, then a dummy block
@@ -194,7 +33,6 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
     const int g = lane >> 2, t = lane & 3;
     const int NB = Q.NB, NQ = Q.NQ, NB1 = NB + 1, NB2 = NB + 2, LPB = (NB + 2) * 64;  // LPB: doubles per stored panel
     constexpr int NV = (MODE == 2) ? 5 : 2;
-    auto dbase = [&](int d) { return d * NB2 - (d * (d - 1)) / 2; };  // first slot of window diagonal d (ring of NB+2-d)
     auto wrap = [](int v, int m) { return v >= m ? v - m : v; };
     auto ldv = [&](unsigned off) { return reinterpret_cast<const double2 *>(smraw + off)[lane]; };
     double *lws = Q.lws + (size_t)blockIdx.x * Q.lws_stride;
@@ -232,21 +70,24 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
         };
         PTL_DECL;
 
-        // ---------------- reset: window and rhs ring to zero, ring constants, slot tables
+        // ---------------- reset: diagonal ring and register slots to zero, ring constants, slot tables
+        double2 C[kPanel2Slots];  // this warp's window / right-hand-side ring slots (update warps)
+#pragma unroll
+        for (int k = 0; k < kPanel2Slots; ++k) C[k] = make_double2(0.0, 0.0);
         {
-            double2 *w2 = reinterpret_cast<double2 *>(win);
-            const int nz = (dbase(NB1) + NB2) * 32;  // window blocks + rhs ring, 32 double2 per block
-            for (int i = tid; i < nz; i += kPanelNT) w2[i] = make_double2(0.0, 0.0);
+            double2 *w2 = reinterpret_cast<double2 *>(wdiag);
+            for (int i = tid; i < NB2 * 32; i += kPanelNT) w2[i] = make_double2(0.0, 0.0);
             if (tid == 0) {
                 ke[Q.R * 36] = 0.0;
                 ke[Q.R * 36 + 1] = 1.0;
                 S.flag = 0;
             }
             if (tid <= NB2) S.colslot[0][tid] = 0;
+            if (tid < 32) reinterpret_cast<double2 *>(lneg + (NB + 2) * 64)[tid] = make_double2(0.0, 0.0);  // the zero block
         }
         __syncthreads();
 
-        double gacc = 0.0;  // warp 0: partial sum of G[g] over this lane's columns
+        double gacc = 0.0;  // update warps: partial sum of G[g] over the columns whose rhs block this warp solved
         // (a) Per-element Q4 Gauss-point kernels of this sample, all warps, thread = element: shape functions,
         // material subroutine at the zero predictor, kt += dvol B^T Ct B over the 2x2 rule
         // (src/mat_subroutine_tf.py:23-110).  The 36 lower-triangle entries go to the CTA's scratch slab in
@@ -334,9 +175,8 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             }
         };
 
-        // ---------------- the first NB+1 block rows fill the window (all warps, records and element matrices
-        //                  read from global; block (q, q-d) in slot q-d).  Meanwhile the records and element
-        //                  matrices of the next rows are on their way into shared memory.
+        // ---------------- the first NB+1 block rows enter one by one: all warps gather row q into the staging area
+        //                  (its diagonal block straight into the diagonal ring), the slot owners pick their blocks up
         const int nrec = (NQ > NB1) ? NQ - NB1 : 0;  // rows that enter during the panel loop
         auto fetch_row = [&](int q, int sl) {  // one thread: row record + the element matrices the row is first to need
             const int e0 = Q.eneed[q - 1], e1 = Q.eneed[q];
@@ -352,55 +192,110 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             }
         }
         __syncthreads();
+        // ring length of diagonal d (d = NB+1: the right-hand-side ring)
+        auto ring_len = [&](int d) { return d <= NB ? NB2 - d : NB2; };
         for (int q = 0; q <= NB && q < NQ; ++q) {
+            {
+                double2 *f2 = reinterpret_cast<double2 *>(fresh);
+                for (int i = tid; i < NB2 * 32; i += kPanelNT) f2[i] = make_double2(0.0, 0.0);
+            }
+            __syncthreads();
             const unsigned char *rc = Q.rec + (size_t)q * Q.rec_stride;
             const int4 hd = *reinterpret_cast<const int4 *>(rc);  // new elements, entries, first new element
-            if (tid < 32) reinterpret_cast<double2 *>(rhs + q * 64)[tid] = reinterpret_cast<const double2 *>(rc + 16)[tid];
+            if (tid < 32) reinterpret_cast<double2 *>(fresh + NB1 * 64)[tid] = reinterpret_cast<const double2 *>(rc + 16)[tid];
             const ushort4 *src = reinterpret_cast<const ushort4 *>(rc + Q.rec_o_src);
             const unsigned short *dstp = reinterpret_cast<const unsigned short *>(rc + Q.rec_o_dst);
             for (int i = tid; i < hd.y; i += kPanelNT) {
                 const int dst = dstp[i];
                 const ushort4 sr = src[i];
                 const int d = dst >> 6;
-                win[(dbase(d) + q - d) * 64 + (dst & 63)] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+                double *blk = d ? fresh + d * 64 : wdiag + q * 64;  // q <= NB: slot q of the diagonal ring
+                blk[dst & 63] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
             }
+            __syncthreads();
+            if (warp < kPanelUpdW) {
+#pragma unroll
+                for (int k = 0; k < kPanel2Slots; ++k) {
+                    const int d = Q.slot_d[warp][k], r = Q.slot_r[warp][k];
+                    if (d == 0) continue;
+                    const int len = ring_len(d);
+                    const bool mine = (d <= NB) ? (d <= q && r == (q - d) % len) : (r == q % len);
+                    if (mine) C[k] = reinterpret_cast<const double2 *>(fresh + (d <= NB ? d : NB1) * 64)[lane];
+                }
+            }
+            __syncthreads();
         }
         fence_async_smem();
         __syncthreads();
         if (tid == 7 * 32)  // ring slots of elements the first rows no longer need may now be overwritten
             for (int j = 0; j < kPanelRecDepth && j < nrec; ++j) fetch_row(NB1 + j, (int)((rec_base + j) % kPanelRecDepth));
-        if (warp == 6) diag_factor(win, lst, S.rd[0], S.minv[0]);  // block (0, 0): diagonal 0, slot 0
+        if (warp == 6) diag_factor(wdiag, lst, S.rd[0], S.minv[0]);  // block (0, 0): slot 0 of the diagonal ring
         __syncthreads();
         PTL(0);
 
-        // ---------------- panels
-        int rslot = 0;  // p mod (NB+2): slot of panel p in the rhs ring
-        for (int p = 0; p < NQ; ++p) {
-            const int par = p & 1;
-            const int *cs = S.colslot[par];
-            double *stg = lst + par * LPB;  // staging panel: [0] inverse unit factor^T, [1..NB] L^T blocks, [NB+1] rhs
-            const double2 r2 = reinterpret_cast<const double2 *>(S.rd[par])[t];
-            // ---- phase B: V = X L11^-T for the blocks below the diagonal block (in place) and the
-            //      right-hand-side block; the scaled copy goes to the staging panel
-            if (warp < kPanelUpdW) {
+        // ---------------- panels.  The three warp roles run their own copy of the panel loop (the register slots
+        //                  of the update warps then never overlap the 36-entry working set of the look-ahead
+        //                  warp's factorisation) and meet at two block barriers per panel.
+        auto bsync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        if (warp < kPanelUpdW) {
+            const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
+            int rslot = 0;  // p mod (NB+2): slot of panel p in the rhs ring and in the diagonal ring
+            // per slot, in one register: J = (r - p) mod len (bits 0..7), len (8..15), d (16..23); J counts down
+            int meta[kPanel2Slots];
+#pragma unroll
+            for (int k = 0; k < kPanel2Slots; ++k) {
+                const int d = Q.slot_d[warp][k], r = Q.slot_r[warp][k];
+                meta[k] = d ? (r | (ring_len(d) << 8) | (d << 16)) : 0;
+            }
+            for (int p = 0; p < NQ; ++p) {
+                const int par = p & 1;
+                double *stg = lst + par * LPB;  // staging panel: [0] inverse unit factor^T, [1..NB] L^T blocks, [NB+1] rhs
+                const double2 r2 = reinterpret_cast<const double2 *>(S.rd[par])[t];
                 const double2 mi = reinterpret_cast<const double2 *>(S.minv[par])[lane];  // Minv[g][2t..2t+1]
-                const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
-                for (int b = warp; b <= NB; b += kPanelUpdW) {  // b = 0: right-hand sides, else block row p+b
-                    double2 *X = reinterpret_cast<double2 *>(b ? win + (dbase(b) + cs[b]) * 64 : rhs + rslot * 64);
-                    const double2 xv = X[lane];
+                // ---- phase B: every slot learns its role in this panel, J = (r - p) mod len.  J = len-2: the block
+                //      assembled during the previous panel moves in.  J = 0: the block is in the panel column:
+                //      V = X L11^-T goes to shared memory for everybody's B fragments, -V D^-1 for the A fragments,
+                //      the scaled transpose to the staging panel.
+                // pass 1 (straight-line, registers only): roles, the entering blocks, the shared-memory offsets of the
+                // update's fragments (a slot that takes no update this panel multiplies by the zero block behind lneg)
+                unsigned offs[kPanel2Slots];  // (A offset) | (B offset << 16), in units of 16 bytes from lneg / vst
+                unsigned solve_mask = 0;
+#pragma unroll
+                for (int k = 0; k < kPanel2Slots; ++k) {
+                    const int J = meta[k] & 255, len = (meta[k] >> 8) & 255, d = meta[k] >> 16;
+                    const bool used = d != 0;
+                    if (used && J == len - 2 && p > 0)
+                        C[k] = reinterpret_cast<const double2 *>(fresh + (d <= NB ? d : NB1) * 64)[lane];
+                    if (used && J == 0) solve_mask |= 1u << k;
+                    const bool upd = used && J >= 1 && J <= len - 2;
+                    const int I = upd ? ((d <= NB) ? J + d : NB1) : NB + 2;  // NB+2: the zero block
+                    offs[k] = (unsigned)(I * 32) | ((unsigned)((upd ? J : 1) * 32) << 16);
+                    if (used) meta[k] += J ? -1 : len - 1;  // the slot's J in the next panel
+                }
+                // pass 2: the (two or three) slots of this warp that sit in the panel column -- one copy of the solve
+                while (solve_mask) {
+                    const int k = __ffs(solve_mask) - 1;
+                    solve_mask &= solve_mask - 1;
+                    double2 xv = make_double2(0.0, 0.0);
+                    int d = 0;
+#pragma unroll
+                    for (int kk = 0; kk < kPanel2Slots; ++kk)
+                        if (kk == k) {
+                            xv = C[kk];
+                            d = meta[kk] >> 16;
+                        }
+                    const int I = (d <= NB) ? d : NB1;  // block row p+d of the window, or the right-hand sides
                     double2 v = make_double2(0.0, 0.0);
                     block_mma<DMMA>(v, xv, mi, lane);
-                    X[lane] = v;
                     const double2 l = make_double2(v.x * r2.x, v.y * r2.y);
-                    reinterpret_cast<double2 *>(lneg + (b ? b : NB + 1) * 64)[lane] = make_double2(-l.x, -l.y);
+                    reinterpret_cast<double2 *>(lneg + I * 64)[lane] = make_double2(-l.x, -l.y);
+                    if (d <= NB) reinterpret_cast<double2 *>(vst + I * 64)[lane] = v;
                     if (MODE > 0) {
-                        // the stored panel holds L^T blocks: I * L^T on the tensor core leaves the transposed block in
-                        // the (lane-contiguous) C fragment layout -- no bank-conflicted scatter
                         double2 lt = make_double2(0.0, 0.0);
                         block_mma<DMMA>(lt, idf, l, lane);
-                        reinterpret_cast<double2 *>(stg + (b ? b : NB + 1) * 64)[lane] = lt;
+                        reinterpret_cast<double2 *>(stg + I * 64)[lane] = lt;
                     }
-                    if (b == 0) {  // warp 0: strain rows against the load row, G[g] += sum_c V[g][c] L[0][c]
+                    if (d > NB) {  // strain rows against the load row, G[g] += sum_c V[g][c] L[0][c]
                         const double lfx = __shfl_sync(kFull, l.x, t), lfy = __shfl_sync(kFull, l.y, t);
                         gacc = fma(v.x, lfx, fma(v.y, lfy, gacc));
                         if (p == NQ - 1 && g == 0) {
@@ -410,74 +305,48 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                     }
                 }
                 if (MODE > 0) fence_async_smem();
-            } else if (warp == 7 && lane <= NB2) {  // slot tables of panel p+1: (p+1) mod (NB+2-d)
-                const int v = cs[lane] + 1;
-                S.colslot[par ^ 1][lane] = (lane <= NB && v < NB2 - lane) ? v : 0;
-            }
-            PTL(1);
-            __syncthreads();
-            PTL(2);
-
-            // ---- phase C
-            if (warp < kPanelUpdW) {
-                // trailing update C(I,J) -= L_I V_J^T.  Lane i works out the shared-memory offsets of this warp's
-                // i-th block into a small table (one broadcast load per block in the loop).  One block per step, two
-                // steps per trip on alternating register sets: the next block's fragments are fetched before the
-                // current block's two (independent) MMAs are issued, and no register is ever copied.
-                const int k0 = Q.kstart[warp], cnt = Q.kstart[warp + 1] - k0;
-                if (lane < cnt) {
-                    const int ub = Q.ub[k0 + lane], I = ub >> 8, J = ub & 255;
-                    uint4 o;
-                    o.x = Q.o_lneg + I * 512;
-                    o.y = Q.o_win + (dbase(J) + cs[J]) * 512;
-                    if (I <= NB) {
-                        const int d = I - J;
-                        o.z = Q.o_win + (dbase(d) + wrap(cs[d] + J, NB2 - d)) * 512;
-                    } else {
-                        o.z = Q.o_rhs + wrap(rslot + J, NB2) * 512;
+                PTL(1);
+                bsync();
+                PTL(2);
+                // ---- phase C: trailing update C(I,J) -= L_I V_J^T on the register slots: two fragment loads and two
+                //      MMAs per slot, no branch -- the loads of the next slots run ahead of the MMAs
+                {
+                    const double2 *la = reinterpret_cast<const double2 *>(lneg) + lane;
+                    const double2 *vb = reinterpret_cast<const double2 *>(vst) + lane;
+#pragma unroll
+                    for (int k = 0; k < kPanel2Slots; ++k) {
+                        const double2 a = la[offs[k] & 0xffffu];
+                        const double2 b = vb[offs[k] >> 16];
+                        if (DMMA) {
+                            dmma884(C[k].x, C[k].y, a.x, b.x);
+                            dmma884(C[k].x, C[k].y, a.y, b.y);
+                        } else {
+                            block_mma<false>(C[k], a, b, lane);
+                        }
                     }
-                    o.w = 0;
-                    S.utab[warp][lane] = o;
                 }
-                __syncwarp();
-                const uint4 *tab = S.utab[warp];
-                const unsigned lo = 16u * lane;
-#define UPD_LOAD(X, P, k)  /* set X <- block k; its A fragment is taken from set P when the block row is the same */ \
-    do {                                                                 \
-        const uint4 t0_ = tab[k];                                        \
-        X##c = t0_.z + lo;                                               \
-        X##o = t0_.x;                                                    \
-        X##a = P##a;                                                     \
-        if (X##o != P##o) X##a = *reinterpret_cast<const double2 *>(smraw + t0_.x + lo); \
-        X##b = *reinterpret_cast<const double2 *>(smraw + t0_.y + lo);   \
-        X##v = *reinterpret_cast<const double2 *>(smraw + X##c);         \
-    } while (0)
-#define UPD_MMA_STORE(X)                                               \
-    do {                                                               \
-        if (DMMA) {                                                    \
-            double2 e_ = make_double2(0.0, 0.0);                       \
-            dmma884(X##v.x, X##v.y, X##a.x, X##b.x);                   \
-            dmma884(e_.x, e_.y, X##a.y, X##b.y);                       \
-            X##v.x += e_.x;                                            \
-            X##v.y += e_.y;                                            \
-        } else {                                                       \
-            block_mma<false>(X##v, X##a, X##b, lane);                  \
-        }                                                              \
-        *reinterpret_cast<double2 *>(smraw + X##c) = X##v;             \
-    } while (0)
-                unsigned Xc, Yc, Xo, Yo = 0xffffffffu;
-                double2 Xa, Xb, Xv, Ya = make_double2(0.0, 0.0), Yb, Yv;
-                if (cnt > 0) UPD_LOAD(X, Y, 0);
-                for (int i = 0; i < cnt; i += 2) {
-                    if (i + 1 < cnt) UPD_LOAD(Y, X, i + 1);
-                    UPD_MMA_STORE(X);
-                    if (i + 1 >= cnt) break;
-                    if (i + 2 < cnt) UPD_LOAD(X, Y, i + 2);
-                    UPD_MMA_STORE(Y);
+                // the diagonal blocks (J, J), J = 2..NB, stay in the shared-memory ring (block (1, 1) belongs to
+                // the look-ahead warp)
+                for (int J = 2 + warp; J <= NB; J += kPanelUpdW) {
+                    double2 *D = reinterpret_cast<double2 *>(wdiag + wrap(rslot + J, NB2) * 64);
+                    double2 c = D[lane];
+                    block_mma<DMMA>(c, reinterpret_cast<const double2 *>(lneg + J * 64)[lane],
+                                    reinterpret_cast<const double2 *>(vst + J * 64)[lane], lane);
+                    D[lane] = c;
                 }
-#undef UPD_LOAD
-#undef UPD_MMA_STORE
-            } else if (warp == 6) {
+                PTL(3);
+                bsync();
+                PTL(4);
+                rslot = (rslot + 1 == NB2) ? 0 : rslot + 1;
+            }
+        } else if (warp == 6) {
+            int rslot = 0;
+            for (int p = 0; p < NQ; ++p) {
+                const int par = p & 1;
+                double *stg = lst + par * LPB;
+                PTL(1);
+                bsync();
+                PTL(2);
                 // the finished panel leaves for HBM; then block (p+1, p+1) gets its update ahead of the others and
                 // is factored at once, so that the next panel's solve can start right after the barrier
                 if (MODE > 0 && lane == 0) {
@@ -486,60 +355,85 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
                 }
                 if (p + 1 < NQ) {
                     __syncwarp();
-                    const double2 v1 = reinterpret_cast<const double2 *>(win + (dbase(1) + cs[1]) * 64)[lane];
-                    double *Dn = win + (dbase(0) + wrap(cs[0] + 1, NB2)) * 64;
+                    double *Dn = wdiag + wrap(rslot + 1, NB2) * 64;
                     double2 c = reinterpret_cast<double2 *>(Dn)[lane];
-                    block_mma<DMMA>(c, reinterpret_cast<const double2 *>(lneg + 64)[lane], v1, lane);
+                    block_mma<DMMA>(c, reinterpret_cast<const double2 *>(lneg + 64)[lane],
+                                    reinterpret_cast<const double2 *>(vst + 64)[lane], lane);
                     reinterpret_cast<double2 *>(Dn)[lane] = c;
                     __syncwarp();
                     diag_factor(Dn, lst + (par ^ 1) * LPB, S.rd[par ^ 1], S.minv[par ^ 1]);
                 }
-            } else {
-                // block row q = p+NB+1 enters the window through the spare slots (block (q, q-d): slot of
-                // relative column NB+1-d): clear, right-hand-side block, element matrices, gather -- all from
-                // the row's record, which a bulk copy brought into shared memory several panels ago
+                PTL(3);
+                bsync();
+                PTL(4);
+                rslot = (rslot + 1 == NB2) ? 0 : rslot + 1;
+            }
+        } else {
+            int rslot = 0;
+            for (int p = 0; p < NQ; ++p) {
+                const int par = p & 1;
+                const int *cs = S.colslot[par];
+                if (lane <= NB2) {  // slot tables of panel p+1: (p+1) mod (NB+2-d)
+                    const int v = cs[lane] + 1;
+                    S.colslot[par ^ 1][lane] = (lane <= NB && v < NB2 - lane) ? v : 0;
+                }
+                PTL(1);
+                bsync();
+                PTL(2);
+                // block row q = p+NB+1 is assembled for the slots that fall free: diagonal block into the spare slot of
+                // the diagonal ring, the others and the right-hand-side block into the staging area -- all from the
+                // row's record, which a bulk copy brought into shared memory several panels ago
                 const int q = p + NB1;
                 const double2 z2 = make_double2(0.0, 0.0);
-                for (int d = 0; d <= NB; ++d)
-                    reinterpret_cast<double2 *>(win + (dbase(d) + wrap(cs[d] + NB1 - d, NB2 - d)) * 64)[lane] = z2;
-                double2 *rdst = reinterpret_cast<double2 *>(rhs + wrap(rslot + NB1, NB2) * 64);
+                double *Dq = wdiag + wrap(rslot + NB1, NB2) * 64;
+                reinterpret_cast<double2 *>(Dq)[lane] = z2;
+                for (int d = 1; d <= NB1; ++d) reinterpret_cast<double2 *>(fresh + d * 64)[lane] = z2;
                 if (q < NQ) {
                     const unsigned use = rec_base + (unsigned)p;
                     const int sl = (int)(use % kPanelRecDepth);
                     const unsigned char *rc = recs + sl * Q.rec_stride;
                     mbar_wait(&S.rbar[sl], (use / kPanelRecDepth) & 1u);
                     const int4 hd = *reinterpret_cast<const int4 *>(rc);
-                    rdst[lane] = reinterpret_cast<const double2 *>(rc + 16)[lane];
+                    __syncwarp();
+                    reinterpret_cast<double2 *>(fresh + NB1 * 64)[lane] = reinterpret_cast<const double2 *>(rc + 16)[lane];
                     const ushort4 *src = reinterpret_cast<const ushort4 *>(rc + Q.rec_o_src);
                     const unsigned short *dstp = reinterpret_cast<const unsigned short *>(rc + Q.rec_o_dst);
                     for (int i = lane; i < hd.y; i += 32) {
                         const int dst = dstp[i];
                         const ushort4 sr = src[i];
                         const int d = dst >> 6;
-                        win[(dbase(d) + wrap(cs[d] + NB1 - d, NB2 - d)) * 64 + (dst & 63)] =
-                            ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
+                        double *blk = d ? fresh + d * 64 : Dq;
+                        blk[dst & 63] = ((ke[sr.x] + ke[sr.y]) + ke[sr.z]) + ke[sr.w];
                     }
                     __syncwarp();
                     if (lane == 0 && p + kPanelRecDepth < nrec) fetch_row(q + kPanelRecDepth, sl);  // this slot's next tenant
-                } else {
-                    rdst[lane] = z2;
                 }
+                PTL(3);
+                bsync();
+                PTL(4);
+                rslot = (rslot + 1 == NB2) ? 0 : rslot + 1;
             }
-            PTL(3);
-            __syncthreads();
-            PTL(4);
-            rslot = (rslot + 1 == NB2) ? 0 : rslot + 1;
         }
+        __syncthreads();
 
+        // the partial sums of G of the six update warps
+        if (warp < kPanelUpdW) {
+            gacc += __shfl_xor_sync(kFull, gacc, 1);
+            gacc += __shfl_xor_sync(kFull, gacc, 2);
+            if (t == 0) S.red[warp * 8 + g] = gacc;
+        }
+        __syncthreads();
         // ---------------- observations: y from the last diagonal block, strains from the accumulated
         //                  products, h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
         const double *stgl = lst + ((NQ - 1) & 1) * LPB;  // last panel: [c][k] = Minv[k][c]
         const double *rdl = S.rd[(NQ - 1) & 1];
         if (MODE > 0 && tid == 6 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (warp == 0) {
-            gacc += __shfl_xor_sync(kFull, gacc, 1);
-            gacc += __shfl_xor_sync(kFull, gacc, 2);
-            if (t == 0) S.G[g] = gacc;
+            if (lane < 8) {
+                double gs = 0.0;
+                for (int w = 0; w < kPanelUpdW; ++w) gs += S.red[w * 8 + lane];
+                S.G[lane] = gs;
+            }
             // D^-1 L11^-1 e_j for the observed node's dofs j (their unit vectors start in the last panel)
             if (lane < 16) {
                 const int k = lane >> 3, c = lane & 7, j = Q.obs_loc[k];
@@ -617,7 +511,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel_kernel(const __grid_con
             // ---------------- reverse pass: x_p = Minv_p^T (W Lrhs_p - sum_d x_(p+d) L_(p+d,p)), panels descending.
             //   Warp 0 finishes panel p (its products with x_(p+2..) were formed one step earlier), warps 1..7
             //   form the products of panel p-1 with the blocks that are already final: one barrier per panel.
-            double *stage0 = win;                 // bulk-load ring (window + rhs ring are free now)
+            double *stage0 = reinterpret_cast<double *>(smraw + Q.o_big);  // bulk-load ring over the forward pass's (now idle) areas
             double *xr = ke;                      // NB+1 solution blocks [v][k]
             double *part = ke + NB1 * 64;         // [2][8] partial products, by panel parity
             const int NS = Q.stages;
