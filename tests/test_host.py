@@ -362,3 +362,17 @@ def test_generate_data_fem_is_seed_compatible(pkg, monkeypatch):
     assert sorted(back) == sorted(["y_data", "y_scaled_data", "z_data", "log_z_data", "z_scaled_data", "y_mean",
                                    "y_std", "z_mean", "z_std", "e_data"])
     assert np.array_equal(back["y_data"], md.y_data) and np.array_equal(back["e_data"], md.e_data)
+
+
+def test_oversized_mesh_fails_cleanly(pkg):
+    """A mesh whose band rows do not fit 16 bits (n > 32767 free dofs) is refused with an error code and a message
+    (it used to double-free the half-built handle); garbage connectivity is refused too."""
+    nx, ny = 130, 130                                   # 2 * 130 * 131 = 34060 free dofs
+    md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(nx, ny))
+    with pytest.raises(pkg.VbfemError, match="too large"):
+        pkg.fem_solver.plan_layout(md, node_id=(nx + 1) * (ny + 1), ele_id=12)
+    md = pkg.PreProcessing.modeldata_initialization_topopt(pkg.cook_membrane_feap(4, 4))
+    md["dof_info"]["IEN"] = md["dof_info"]["IEN"].copy()
+    md["dof_info"]["IEN"][0, 0] = 999
+    with pytest.raises(pkg.VbfemError, match="out of range"):
+        pkg.fem_solver.plan_layout(md, node_id=25, ele_id=2)
