@@ -395,7 +395,7 @@ def run_cuda(args):
     B = 64
     yd = np.random.default_rng(2).standard_normal((10000, 2)) * np.array([0.53, 0.65]) + np.array([-4.24, 5.71])
 
-    def time_elbo(S, seed, graphed=True):
+    def time_elbo(S, seed, graphed=True, pipelined=True):
         e_data = torch.tensor(np.random.default_rng(seed).standard_normal((S, 2)), device=dev)
         loss_fn = pkg.elbo.Step1Loss(eng, e_data, 0.1, rank=rank, world=world)
         model = pkg.elbo.make_step1_model(device=dev)
@@ -421,13 +421,21 @@ def run_cuda(args):
             run(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(n):
-            last = run(3 + i)
+        if graphed and pipelined:
+            # every step: pinned batch -> H2D -> graph replay -> loss D2H into pinned memory; the host reads a step's
+            # loss a few steps later instead of stalling the launch of the next step on it
+            tickets = [step.step_async(yd[((3 + i) * B) % 9984:((3 + i) * B) % 9984 + B]) for i in range(n)]
+            last = step.loss_of(tickets[-1])
+        else:
+            for i in range(n):
+                last = run(3 + i)
         barrier()
         dt = time.perf_counter() - t0
         return n, dt, last, step
 
     elbo_steps, elbo_s, last_loss_g, gstep = time_elbo(128 * world, 5)
+    _, elbo_sync_s, _, gstep_sync = time_elbo(128 * world, 5, pipelined=False)
+    del gstep_sync
     _, elbo_eager_s, last_loss, _ = time_elbo(128 * world, 5, graphed=False)
     c3 = None
     if world == 1:  # config 3 (shapes of the shipped data file: S = 100)
@@ -463,11 +471,11 @@ def run_cuda(args):
     c4_info = dict(eng4.info)
 
     # ---------------- max over ranks
-    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms],
+    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms, elbo_sync_s],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms = t.tolist()
+    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms, elbo_sync_s = t.tolist()
 
     if rank == 0:
         import ctypes
@@ -548,6 +556,7 @@ def run_cuda(args):
                      "samples_per_step": B * S5, "samples_per_gpu": B * S5 // world, "scaling": "weak",
                      "fem_solves_per_s": B * S5 * elbo_rate, "last_loss": last_loss_g,
                      "cuda_graph": bool(gstep.graphed), "eager_steps_per_s": elbo_steps / elbo_eager_s,
+                     "host_synchronised_every_step_steps_per_s": elbo_steps / elbo_sync_s,
                      "eager_last_loss": last_loss, "timed_steps": elbo_steps,
                      "collective": ("one NCCL all-reduce of 3 + 4B doubles per step INSIDE the timed region "
                                     "(a node of the captured graph)") if world > 1 else "none (one GPU)",
@@ -556,8 +565,10 @@ def run_cuda(args):
                                   "note": "0.716 MFLOP per reparameterised sample (FEM forward + adjoint); the two "
                                           "1884-parameter MLPs and Adam are < 0.1 % of the flops"},
                      "cpu_baseline": cpu_elbo,
-                     "what": "pinned batch H2D -> NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd -> Adam "
-                             "-> loss D2H; one CUDA graph replay per step",
+                     "what": "every step: pinned batch H2D -> NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd "
+                             "-> Adam (one CUDA graph replay) -> loss D2H into pinned memory; the host launches up to four "
+                             "steps ahead and reads each loss afterwards (GraphedStep1.step_async); "
+                             "host_synchronised_every_step_steps_per_s = the same with float(loss) after every step",
                      "config3": c3},
             "config4": {"workload": "Cook 80x40 (n=6560, half bandwidth 85), batch 1024 per GPU, fused forward+adjoint "
                                     "(BASELINE configs[3]); x seed 4, cotangents seed 5",

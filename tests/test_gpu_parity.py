@@ -492,6 +492,17 @@ def test_graphed_elbo_step_equals_eager(pkg, engine):
         assert step.graphed == graph
         losses[graph] = np.array(seq)
     assert np.max(np.abs(losses[True] - losses[False])) < 1e-10 * np.max(np.abs(losses[False]))
+    # pipelined stepping (the host runs ahead of the GPU, losses are read afterwards): the same sequence
+    model = pkg.elbo.make_step1_model(device=dev, seed=5)
+    step = pkg.elbo.GraphedStep1(model, pkg.elbo.make_step1_optimizer_capturable(model),
+                                 pkg.elbo.Step1Loss(engine, e_data, 0.1), 16, dev)
+    tickets = [step.step_async(b, depth=3) for b in yd[:3]]
+    first = [step.loss_of(t) for t in tickets]
+    tickets = [step.step_async(b, depth=3) for b in yd[3:]]
+    seq = np.array(first + [step.loss_of(t) for t in tickets])
+    assert np.max(np.abs(seq - losses[True])) < 1e-10 * np.max(np.abs(losses[True]))
+    with pytest.raises(ValueError):
+        step.loss_of(0)        # its staging slot has been reused
 
 
 def test_elbo_step2_fused_vs_oracle(pkg, engine, torch_oracle):

@@ -176,7 +176,6 @@ class GraphedStep1:
         self._device = device
 
     def _body(self):
-        self.yb.copy_(self.pin, non_blocking=True)
         self.opt.zero_grad(set_to_none=True)
         mu, sig, ls = self.model(self.yb)
         loss = self.loss_fn(self.yb, mu, sig, ls)
@@ -189,6 +188,7 @@ class GraphedStep1:
         side = torch.cuda.Stream(device=self._device)
         side.wait_stream(torch.cuda.current_stream(self._device))
         with torch.cuda.stream(side):
+            self.yb.copy_(self.pin, non_blocking=True)
             for _ in range(self._warm):   # also sizes the library's scratch buffers before capture
                 self._body()
         torch.cuda.current_stream(self._device).wait_stream(side)
@@ -205,14 +205,55 @@ class GraphedStep1:
             torch.cuda.synchronize(self._device)
 
     def step(self, y_batch_host):
+        """One training step on the batch; returns the loss tensor (device): reading it is the only synchronisation."""
         self.pin.copy_(self.torch.as_tensor(y_batch_host, dtype=self.torch.float64))
         if self._use_graph and self.graph is None and not hasattr(self, "capture_error"):
             self._capture()
+        self.yb.copy_(self.pin, non_blocking=True)   # H2D on the launch stream, then the graph finds the batch on the device
         if self.graphed:
             self.graph.replay()
         else:
             self._body()
         return self.loss
+
+    # ---- pipelined stepping: the host does not wait for a step's loss before it launches the next one
+    def step_async(self, y_batch_host, depth=4):
+        """Like ``step`` but without a host synchronisation per step: the batch goes through a ring of ``depth``
+        pinned staging buffers (H2D on the launch stream right before the graph replay), the loss comes back through
+        a ring of pinned scalars (D2H right after the replay).  Returns a ticket for ``loss_of``; a staging slot is
+        reused only after the step that used it has finished on the GPU.  Every step still does its own H2D copy and
+        D2H read -- the host just runs ahead of the GPU by up to ``depth`` steps, like any training loop that does not
+        print the loss every step."""
+        torch = self.torch
+        if not hasattr(self, "_ring"):
+            self._ring = [{"pin": torch.empty_like(self.pin).pin_memory(),
+                           "loss": torch.zeros((), dtype=torch.float64).pin_memory(),
+                           "done": torch.cuda.Event()} for _ in range(depth)]
+            self._tick = 0
+        if self._use_graph and self.graph is None and not hasattr(self, "capture_error"):
+            self.pin.copy_(torch.as_tensor(y_batch_host, dtype=torch.float64))
+            self._capture()       # warm-up steps + capture on the first call (they train on this batch, like step())
+        slot = self._ring[self._tick % len(self._ring)]
+        if self._tick >= len(self._ring):
+            slot["done"].synchronize()   # the step that used this slot last has finished
+        slot["pin"].copy_(torch.as_tensor(y_batch_host, dtype=torch.float64))
+        self.yb.copy_(slot["pin"], non_blocking=True)
+        if self.graphed:
+            self.graph.replay()
+        else:
+            self._body()
+        slot["loss"].copy_(self.loss, non_blocking=True)
+        slot["done"].record()
+        self._tick += 1
+        return self._tick - 1
+
+    def loss_of(self, ticket):
+        """The loss of the step ``ticket`` (blocks until that step has finished)."""
+        if self._tick - ticket > len(self._ring):
+            raise ValueError("ticket too old: its staging slot has been reused")
+        slot = self._ring[ticket % len(self._ring)]
+        slot["done"].synchronize()
+        return float(slot["loss"])
 
 
 # ------------------------------------------------------------------------------------- step 2
