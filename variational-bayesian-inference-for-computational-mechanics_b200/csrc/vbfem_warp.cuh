@@ -323,9 +323,14 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 __stcs(pan + lane, reinterpret_cast<const double2 *>(stg)[lane]);
 #pragma unroll
                 for (int b = 0; b < NB1; ++b) {
-                    double2 lt = z2;
-                    block_mma<true>(lt, idf, Ln[b], lane);
-                    __stcs(pan + (b ? b : NB + 1) * 32 + lane, make_double2(-lt.x, -lt.y));
+                    // transpose in the fragment layout: lane (g, t) needs (L[2t][g], L[2t+1][g]), held by lanes
+                    // (2t, g >> 1) and (2t + 1, g >> 1) in component g & 1 -- four shuffles instead of two MMAs on
+                    // the shared FP64 / tensor pipe
+                    const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
+                    const double ax = __shfl_sync(kFull, Ln[b].x, s0), ay = __shfl_sync(kFull, Ln[b].y, s0);
+                    const double bx = __shfl_sync(kFull, Ln[b].x, s1), by = __shfl_sync(kFull, Ln[b].y, s1);
+                    const bool odd = g & 1;
+                    __stcs(pan + (b ? b : NB + 1) * 32 + lane, make_double2(-(odd ? ay : ax), -(odd ? by : bx)));
                 }
             }
             WTL(3);
