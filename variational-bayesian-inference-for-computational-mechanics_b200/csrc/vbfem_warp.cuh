@@ -30,7 +30,7 @@ namespace vbfem {
 
 constexpr int kWarpNB = 3;      // block half bandwidth of the register window (8x8 blocks)
 constexpr int kWarpBatch = 32;  // element matrices per just-in-time batch (lane = element); WarpModel::batch may be smaller
-constexpr int kWarpFixed = 1664 + (kWarpNB + 1) * 512;  // bytes per warp ahead of the element ring
+constexpr int kWarpFixed = 640 + (kWarpNB + 1) * 512;  // bytes per warp ahead of the element ring: Minv^T and 1/d of the last panel, flag, staging area
 
 struct WarpModel {
     int n, off, npad, NQ, R, nele;
@@ -58,63 +58,48 @@ struct WarpModel {
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// LDL^T of an 8x8 diagonal block and the inverse of its unit factor, every lane redundantly in registers
-// (see fem_panel_kernel's diag_factor): D in shared memory, row major, lower triangle.  Writes
-// stg[c][k] = Minv[k][c], mro[k][c] = Minv[k][c] and rdo[k] = 1 / d_k.
-__device__ __forceinline__ void warp_diag_load(const double *D, double (&a)[36]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; j += 2) {
-            const double2 v = reinterpret_cast<const double2 *>(D + i * 8)[j >> 1];
-            a[tri(i, j)] = v.x;
-            if (j + 1 <= i) a[tri(i, j + 1)] = v.y;
-        }
-}
-__device__ __forceinline__ void warp_diag_compute(double (&a)[36], double *stg, double *rdo, double *mro, int *flag,
-                                                  int lane) {
+// LDL^T of an 8x8 diagonal block and the inverse of its unit factor in the MMA fragment layout, without redundant
+// arithmetic (lane (g, t) holds D[g][2t], D[g][2t+1]; only the lower triangle of D is meaningful): right-looking LDL^T, column k broadcast by four shuffles per step (pivot, this
+// lane's row entry, the entries of this lane's two columns), the inverse of the unit factor built alongside by forward
+// substitution on the identity (row k of the inverse is final when step k starts).  80 FP64 instructions and ~100
+// shuffles (the first version factored the block redundantly in every lane: 190 FP64 instructions, 18 broadcast loads,
+// two warp barriers and a 36-entry working set in registers).  Returns Minv (C layout = the solve's B fragment), its transpose (the reverse
+// pass's B fragment), the reciprocal pivots of this lane's two columns.
+__device__ __forceinline__ void warp_diag_fragment(double2 D, double2 &Minv, double2 &MinvT, double2 &r2, int *flag,
+                                                   int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double2 M = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);
+    r2 = make_double2(0.0, 0.0);
     int bad = 0;
-    double rdv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const double d = a[tri(k, k)];
-        // positive, finite, not tiny: sign and exponent bits only (integer pipe; the FP64 pipe is the busy one)
-        bad |= (unsigned)(__double2hiint(d) - 0x00200000) >= 0x7fd00000u;
-        rdv[k] = fast_rcp3(d);
-        // the next pivot first, one level after the reciprocal: d' = a' - (a_(k+1,k))^2 / d with the square formed
-        // while the reciprocal is refined -- it heads the dependency chain of the whole block
-        if (k + 1 < 8) {
-            const double sq = a[tri(k + 1, k)] * a[tri(k + 1, k)];
-            a[tri(k + 1, k + 1)] = fma(-sq, rdv[k], a[tri(k + 1, k + 1)]);
+        const int kt = k >> 1;
+        const double src = (k & 1) ? D.y : D.x;  // column k lives in the lanes with t == k / 2
+        const double dk = __shfl_sync(kFull, src, 4 * k + kt);
+        const double cg = __shfl_sync(kFull, src, 4 * g + kt);
+        const double cj0 = __shfl_sync(kFull, src, 8 * t + kt);
+        const double cj1 = __shfl_sync(kFull, src, 8 * t + 4 + kt);
+        bad |= (unsigned)(__double2hiint(dk) - 0x00200000) >= 0x7fd00000u;
+        const double rk = fast_rcp3(dk);
+        const double lg = (g > k) ? cg * rk : 0.0;  // L[g][k]
+        if (2 * t > k) D.x = fma(-lg, cj0, D.x);
+        if (2 * t + 1 > k) D.y = fma(-lg, cj1, D.y);
+        if (t == kt) {
+            if (k & 1) r2.y = rk;
+            else r2.x = rk;
         }
-#pragma unroll
-        for (int j = k + 1; j < 8; ++j) {
-            const double ljk = a[tri(j, k)] * rdv[k];
-#pragma unroll
-            for (int i = j; i < 8; ++i)
-                if (!(i == k + 1 && j == k + 1)) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
-            a[tri(j, k)] = ljk;
+        if (k < 7) {
+            const double mkx = __shfl_sync(kFull, M.x, 4 * k + t), mky = __shfl_sync(kFull, M.y, 4 * k + t);
+            M.x = fma(-lg, mkx, M.x);
+            M.y = fma(-lg, mky, M.y);
         }
     }
     if (bad && lane == 0) *flag = 1;
-    // column j of the inverse of the unit factor, column oriented (dependency depth 7 instead of 28)
-    const int j = lane & 7;
-    double m[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k)
-#pragma unroll
-        for (int i = k + 1; i < 8; ++i) m[i] = fma(-a[tri(i, k)], m[k], m[i]);  // m[k] = 0 for k < j: rows above j stay 0
-    if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) reinterpret_cast<double2 *>(stg + j * 8)[i >> 1] = make_double2(m[i], m[i + 1]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mro[i * 8 + j] = m[i];
-    } else if (lane == 8) {
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) reinterpret_cast<double2 *>(rdo)[k >> 1] = make_double2(rdv[k], rdv[k + 1]);
-    }
+    Minv = M;
+    const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
+    const double ax = __shfl_sync(kFull, M.x, s0), ay = __shfl_sync(kFull, M.y, s0);
+    const double bx = __shfl_sync(kFull, M.x, s1), by = __shfl_sync(kFull, M.y, s1);
+    MinvT = make_double2((g & 1) ? ay : ax, (g & 1) ? by : bx);
 }
 
 // One just-in-time batch of element matrices (lane = element, first-use order) into the ring.  Kept out of line:
@@ -181,9 +166,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
     const unsigned long long *gtab = reinterpret_cast<const unsigned long long *>(smraw);
     const int2 *rowtab = reinterpret_cast<const int2 *>(smraw + (size_t)Q.nent * 8);
     unsigned char *wsm = smraw + Q.tab_bytes + (size_t)warp * Q.warp_smem;
-    double *dg = reinterpret_cast<double *>(wsm), *stg = dg + 64, *minv = dg + 128, *rd = dg + 192;
-    int *flagp = reinterpret_cast<int *>(wsm + 1600);
-    double *stage = reinterpret_cast<double *>(wsm + 1664);  // NB+1 blocks of the entering row, by block diagonal
+    double *stg = reinterpret_cast<double *>(wsm), *rd = stg + 64;  // the last panel's Minv^T and 1 / d (observations)
+    int *flagp = reinterpret_cast<int *>(wsm + 576);
+    double *stage = reinterpret_cast<double *>(wsm + 640);  // NB+1 blocks of the entering row, by block diagonal
     double *ke = reinterpret_cast<double *>(wsm + kWarpFixed);  // R element matrices (36 each), then 0.0, 1.0
     // after the forward pass the staging area holds the small vectors of the observation / reverse pass
     double *sW = stage, *nodew = stage + 64, *nodeL = stage + 80, *sG = stage + 96, *lf_last = stage + 104,
@@ -285,19 +270,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
         // ---------------- panels
         double gacc = 0.0;  // partial sum over this lane's columns of G[g] = q_g^T K^-1 f
         const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
-        {   // diagonal block of panel 0: LDL^T, inverse of the unit factor
-            reinterpret_cast<double2 *>(dg)[lane] = W[0][0];
-            __syncwarp();
-            double a[36];
-            warp_diag_load(dg, a);
-            warp_diag_compute(a, stg, rd, minv, flagp, lane);
-            __syncwarp();
-        }
+        double2 mi, mit, r2;  // of the current panel: Minv[g][2t..2t+1], its transpose, 1 / d of columns 2t, 2t+1
+        warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);  // diagonal block of panel 0
 #pragma unroll 1
         for (int p = 0; p < NQ; ++p) {
             WTL(1);
-            const double2 mi = reinterpret_cast<const double2 *>(minv)[lane];  // Minv[g][2t..2t+1]
-            const double2 r2 = reinterpret_cast<const double2 *>(rd)[t];
             // ---- solve: V = X L11^-T for the right-hand sides (b = 0) and the blocks below; Ln = -V D^-1
             double2 V[NB1], Ln[NB1];
 #pragma unroll
@@ -320,7 +297,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 // the scaled panel leaves for the slab: [0] Minv^T, [1..NB] L^T blocks, [NB+1] D^-1 z rows, transposed
                 // on the tensor core (I * L^T leaves the transposed block in the C-fragment layout)
                 double2 *pan = reinterpret_cast<double2 *>(lws + (size_t)p * LPB);
-                __stcs(pan + lane, reinterpret_cast<const double2 *>(stg)[lane]);
+                __stcs(pan + lane, mit);
 #pragma unroll
                 for (int b = 0; b < NB1; ++b) {
                     // transpose in the fragment layout: lane (g, t) needs (L[2t][g], L[2t+1][g]), held by lanes
@@ -356,13 +333,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
             //      one instruction stream, two independent dependency chains
             const int q = p + NB1;
             if (p + 1 < NQ) {
-                reinterpret_cast<double2 *>(dg)[lane] = W[0][0];
-                if (q < NQ) row_prepare(q);
-                __syncwarp();
-                double a[36];
-                warp_diag_load(dg, a);
-                if (q < NQ) row_gather(q);
-                warp_diag_compute(a, stg, rd, minv, flagp, lane);
+                if (q < NQ) {
+                    row_prepare(q);
+                    __syncwarp();
+                    row_gather(q);
+                }
+                warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);
                 __syncwarp();
             }
             WTL(2);
@@ -382,6 +358,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
         WTL(1);
         // ---------------- observations: y from the last diagonal block, strains from the accumulated products,
         //                  h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
+        __syncwarp();
+        reinterpret_cast<double2 *>(stg)[lane] = mit;  // the last panel's Minv^T [c][k] and 1 / d for the lanes below
+        if (g == 0) reinterpret_cast<double2 *>(rd)[t] = r2;
         __syncwarp();
         gacc += __shfl_xor_sync(kFull, gacc, 1);
         gacc += __shfl_xor_sync(kFull, gacc, 2);
