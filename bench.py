@@ -35,9 +35,9 @@ FLOP_PER_SOLVE = 1600 * 200 + 440 * (25 * 25 + 3 * 25) + 2 * 4 * 440 * 25   # = 
 BYTES_PER_SOLVE = 96                                                          # x, gy, gh in; y, h, gx out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch at batch 4096 from the committed
 # `ncu --set full` capture of the warp-per-sample kernel (profiles/r02_ncu_warp_adj_raw_selected.txt):
-# 366.5 MB read + 533.3 MB written -- the factor slab of the adjoint (141 KB per sample, written once, read once);
+# 371.7 MB read + 534.7 MB written -- the factor slab of the adjoint (141 KB per sample, written once, read once);
 # the forward-only launch moves the compulsory 48 B per sample.
-NCU_DRAM_BYTES_PER_LAUNCH = 366493184 + 533329152
+NCU_DRAM_BYTES_PER_LAUNCH = 371697152 + 534670336
 # config 4 (80x40): DRAM bytes per fused forward+adjoint SOLVE from the committed capture of the panel kernel
 NCU_C4_DRAM_BYTES_PER_SOLVE = int((1.871130e9 + 1.928987e9) / 296)   # 12.84 MB (read 6.32 + written 6.52)
 
