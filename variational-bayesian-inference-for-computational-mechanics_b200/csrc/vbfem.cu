@@ -201,6 +201,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 }  // namespace vbfem
 #include "vbfem_front_kernel.cuh"
 #include "vbfem_panel.cuh"
+#include "vbfem_panel2.cuh"
 #include "vbfem_warp.cuh"
 namespace vbfem {
 
@@ -1257,6 +1258,10 @@ struct PanelPlan {
     int obs_loc[2] = {-1, -1};
     int kstart[kPanelNW + 1] = {0};
     int o_win = 0, o_rhs = 0, o_lst = 0, o_ke = 0, o_lneg = 0, smem_bytes = 0, stages = 0;
+    // second generation (window in registers; laid out for NB = kPanel2NB)
+    bool v2 = false;
+    int o2_wdiag = 0, o2_fresh = 0, o2_vst = 0, o2_big = 0, o2_lneg = 0, o2_rec = 0, o2_lst = 0, o2_ke = 0, smem2_bytes = 0,
+        stages2 = 0;
     std::vector<int> gptr, eneed, eord, elm;
     std::vector<double> ecoord;
     std::vector<unsigned char> rec;  // row records (PanelModel::rec)
@@ -1482,6 +1487,29 @@ static PanelPlan plan_panel(const vbfem_mesh *m, const std::vector<int> &dof2ban
     P.stages = std::min(kPanelStagesMax, (nwin + NB + 2) * 512 / LPBb);
     if (P.stages < 2) return no("window too small for the reverse pass");
     P.ok = true;
+    {   // second generation: shared memory without the window; the diagonal ring, the entering-row staging area, the V
+        // blocks, -L and the record ring form one region that the reverse pass re-uses as its bulk-load ring
+        int o = (int)((sizeof(PanelSmem) + 15) & ~(size_t)15);
+        P.o2_big = o;
+        P.o2_wdiag = o;
+        o += (NB + 2) * 512;
+        P.o2_fresh = o;
+        o += (NB + 2) * 512;
+        P.o2_vst = o;
+        o += NB1 * 512;
+        P.o2_lneg = o;
+        o += (NB + 3) * 512;
+        P.o2_rec = o;
+        o += kPanelRecDepth * P.rec_stride;
+        const int big = o - P.o2_big;
+        P.o2_lst = o;
+        o += 2 * LPBb;
+        P.o2_ke = o;
+        o += (ke_bytes + 15) & ~15;
+        P.smem2_bytes = o;
+        P.stages2 = std::min(kPanelStagesMax, big / LPBb);
+        P.v2 = NB == kPanel2NB && P.stages2 >= 2 && P.NQ > NB1;
+    }
     return P;
 }
 
@@ -1940,6 +1968,22 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
             panel_fn ks[3] = {dfma ? fem_panel_kernel<0, false> : fem_panel_kernel<0, true>,
                               dfma ? fem_panel_kernel<1, false> : fem_panel_kernel<1, true>,
                               dfma ? fem_panel_kernel<2, false> : fem_panel_kernel<2, true>};
+            if (P.v2 && getenv("VBFEM_PANEL_V1") == nullptr) {  // second generation: window in registers
+                ks[0] = dfma ? fem_panel2_kernel<0, false> : fem_panel2_kernel<0, true>;
+                ks[1] = dfma ? fem_panel2_kernel<1, false> : fem_panel2_kernel<1, true>;
+                ks[2] = dfma ? fem_panel2_kernel<2, false> : fem_panel2_kernel<2, true>;
+                Q.o_wdiag = P.o2_wdiag;
+                Q.o_fresh = P.o2_fresh;
+                Q.o_vst = P.o2_vst;
+                Q.o_big = P.o2_big;
+                Q.o_lneg = P.o2_lneg;
+                Q.o_rec = P.o2_rec;
+                Q.o_lst = P.o2_lst;
+                Q.o_ke = P.o2_ke;
+                Q.smem_bytes = P.smem2_bytes;
+                Q.stages = P.stages2;
+                P.smem_bytes = P.smem2_bytes;
+            }
             int nbmin = 1 << 30;
             bool fits = true;
             for (int q = 0; q < 3 && fits; ++q) {

@@ -55,6 +55,9 @@ struct PanelModel {
     int stages;                // bulk-load ring of the reverse pass
     int o_lneg;                // NB+2 blocks: -L of the current panel, row major (block b: block row p+b; NB+1: rhs), then a dummy block
     int o_rec, rec_stride, rec_o_src, rec_o_dst;  // row-record ring in shared memory / record layout (bytes)
+    // second generation (vbfem_panel2.cuh): shared-memory offsets of the diagonal ring, the entering-row staging area,
+    // the V blocks, and of the region the reverse pass re-uses as its bulk-load ring
+    int o_wdiag, o_fresh, o_vst, o_big;
     int kstart[kPanelNW + 1];  // update blocks [kstart[w], kstart[w+1]) belong to warp w < kPanelUpdW
     unsigned short ub[kPanelNBMax * (kPanelNBMax + 1) / 2 + kPanelNBMax];  // (I << 8) | J
     // Row record of block row q (rec_stride bytes, what the row needs to enter the window): int32 header
