@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_co
                 constexpr int NA_ = decltype(na_)::value, NB_ = decltype(nb_)::value;  // live blocks of the two diagonals
                 constexpr int dA = decltype(da_)::value, dB = decltype(db_)::value;    // kPanel2NB + 1: the right-hand-side row
                 constexpr int NB = kPanel2NB, NB1 = NB + 1, NB2 = NB + 2;               // compile-time here: static block roles
-                const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
                 const double2 *fA = reinterpret_cast<const double2 *>(fresh + dA * 64) + lane;
                 const double2 *fB = reinterpret_cast<const double2 *>(fresh + dB * 64) + lane;
                 double2 CA[NA_], CB[NB_];
@@ -245,19 +244,39 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_co
                         CB[NB_ - 1] = *fB;
                     }
                     double2 vA = make_double2(0.0, 0.0), vB = vA;
-                    block_mma<DMMA>(vA, CA[0], mi, lane);
-                    block_mma<DMMA>(vB, CB[0], mi, lane);
+                    if (DMMA) {  // four independent MMAs, then two adds: no MMA waits for another one
+                        double2 wA = vA, wB = vB;
+                        dmma884(vA.x, vA.y, CA[0].x, mi.x);
+                        dmma884(vB.x, vB.y, CB[0].x, mi.x);
+                        dmma884(wA.x, wA.y, CA[0].y, mi.y);
+                        dmma884(wB.x, wB.y, CB[0].y, mi.y);
+                        vA = make_double2(vA.x + wA.x, vA.y + wA.y);
+                        vB = make_double2(vB.x + wB.x, vB.y + wB.y);
+                    } else {
+                        block_mma<false>(vA, CA[0], mi, lane);
+                        block_mma<false>(vB, CB[0], mi, lane);
+                    }
                     const double2 lA = make_double2(vA.x * r2.x, vA.y * r2.y), lB = make_double2(vB.x * r2.x, vB.y * r2.y);
                     reinterpret_cast<double2 *>(lneg + dA * 64)[lane] = make_double2(-lA.x, -lA.y);
                     reinterpret_cast<double2 *>(lneg + dB * 64)[lane] = make_double2(-lB.x, -lB.y);
                     if (dA <= NB) reinterpret_cast<double2 *>(vst + dA * 64)[lane] = vA;
                     reinterpret_cast<double2 *>(vst + dB * 64)[lane] = vB;
                     if (MODE > 0) {
-                        double2 ltA = make_double2(0.0, 0.0), ltB = ltA;
-                        block_mma<DMMA>(ltA, idf, lA, lane);
-                        block_mma<DMMA>(ltB, idf, lB, lane);
-                        reinterpret_cast<double2 *>(stg + dA * 64)[lane] = ltA;
-                        reinterpret_cast<double2 *>(stg + dB * 64)[lane] = ltB;
+                        // the stored panel holds L^T blocks: transposed in the fragment layout by four shuffles
+                        // (lane (g, t) needs L[2t][g], L[2t+1][g], held by lanes (2t, g >> 1), (2t+1, g >> 1) in
+                        // component g & 1)
+                        const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
+                        const bool odd = g & 1;
+                        {
+                            const double ax = __shfl_sync(kFull, lA.x, s0), ay = __shfl_sync(kFull, lA.y, s0);
+                            const double bx = __shfl_sync(kFull, lA.x, s1), by = __shfl_sync(kFull, lA.y, s1);
+                            reinterpret_cast<double2 *>(stg + dA * 64)[lane] = make_double2(odd ? ay : ax, odd ? by : bx);
+                        }
+                        {
+                            const double ax = __shfl_sync(kFull, lB.x, s0), ay = __shfl_sync(kFull, lB.y, s0);
+                            const double bx = __shfl_sync(kFull, lB.x, s1), by = __shfl_sync(kFull, lB.y, s1);
+                            reinterpret_cast<double2 *>(stg + dB * 64)[lane] = make_double2(odd ? ay : ax, odd ? by : bx);
+                        }
                         fence_async_smem();
                     }
                     if (dA > NB) {  // warp 0: strain rows against the load row, G[g] += sum_c V[g][c] L[0][c]
