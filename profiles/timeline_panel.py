@@ -31,8 +31,8 @@ roles = ["warp 0 (solve + update)", "warp 1 (solve + update)", "warp 6 (look-ahe
 npan = 820
 for w in range(4):
     print(f"--- {roles[w]}   (mean over {t.shape[0]} CTAs; per panel = / {npan})")
-    tot = t[:, w, :10].sum(axis=1).mean()
-    names_w = names if w == 3 else names[:10]
+    tot = t[:, w, :13].sum(axis=1).mean() if w == 2 else t[:, w, :10].sum(axis=1).mean()
+    names_w = names if w == 3 else (names[:10] + ["  look-ahead: bulk store + wait for the other staging buffer", "  look-ahead: update of the next diagonal block", "  look-ahead: LDL^T + inverse of the next diagonal block"] if w == 2 else names[:10])
     for i, nm in enumerate(names_w):
         v = t[:, w, i].mean()
         print(f"  {nm:48s} {v:12.0f} cycles  {100 * v / tot:5.1f} %   per panel {v / npan:8.1f}")

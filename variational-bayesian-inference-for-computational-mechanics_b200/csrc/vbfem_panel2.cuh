@@ -328,6 +328,13 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_co
                                         reinterpret_cast<const double2 *>(vst + J * 64)[lane], lane);
                         D[lane] = c;
                     }
+                    if (MODE > 0 && dA == 5 && lane == 0) {
+                        // the finished panel leaves for HBM.  The update warps reach the barrier long before the look-ahead
+                        // warp does: one of them waits here until the copy has read the staging buffer, so that the
+                        // look-ahead warp (which writes the next panel's Minv^T into the other buffer) never has to
+                        bulk_store(lws + (size_t)p * LPB, stg, LPB * 8);
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     PTL(3);
                     bsync();
                     PTL(4);
@@ -382,12 +389,8 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_co
                     PTL(1);
                     bsync();
                     PTL(2);
-                    // the finished panel leaves for HBM; then block (p+1, p+1) gets its update ahead of the others and
-                    // is factored at once, so that the next panel's solve can start right after the barrier
-                    if (MODE > 0 && lane == 0) {
-                        bulk_store(lws + (size_t)p * LPB, stg, LPB * 8);
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // panel p-1 has left the other buffer
-                    }
+                    // block (p+1, p+1) gets its update ahead of the others and is factored at once, so that the next panel's
+                    // solve can start right after the barrier.  This warp is the critical path of the panel: nothing else here.
                     if (p + 1 < NQ) {
                         __syncwarp();
                         double *Dn = wdiag + wrap(rslot + 1, NB2) * 64;
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_co
         //                  products, h = von Mises at the two observed Gauss points (src/fem_postprocess.py:172-185)
         const double *stgl = lst + ((NQ - 1) & 1) * LPB;  // last panel: [c][k] = Minv[k][c]
         const double *rdl = S.rd[(NQ - 1) & 1];
-        if (MODE > 0 && tid == 6 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (MODE > 0 && tid == 5 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (warp == 0) {
             gacc += __shfl_xor_sync(kFull, gacc, 1);
             gacc += __shfl_xor_sync(kFull, gacc, 2);

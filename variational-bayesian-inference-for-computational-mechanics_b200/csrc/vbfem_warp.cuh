@@ -58,50 +58,6 @@ struct WarpModel {
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// LDL^T of an 8x8 diagonal block and the inverse of its unit factor in the MMA fragment layout, without redundant
-// arithmetic (lane (g, t) holds D[g][2t], D[g][2t+1]; only the lower triangle of D is meaningful): right-looking LDL^T, column k broadcast by four shuffles per step (pivot, this
-// lane's row entry, the entries of this lane's two columns), the inverse of the unit factor built alongside by forward
-// substitution on the identity (row k of the inverse is final when step k starts).  80 FP64 instructions and ~100
-// shuffles (the first version factored the block redundantly in every lane: 190 FP64 instructions, 18 broadcast loads,
-// two warp barriers and a 36-entry working set in registers).  Returns Minv (C layout = the solve's B fragment), its transpose (the reverse
-// pass's B fragment), the reciprocal pivots of this lane's two columns.
-__device__ __forceinline__ void warp_diag_fragment(double2 D, double2 &Minv, double2 &MinvT, double2 &r2, int *flag,
-                                                   int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    double2 M = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);
-    r2 = make_double2(0.0, 0.0);
-    int bad = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int kt = k >> 1;
-        const double src = (k & 1) ? D.y : D.x;  // column k lives in the lanes with t == k / 2
-        const double dk = __shfl_sync(kFull, src, 4 * k + kt);
-        const double cg = __shfl_sync(kFull, src, 4 * g + kt);
-        const double cj0 = __shfl_sync(kFull, src, 8 * t + kt);
-        const double cj1 = __shfl_sync(kFull, src, 8 * t + 4 + kt);
-        bad |= (unsigned)(__double2hiint(dk) - 0x00200000) >= 0x7fd00000u;
-        const double rk = fast_rcp3(dk);
-        const double lg = (g > k) ? cg * rk : 0.0;  // L[g][k]
-        if (2 * t > k) D.x = fma(-lg, cj0, D.x);
-        if (2 * t + 1 > k) D.y = fma(-lg, cj1, D.y);
-        if (t == kt) {
-            if (k & 1) r2.y = rk;
-            else r2.x = rk;
-        }
-        if (k < 7) {
-            const double mkx = __shfl_sync(kFull, M.x, 4 * k + t), mky = __shfl_sync(kFull, M.y, 4 * k + t);
-            M.x = fma(-lg, mkx, M.x);
-            M.y = fma(-lg, mky, M.y);
-        }
-    }
-    if (bad && lane == 0) *flag = 1;
-    Minv = M;
-    const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
-    const double ax = __shfl_sync(kFull, M.x, s0), ay = __shfl_sync(kFull, M.y, s0);
-    const double bx = __shfl_sync(kFull, M.x, s1), by = __shfl_sync(kFull, M.y, s1);
-    MinvT = make_double2((g & 1) ? ay : ax, (g & 1) ? by : bx);
-}
-
 // One just-in-time batch of element matrices (lane = element, first-use order) into the ring.  Kept out of line:
 // the 36 accumulators and the shape-function state would otherwise sit on top of the register window.
 __device__ __noinline__ void warp_element_batch(const double *__restrict__ ecoord, double *__restrict__ ke, int k,
