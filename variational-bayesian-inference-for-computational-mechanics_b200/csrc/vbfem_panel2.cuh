@@ -146,28 +146,34 @@ __global__ void __launch_bounds__(kPanelNT, 2) fem_panel2_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const double d = a[tri(k, k)];
-                bad |= !(d > 0.0 && d < 1.0e300);
+                // positive, finite, not tiny: sign and exponent bits only (integer pipe; the FP64 pipe is the contended one)
+                bad |= (unsigned)(__double2hiint(d) - 0x00200000) >= 0x7fd00000u;
                 rdv[k] = fast_rcp3(d);
+                // the next pivot first, one level after the reciprocal: it heads the dependency chain of the block --
+                // and this warp's chain is the critical path of the panel
+                if (k + 1 < 8) {
+                    const double sq = a[tri(k + 1, k)] * a[tri(k + 1, k)];
+                    a[tri(k + 1, k + 1)] = fma(-sq, rdv[k], a[tri(k + 1, k + 1)]);
+                }
 #pragma unroll
                 for (int j = k + 1; j < 8; ++j) {
                     const double ljk = a[tri(j, k)] * rdv[k];
 #pragma unroll
-                    for (int i = j; i < 8; ++i) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
+                    for (int i = j; i < 8; ++i)
+                        if (!(i == k + 1 && j == k + 1)) a[tri(i, j)] = fma(-a[tri(i, k)], ljk, a[tri(i, j)]);
                     a[tri(j, k)] = ljk;  // rows i > j of column k stay unscaled until their own turn
                 }
             }
             if (bad && lane == 0) S.flag = 1;
+            // column j of the inverse of the unit factor, column oriented: dependency depth 7 instead of 28
             const int j = lane & 7;
             double m[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) m[i] = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-            for (int i = 1; i < 8; ++i) {
-                double acc = 0.0;
+            for (int k = 0; k < 7; ++k)
 #pragma unroll
-                for (int k = 0; k < i; ++k) acc = fma(a[tri(i, k)], m[k], acc);  // m[k] = 0 for k < j
-                m[i] = (i > j) ? -acc : m[i];
-            }
+                for (int i = k + 1; i < 8; ++i) m[i] = fma(-a[tri(i, k)], m[k], m[i]);  // m[k] = 0 for k < j
             if (lane < 8) {
 #pragma unroll
                 for (int i = 0; i < 8; i += 2)
