@@ -395,9 +395,19 @@ def run_cuda(args):
     B = 64
     yd = np.random.default_rng(2).standard_normal((10000, 2)) * np.array([0.53, 0.65]) + np.array([-4.24, 5.71])
 
-    def time_elbo(S, seed, graphed=True, pipelined=True):
+    # the ranks' exchange: P2P stores into the peers' mailboxes from inside the reduction kernel (NVLink); NCCL if the
+    # box does not allow CUDA IPC between the rank processes
+    peer_note = None
+    if world > 1:
+        try:
+            eng.peer_connect_group(cap_doubles=3 + 4 * B)
+        except Exception as exc:   # noqa: BLE001 -- reported in the JSON line
+            peer_note = repr(exc)[:200]
+    use_peer = world > 1 and eng.peer_world == world
+
+    def time_elbo(S, seed, graphed=True, pipelined=True, peer=None):
         e_data = torch.tensor(np.random.default_rng(seed).standard_normal((S, 2)), device=dev)
-        loss_fn = pkg.elbo.Step1Loss(eng, e_data, 0.1, rank=rank, world=world)
+        loss_fn = pkg.elbo.Step1Loss(eng, e_data, 0.1, rank=rank, world=world, peer=peer)
         model = pkg.elbo.make_step1_model(device=dev)
         if graphed:
             step = pkg.elbo.GraphedStep1(model, pkg.elbo.make_step1_optimizer_capturable(model), loss_fn, B, dev)
@@ -437,6 +447,11 @@ def run_cuda(args):
     _, elbo_sync_s, _, gstep_sync = time_elbo(128 * world, 5, pipelined=False)
     del gstep_sync
     _, elbo_eager_s, last_loss, _ = time_elbo(128 * world, 5, graphed=False)
+    elbo_nccl_s, nccl_loss = 0.0, None
+    if use_peer:   # A/B: the same step with one NCCL all-reduce after the reduction kernel
+        _, elbo_nccl_s, nccl_loss, gstep_nccl = time_elbo(128 * world, 5, peer=False)
+        del gstep_nccl
+        eng.peer_status()   # raises if any exchange timed out
     c3 = None
     if world == 1:  # config 3 (shapes of the shipped data file: S = 100)
         n3, c3_s, c3_loss, c3step = time_elbo(100, 3)
@@ -471,11 +486,13 @@ def run_cuda(args):
     c4_info = dict(eng4.info)
 
     # ---------------- max over ranks
-    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms, elbo_sync_s],
+    t = torch.tensor([dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms, elbo_sync_s,
+                      elbo_nccl_s],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms, elbo_sync_s = t.tolist()
+    (dev_ms, b2b_ms, fwd_ms, e2e_s, elbo_s, elbo_eager_s, sus_ms, c4_adj_ms, c4_fwd_ms, elbo_sync_s,
+     elbo_nccl_s) = t.tolist()
 
     if rank == 0:
         import ctypes
@@ -558,8 +575,14 @@ def run_cuda(args):
                      "cuda_graph": bool(gstep.graphed), "eager_steps_per_s": elbo_steps / elbo_eager_s,
                      "host_synchronised_every_step_steps_per_s": elbo_steps / elbo_sync_s,
                      "eager_last_loss": last_loss, "timed_steps": elbo_steps,
-                     "collective": ("one NCCL all-reduce of 3 + 4B doubles per step INSIDE the timed region "
-                                    "(a node of the captured graph)") if world > 1 else "none (one GPU)",
+                     "collective": ("none (one GPU)" if world == 1 else
+                                    "3 + 4B doubles per step exchanged INSIDE the timed region by the reduction kernel "
+                                    "itself: P2P stores into every peer's mailbox over NVLink, sequence flags, sum in "
+                                    "rank order (csrc/vbfem_peer.cuh; a node of the captured graph)" if use_peer else
+                                    "one NCCL all-reduce of 3 + 4B doubles per step INSIDE the timed region (a node of "
+                                    "the captured graph); peer mailboxes unavailable: " + str(peer_note)),
+                     "nccl_all_reduce_steps_per_s": (elbo_steps / elbo_nccl_s) if use_peer and elbo_nccl_s else None,
+                     "nccl_last_loss": nccl_loss,
                      "roofline": {"bound": "fp64", "achieved": elbo_tflops, "peak": fp64.value * world,
                                   "unit": "TFLOP/s", "frac": elbo_tflops / (fp64.value * world) if fp64.value else None,
                                   "note": "0.716 MFLOP per reparameterised sample (FEM forward + adjoint); the two "

@@ -188,6 +188,42 @@ int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t 
                      const double *mu_dev, const double *sig2_dev, const double *e_dev,
                      double *sums_dev, double *h_dev /* optional */, void *stream);
 
+/* ---- ELBO partial sums all-reduced over NVLink peer memory (one process per GPU) ----------------
+ * The only exchange of the sharded ELBO step is the sum over ranks of 3 + 4B doubles
+ * (step 1) or 4 doubles (step 2).  Instead of a collective AFTER the reduction kernel, the reduction
+ * kernel stores its partial sums into a mailbox in every peer's memory (P2P stores), raises a
+ * sequence flag there, waits for the peers' flags and adds the partials in rank order: one launch
+ * less per step, no separate collective, bit-identical totals on every rank.
+ *
+ *   vbfem_peer_open      allocate this rank's mailbox for `cap` doubles per exchange; writes its CUDA IPC
+ *                        handle (64 bytes) to ipc_handle_out and/or its address to mailbox_out
+ *   (host side: all-gather the handles in rank order -- torch.distributed, MPI, a file ...)
+ *   vbfem_peer_connect   map the peers' mailboxes: ipc_handles = world x 64 bytes (one process per
+ *                        GPU), or mailboxes = world addresses (several handles of ONE process).
+ *                        The caller puts a host barrier between connect and the first exchange.
+ *   vbfem_peer_allreduce in-place sum of buf_dev[0, n) over the ranks (stand-alone form)
+ *   vbfem_peer_status    synchronises; number of exchanges done so far, or -7 if a wait timed out
+ *                        (a peer never arrived; VBFEM_PEER_TIMEOUT_MS, default 10000)
+ * Every rank must issue the same sequence of exchanges (like any collective).  All calls are legal
+ * inside CUDA-graph capture except open / connect / status. */
+int vbfem_peer_open(vbfem_t *h, int32_t rank, int32_t world, int32_t cap_doubles,
+                    void *ipc_handle_out /* 64 bytes or NULL */, void **mailbox_out /* or NULL */);
+int vbfem_peer_connect(vbfem_t *h, const void *ipc_handles /* world x 64 bytes or NULL */,
+                       void *const *mailboxes /* world pointers or NULL */);
+int vbfem_peer_allreduce(vbfem_t *h, double *buf_dev, int32_t n, void *stream);
+int64_t vbfem_peer_status(vbfem_t *h);
+
+/* vbfem_elbo_step1 with the exchange fused into its reduction kernel:
+ * totals_dev[3 + 4B] = [sums(3) | gmu(B x 2) | gsig2(B x 2)] summed over all ranks' sample ranges. */
+int vbfem_elbo_step1_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                               const double *mu_dev, const double *sig2_dev, const double *e_dev,
+                               const double *ybatch_dev, double sig_e, double *totals_dev,
+                               double *f_dev /* optional */, void *stream);
+/* vbfem_elbo_step2 likewise: totals_dev[4] summed over all ranks. */
+int vbfem_elbo_step2_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                               const double *mu_dev, const double *sig2_dev, const double *e_dev,
+                               double *totals_dev, double *h_dev /* optional */, void *stream);
+
 /* Per-sample status words of the last launch (0 = ok, bit0 = non-positive or
  * non-finite pivot).  Synchronises.  Returns the number of flagged samples,
  * or a negative error. */

@@ -1,0 +1,216 @@
+"""The ELBO step's exchange over NVLink peer memory (csrc/vbfem_peer.cuh, include/vbfem.h vbfem_peer_*):
+partial sums stored into every peer's mailbox from inside the reduction kernel, summed in rank order.
+
+* one GPU, two engines of one process as two "ranks" on two streams (mailboxes by address): stand-alone
+  all-reduce (parity reuse over many calls), fused step-1 / step-2 totals against the unsharded partials,
+  Step1Loss(peer=True) against the torch.distributed-free single-rank loss;
+* two GPUs (skipped on a one-GPU box): one process per GPU over CUDA IPC handles, NCCL all-reduce as the
+  checker, the graph-captured training step with the exchange inside.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, eng):
+    import torch
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=eng.device)
+
+
+@pytest.fixture(scope="module")
+def two_ranks(pkg, golden_model):
+    """Two engines on cuda:0 connected through each other's mailbox addresses, each with its own stream."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    engs = [pkg.CookFemEngine(golden_model, device=0) for _ in range(2)]
+    boxes = [e.peer_open(r, 2, 3 + 4 * 64)[1] for r, e in enumerate(engs)]
+    for e in engs:
+        e.peer_connect(mailboxes=boxes)
+        e.reserve(4096)   # no buffer growth (cudaDeviceSynchronize) while the other "rank" waits in its kernel
+    streams = [torch.cuda.Stream(device=0) for _ in range(2)]
+    torch.cuda.synchronize()
+    yield engs, streams
+    for e in engs:
+        e.close()
+
+
+def test_peer_allreduce_two_ranks_one_gpu(two_ranks):
+    import torch
+    engs, streams = two_ranks
+    rng = np.random.default_rng(0)
+    for it in range(7):   # odd and even call numbers: both parities of the mailbox, reused
+        n = [259, 4, 1, 100, 259, 17, 259][it]
+        a = [rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4) for _ in range(2)]
+        bufs = [_t(a[r], engs[r]) for r in range(2)]
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                engs[r].peer_allreduce(bufs[r])
+        torch.cuda.synchronize()
+        want = a[0] + a[1]            # rank order 0 + 1: exactly what the kernel does
+        for r in range(2):
+            assert np.array_equal(bufs[r].cpu().numpy(), want), f"call {it}, rank {r}"
+    assert engs[0].peer_status() == engs[1].peer_status() >= 7
+
+
+def test_elbo_totals_fused_exchange(pkg, two_ranks):
+    """Fused step-1 / step-2 exchange: two ranks own halves of the B*S samples; the totals both ranks end up with
+    are bit-identical and equal the sum of the range-restricted partials (the pre-existing, separately tested path)."""
+    import torch
+    engs, streams = two_ranks
+    rng = np.random.default_rng(5)
+    B, S = 64, 10
+    mu = rng.standard_normal((B, 2)) * 0.3
+    sig2 = np.exp(rng.standard_normal((B, 2)) * 0.2)
+    e = rng.standard_normal((S, 2))
+    yb = rng.standard_normal((B, 2)) * 0.5 + np.array([-4.2, 5.7])
+    args = [[_t(v, engs[r]) for v in (mu, sig2, e, yb)] for r in range(2)]
+    cut = [pkg.elbo.shard_range(B * S, r, 2) for r in range(2)]
+    # checker: partials per range, added in rank order on the host side
+    parts = [engs[0].elbo_step1_partials(*args[0], 0.1, lo, hi)[:3] for lo, hi in cut]
+    want = torch.cat([(parts[0][k] + parts[1][k]).reshape(-1) for k in range(3)]).cpu().numpy()
+    torch.cuda.synchronize()
+    tot = [None, None]
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            tot[r] = engs[r].elbo_step1_totals(*args[r], 0.1, *cut[r])
+    torch.cuda.synchronize()
+    t0, t1 = tot[0].cpu().numpy(), tot[1].cpu().numpy()
+    assert np.array_equal(t0, t1)
+    assert np.array_equal(t0, want)
+    # step 2
+    parts2 = [engs[0].elbo_step2_partials(args[0][0], args[0][1], args[0][2], lo, hi)[0] for lo, hi in cut]
+    want2 = (parts2[0] + parts2[1]).cpu().numpy()
+    torch.cuda.synchronize()
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            tot[r] = engs[r].elbo_step2_totals(args[r][0], args[r][1], args[r][2], *cut[r])
+    torch.cuda.synchronize()
+    assert np.array_equal(tot[0].cpu().numpy(), tot[1].cpu().numpy())
+    assert np.array_equal(tot[0].cpu().numpy(), want2)
+    for g in engs:
+        g.peer_status()
+
+
+def test_step1_loss_with_peer_exchange_equals_unsharded(pkg, two_ranks, engine):
+    import torch
+    engs, streams = two_ranks
+    rng = np.random.default_rng(6)
+    B, S = 8, 12
+    mu, ls = rng.standard_normal((B, 2)) * 0.3, rng.standard_normal((B, 2)) * 0.2
+    e = rng.standard_normal((S, 2))
+    yb = rng.standard_normal((B, 2)) * 0.5 + np.array([-4.2, 5.7])
+    mu0, ls0 = _t(mu, engine).requires_grad_(True), _t(ls, engine).requires_grad_(True)
+    ref = pkg.elbo.Step1Loss(engine, _t(e, engine), 0.1)(_t(yb, engine), mu0, torch.exp(ls0), ls0)
+    ref.backward()
+    torch.cuda.synchronize()
+    outs = []
+    leaves = []
+    for r in range(2):   # warm torch's allocator on both streams: no cudaMalloc while a "rank" waits in its kernel
+        with torch.cuda.stream(streams[r]):
+            m, l = _t(mu, engs[r]).requires_grad_(True), _t(ls, engs[r]).requires_grad_(True)
+            pkg.elbo.Step1Loss(engs[r], _t(e, engs[r]), 0.1)(_t(yb, engs[r]), m, torch.exp(l), l).backward()
+    torch.cuda.synchronize()
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            m, l = _t(mu, engs[r]).requires_grad_(True), _t(ls, engs[r]).requires_grad_(True)
+            loss = pkg.elbo.Step1Loss(engs[r], _t(e, engs[r]), 0.1, rank=r, world=2, peer=True)(
+                _t(yb, engs[r]), m, torch.exp(l), l)
+            outs.append(loss)
+            leaves.append((m, l))
+    torch.cuda.synchronize()
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            outs[r].backward()
+    torch.cuda.synchronize()
+    assert float(outs[0]) == float(outs[1])
+    assert abs(float(outs[0]) - float(ref)) < 1e-12 * abs(float(ref))
+    for m, l in leaves:
+        assert relerr(m.grad.cpu().numpy(), mu0.grad.cpu().numpy()) < 1e-12
+        assert relerr(l.grad.cpu().numpy(), ls0.grad.cpu().numpy()) < 1e-12
+
+
+def test_peer_calls_refused_without_mailboxes(pkg, engine):
+    import torch
+    buf = torch.zeros(4, dtype=torch.float64, device=engine.device)
+    with pytest.raises(pkg.VbfemError):
+        engine.peer_allreduce(buf)
+    with pytest.raises(ValueError):
+        pkg.elbo.Step1Loss(engine, buf.reshape(2, 2), 0.1, rank=0, world=2, peer=True)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import importlib
+import numpy as np, torch, torch.distributed as dist
+pkg = importlib.import_module("variational-bayesian-inference-for-computational-mechanics_b200")
+from conftest import model_from_golden
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+g = np.load(os.path.join({root!r}, "tests", "golden", "ref_numpy_twin.npz"))
+eng = pkg.CookFemEngine(model_from_golden(g), device=rank)
+eng.peer_connect_group(cap_doubles=3 + 4 * 64)
+dev = eng.device
+rng = np.random.default_rng(100 + rank)
+worst = 0.0
+for it in range(6):
+    a = torch.tensor(rng.standard_normal(259), device=dev)
+    b = a.clone()
+    eng.peer_allreduce(a)
+    dist.all_reduce(b)
+    worst = max(worst, float((a - b).abs().max() / b.abs().max()))
+    gathered = [torch.empty_like(a) for _ in range(world)]
+    dist.all_gather(gathered, a)
+    assert all(torch.equal(gathered[0], t) for t in gathered), "totals differ between ranks"
+# the training step, graph-captured, exchange inside: peer mailboxes against NCCL, same seeds
+B, S = 64, 16 * world
+yd = np.random.default_rng(2).standard_normal((640, 2)) * np.array([0.53, 0.65]) + np.array([-4.24, 5.71])
+e = torch.tensor(np.random.default_rng(5).standard_normal((S, 2)), device=dev)
+losses = {{}}
+for peer in (True, False):
+    model = pkg.elbo.make_step1_model(device=dev)
+    lf = pkg.elbo.Step1Loss(eng, e, 0.1, rank=rank, world=world, peer=peer)
+    step = pkg.elbo.GraphedStep1(model, pkg.elbo.make_step1_optimizer_capturable(model), lf, B, dev)
+    losses[peer] = [float(step.step(yd[i * B:(i + 1) * B])) for i in range(6)]
+    assert step.graphed, getattr(step, "capture_error", "")
+err = max(abs(p - q) / abs(q) for p, q in zip(losses[True], losses[False]))
+print("RANK", rank, "ALLREDUCE_ERR", worst, "STEP_ERR", err, "exchanges", eng.peer_status(), flush=True)
+assert worst < 1e-14 and err < 1e-10
+dist.barrier()
+torch.cuda.synchronize()
+sys.stdout.flush()
+# no destroy_process_group: with a captured graph that holds NCCL nodes still alive, torch's teardown of the
+# communicator was seen to block on this box; the result is already printed
+os._exit(0)
+'''
+
+
+def test_peer_exchange_two_gpus_ipc(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29621", VBFEM_PEER_TIMEOUT_MS="20000")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), WORLD_SIZE="2"),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=150)[0])
+        except subprocess.TimeoutExpired:
+            p.kill()
+            outs.append(p.communicate()[0])
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+        assert "STEP_ERR" in o

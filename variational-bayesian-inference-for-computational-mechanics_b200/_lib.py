@@ -19,7 +19,7 @@ INCLUDE = os.path.join(REPO, "include")
 LIB_PATH = os.environ.get("VBFEM_LIB", os.path.join(CSRC, "libvbfem.so"))  # VBFEM_LIB: profiling builds
 SOURCES = ["vbfem.cu"]
 HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", "vbfem_panel.cuh", "vbfem_panel2.cuh",
-           "vbfem_warp.cuh",
+           "vbfem_warp.cuh", "vbfem_peer.cuh",
            os.path.join(INCLUDE, "vbfem.h")]
 
 NVCC_FLAGS = [
@@ -37,6 +37,8 @@ SYMBOLS = [
     "vbfem_backward", "vbfem_keep_ticket", "vbfem_backward_ticket", "vbfem_forward_jac", "vbfem_jac_vjp",
     "vbfem_debug_panel_tables", "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
     "vbfem_forward_backward_host", "vbfem_measure_peaks",
+    "vbfem_peer_open", "vbfem_peer_connect", "vbfem_peer_allreduce", "vbfem_peer_status",
+    "vbfem_elbo_step1_allreduce", "vbfem_elbo_step2_allreduce",
 ]
 
 
@@ -151,6 +153,21 @@ def load():
     lib.vbfem_elbo_step2.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp, c_dp,
                                      c_dp, c_dp, c_dp]
     lib.vbfem_elbo_step2.restype = ctypes.c_int
+    lib.vbfem_elbo_step1_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp,
+                                               c_dp, c_dp, ctypes.c_double, c_dp, c_dp, c_dp]
+    lib.vbfem_elbo_step1_allreduce.restype = ctypes.c_int
+    lib.vbfem_elbo_step2_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp,
+                                               c_dp, c_dp, c_dp, c_dp]
+    lib.vbfem_elbo_step2_allreduce.restype = ctypes.c_int
+    lib.vbfem_peer_open.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_dp,
+                                    ctypes.POINTER(ctypes.c_void_p)]
+    lib.vbfem_peer_open.restype = ctypes.c_int
+    lib.vbfem_peer_connect.argtypes = [ctypes.c_void_p, c_dp, ctypes.POINTER(ctypes.c_void_p)]
+    lib.vbfem_peer_connect.restype = ctypes.c_int
+    lib.vbfem_peer_allreduce.argtypes = [ctypes.c_void_p, c_dp, ctypes.c_int32, c_dp]
+    lib.vbfem_peer_allreduce.restype = ctypes.c_int
+    lib.vbfem_peer_status.argtypes = [ctypes.c_void_p]
+    lib.vbfem_peer_status.restype = i64
     lib.vbfem_status.argtypes = [ctypes.c_void_p, c_dp, i64]
     lib.vbfem_status.restype = i64
     lib.vbfem_forward_host.argtypes = [ctypes.c_void_p, i64, c_dp, c_dp, c_dp]

@@ -203,6 +203,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 #include "vbfem_panel.cuh"
 #include "vbfem_panel2.cuh"
 #include "vbfem_warp.cuh"
+#include "vbfem_peer.cuh"
 namespace vbfem {
 
 // ------------------------------------------------------------------------------------------
@@ -850,11 +851,19 @@ __global__ void __launch_bounds__(NT, MINB) fem_kernel(const __grid_constant__ D
 // Step-1 ELBO reductions over the local sample range (deterministic: fixed order per output).
 //   sums[0..1] = sum_j f_j, sums[2] = sum_j |f_j|^2
 //   gmu[b][k]  = sum_s gtheta[b,s][k],  gsig2[b][k] = sum_s gtheta[b,s][k] * e[s][k] / (2 sqrt(sig2[b][k]))
+// PEER: the partial sums go straight into every rank's mailbox (vbfem_peer.cuh) and the last block to arrive
+// writes the world's totals [sums(3) | gmu(2B) | gsig2(2B)] to `sums` (then one contiguous buffer).
+template <bool PEER>
 __global__ void elbo_reduce_kernel(int B, int S, long long j_begin, long long j_end, const double *f,
                                    const double *gth, const double *e, const double *sig2, double *sums,
-                                   double *gmu, double *gsig2) {
+                                   double *gmu, double *gsig2, const PeerCtx P) {
     __shared__ double sh[3][256];
     const int tid = threadIdx.x;
+    unsigned long long q = 0;
+    if (PEER) {
+        q = *P.seq + 1;
+        __syncthreads();
+    }
     if (blockIdx.x == 0) {
         double a0 = 0, a1 = 0, a2 = 0;
         for (long long j = j_begin + tid; j < j_end; j += blockDim.x) {
@@ -872,7 +881,10 @@ __global__ void elbo_reduce_kernel(int B, int S, long long j_begin, long long j_
                 for (int q = 0; q < 3; ++q) sh[q][tid] += sh[q][tid + o];
             __syncthreads();
         }
-        if (tid < 3) sums[tid] = sh[tid][0];
+        if (tid < 3) {
+            if (PEER) peer_push(P, q, tid, sh[tid][0]);
+            else sums[tid] = sh[tid][0];
+        }
     } else {
         const int idx = (blockIdx.x - 1) * blockDim.x + tid;  // (b, k)
         if (idx < 2 * B) {
@@ -886,17 +898,30 @@ __global__ void elbo_reduce_kernel(int B, int S, long long j_begin, long long j_
                 gm += g;
                 gs += g * e[2 * (j - (long long)bb * S) + k];
             }
-            gmu[idx] = gm;
-            gsig2[idx] = gs * 0.5 / sqrt(sig2[idx]);
+            const double gs2 = gs * 0.5 / sqrt(sig2[idx]);
+            if (PEER) {
+                peer_push(P, q, 3 + idx, gm);
+                peer_push(P, q, 3 + 2 * B + idx, gs2);
+            } else {
+                gmu[idx] = gm;
+                gsig2[idx] = gs2;
+            }
         }
     }
+    if (PEER) peer_finish(P, q, (int)gridDim.x, 3 + 4 * B, sums);
 }
 
 // Step-2 sufficient statistics over the local sample range (fixed order):
 //   sums[0..1] = sum_j h_j (per component), sums[2..3] = sum_j h_j^2
-__global__ void hsum_kernel(long long nloc, const double *h, double *sums) {
+template <bool PEER>
+__global__ void hsum_kernel(long long nloc, const double *h, double *sums, const PeerCtx P) {
     __shared__ double sh[4][256];
     const int tid = threadIdx.x;
+    unsigned long long q = 0;
+    if (PEER) {
+        q = *P.seq + 1;
+        __syncthreads();
+    }
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (long long j = tid; j < nloc; j += blockDim.x) {
         const double h0 = h[2 * j], h1 = h[2 * j + 1];
@@ -915,7 +940,11 @@ __global__ void hsum_kernel(long long nloc, const double *h, double *sums) {
             for (int q = 0; q < 4; ++q) sh[q][tid] += sh[q][tid + o];
         __syncthreads();
     }
-    if (tid < 4) sums[tid] = sh[tid][0];
+    if (tid < 4) {
+        if (PEER) peer_push(P, q, tid, sh[tid][0]);
+        else sums[tid] = sh[tid][0];
+    }
+    if (PEER) peer_finish(P, q, 1, 4, sums);
 }
 
 __global__ void ysum_kernel(int B, const double *y, double *out) {
@@ -1015,6 +1044,11 @@ struct vbfem_handle {
     int n_real = 0;   // order of the system without padding rows
     int variant = 0;  // 0 = generic per-column kernel, 2 = on-chip front kernel, 3 = blocked panel kernel
     long long *timeline = nullptr;
+    // NVLink peer mailboxes of the ELBO all-reduce (vbfem_peer.cuh)
+    PeerCtx peer{};
+    void *peer_mail = nullptr, *peer_state = nullptr;
+    std::vector<void *> peer_opened;
+    bool peer_ready = false;
 };
 
 template <typename T>
@@ -2138,6 +2172,9 @@ extern "C" void vbfem_destroy(vbfem_t *h) {
     cudaFree(h->stage);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    for (void *p : h->peer_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(h->peer_mail);
+    cudaFree(h->peer_state);
     delete h;
 }
 
@@ -2399,10 +2436,13 @@ extern "C" int vbfem_fields_elementwise(vbfem_t *h, int64_t N, const double *ema
     return launch(h, a, stream);
 }
 
-extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
-                                const double *sig2, const double *e, const double *ybatch, double sig_e,
-                                double *sums, double *gmu, double *gsig2, double *f_out, void *stream) {
-    if (!h || !mu || !sig2 || !e || !ybatch || !sums || !gmu || !gsig2) return fail(-1, "null argument");
+static int elbo_step1_impl(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
+                           const double *sig2, const double *e, const double *ybatch, double sig_e, double *sums,
+                           double *gmu, double *gsig2, double *f_out, void *stream, bool peer) {
+    if (!h || !mu || !sig2 || !e || !ybatch || !sums || (!peer && (!gmu || !gsig2))) return fail(-1, "null argument");
+    if (peer && !h->peer_ready) return fail(-6, "no peer mailboxes: vbfem_peer_open / vbfem_peer_connect first");
+    if (peer && 3 + 4 * (int64_t)B > h->peer.cap) return fail(-6, "peer mailbox holds %d doubles, the step needs %lld",
+                                                              h->peer.cap, 3 + 4 * (long long)B);
     if (B <= 0 || S <= 0 || j_begin < 0 || j_end < j_begin || j_end > (int64_t)B * S)
         return fail(-1, "bad ELBO sample range");
     CU(cudaSetDevice(h->device));
@@ -2427,14 +2467,33 @@ extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
     rc = launch(h, a, stream);
     if (rc) return rc;
     const int nblk = 1 + (2 * B + 255) / 256;
-    elbo_reduce_kernel<<<nblk, 256, 0, st>>>(B, S, j_begin, j_end, a.f_out, h->elbo_g, e, sig2, sums, gmu, gsig2);
+    if (peer)
+        elbo_reduce_kernel<true><<<nblk, 256, 0, st>>>(B, S, j_begin, j_end, a.f_out, h->elbo_g, e, sig2, sums, nullptr,
+                                                       nullptr, h->peer);
+    else
+        elbo_reduce_kernel<false><<<nblk, 256, 0, st>>>(B, S, j_begin, j_end, a.f_out, h->elbo_g, e, sig2, sums, gmu,
+                                                        gsig2, PeerCtx{});
     CU(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
-                                const double *sig2, const double *e, double *sums, double *h_out, void *stream) {
+extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
+                                const double *sig2, const double *e, const double *ybatch, double sig_e,
+                                double *sums, double *gmu, double *gsig2, double *f_out, void *stream) {
+    return elbo_step1_impl(h, B, S, j_begin, j_end, mu, sig2, e, ybatch, sig_e, sums, gmu, gsig2, f_out, stream, false);
+}
+
+extern "C" int vbfem_elbo_step1_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                                          const double *mu, const double *sig2, const double *e, const double *ybatch,
+                                          double sig_e, double *totals, double *f_out, void *stream) {
+    return elbo_step1_impl(h, B, S, j_begin, j_end, mu, sig2, e, ybatch, sig_e, totals, nullptr, nullptr, f_out, stream,
+                           true);
+}
+
+static int elbo_step2_impl(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
+                           const double *sig2, const double *e, double *sums, double *h_out, void *stream, bool peer) {
     if (!h || !mu || !sig2 || !e || !sums) return fail(-1, "null argument");
+    if (peer && !h->peer_ready) return fail(-6, "no peer mailboxes: vbfem_peer_open / vbfem_peer_connect first");
     if (B <= 0 || S <= 0 || j_begin < 0 || j_end < j_begin || j_end > (int64_t)B * S)
         return fail(-1, "bad ELBO sample range");
     CU(cudaSetDevice(h->device));
@@ -2453,9 +2512,119 @@ extern "C" int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
     a.h = h_out ? h_out : h->elbo_g;
     rc = launch(h, a, stream);
     if (rc) return rc;
-    hsum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(nloc, a.h, sums);
+    if (peer) hsum_kernel<true><<<1, 256, 0, (cudaStream_t)stream>>>(nloc, a.h, sums, h->peer);
+    else hsum_kernel<false><<<1, 256, 0, (cudaStream_t)stream>>>(nloc, a.h, sums, PeerCtx{});
     CU(cudaGetLastError());
     return 0;
+}
+
+extern "C" int vbfem_elbo_step2(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
+                                const double *sig2, const double *e, double *sums, double *h_out, void *stream) {
+    return elbo_step2_impl(h, B, S, j_begin, j_end, mu, sig2, e, sums, h_out, stream, false);
+}
+
+extern "C" int vbfem_elbo_step2_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                                          const double *mu, const double *sig2, const double *e, double *totals,
+                                          double *h_out, void *stream) {
+    return elbo_step2_impl(h, B, S, j_begin, j_end, mu, sig2, e, totals, h_out, stream, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// NVLink peer mailboxes (vbfem_peer.cuh): one process per GPU exchanges CUDA IPC handles of its mailbox
+// (any host-side all-gather: torch.distributed, MPI, a file); several handles of ONE process pass the
+// mailbox addresses instead.
+// ------------------------------------------------------------------------------------------
+static size_t peer_mail_bytes(int world, int cap) {
+    return ((size_t)2 * world * cap) * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+}
+
+extern "C" int vbfem_peer_open(vbfem_t *h, int32_t rank, int32_t world, int32_t cap, void *ipc_handle_out,
+                               void **mailbox_out) {
+    if (!h) return fail(-1, "null argument");
+    if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || cap < 4)
+        return fail(-1, "bad peer geometry (rank %d of %d, %d doubles; at most %d ranks)", rank, world, cap,
+                    kPeerMaxWorld);
+    if (h->peer_mail) return fail(-6, "peer mailbox already open");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = peer_mail_bytes(world, cap);
+    CU(cudaMalloc(&h->peer_mail, bytes));
+    CU(cudaMemset(h->peer_mail, 0, bytes));
+    CU(cudaMalloc(&h->peer_state, 64));
+    CU(cudaMemset(h->peer_state, 0, 64));
+    CU(cudaDeviceSynchronize());
+    h->peer = PeerCtx{};
+    h->peer.rank = rank;
+    h->peer.world = world;
+    h->peer.cap = cap;
+    h->peer.seq = (unsigned long long *)h->peer_state;
+    h->peer.arrived = (unsigned int *)((char *)h->peer_state + 8);
+    h->peer.err = (int *)((char *)h->peer_state + 16);
+    const char *to = getenv("VBFEM_PEER_TIMEOUT_MS");
+    h->peer.timeout_ns = (unsigned long long)(to ? atoll(to) : 10000) * 1000000ull;
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t ih;
+        CU(cudaIpcGetMemHandle(&ih, h->peer_mail));
+        memcpy(ipc_handle_out, &ih, sizeof ih);
+    }
+    if (mailbox_out) *mailbox_out = h->peer_mail;
+    return 0;
+}
+
+extern "C" int vbfem_peer_connect(vbfem_t *h, const void *ipc_handles, void *const *mailboxes) {
+    if (!h || (!ipc_handles && !mailboxes)) return fail(-1, "null argument");
+    if (!h->peer_mail) return fail(-6, "vbfem_peer_open first");
+    if (h->peer_ready) return fail(-6, "peers already connected");
+    CU(cudaSetDevice(h->device));
+    for (int r = 0; r < h->peer.world; ++r) {
+        if (r == h->peer.rank) {
+            h->peer.mail[r] = (double *)h->peer_mail;
+        } else if (mailboxes) {  // same process: use the address; enable peer access if it lives on another device
+            cudaPointerAttributes at{};
+            CU(cudaPointerGetAttributes(&at, mailboxes[r]));
+            if (at.type != cudaMemoryTypeDevice) return fail(-1, "mailbox %d is not device memory", r);
+            if (at.device != h->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, h->device, at.device));
+                if (!can) return fail(-6, "device %d cannot access device %d", h->device, at.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(-2, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            h->peer.mail[r] = (double *)mailboxes[r];
+        } else {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, (const char *)ipc_handles + (size_t)r * sizeof ih, sizeof ih);
+            void *p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_opened.push_back(p);
+            h->peer.mail[r] = (double *)p;
+        }
+    }
+    h->peer_ready = true;
+    return 0;
+}
+
+extern "C" int vbfem_peer_allreduce(vbfem_t *h, double *buf, int32_t n, void *stream) {
+    if (!h || !buf) return fail(-1, "null argument");
+    if (!h->peer_ready) return fail(-6, "no peer mailboxes: vbfem_peer_open / vbfem_peer_connect first");
+    if (n < 0 || n > h->peer.cap) return fail(-1, "%d doubles do not fit the mailbox (%d)", n, h->peer.cap);
+    CU(cudaSetDevice(h->device));
+    peer_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(h->peer, buf, n);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int64_t vbfem_peer_status(vbfem_t *h) {
+    if (!h) return fail(-1, "null argument");
+    if (!h->peer_state) return fail(-6, "no peer mailboxes");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long st[3] = {0, 0, 0};
+    CU(cudaMemcpy(st, h->peer_state, sizeof st, cudaMemcpyDeviceToHost));
+    if ((int)st[2]) return fail(-7, "a peer never arrived at exchange %llu (timed out)", st[0] + 1);
+    return (int64_t)st[0];
 }
 
 extern "C" int64_t vbfem_status(vbfem_t *h, int32_t *flags_host, int64_t N) {

@@ -60,13 +60,19 @@ def _data_term_function():
         def forward(ctx, mu, sig2, loss_obj, y_batch):
             B, S = mu.shape[0], loss_obj.e_data.shape[0]
             lo, hi = shard_range(B * S, loss_obj.rank, loss_obj.world)
-            sums, gmu, gsig2, _ = loss_obj.engine.elbo_step1_partials(
-                mu.detach().contiguous(), sig2.detach().contiguous(), loss_obj.e_data, y_batch.contiguous(),
-                loss_obj.sig_e, lo, hi)
-            buf = torch.cat([sums, gmu.reshape(-1), gsig2.reshape(-1)])
-            if loss_obj.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=loss_obj.group)
+            if loss_obj.world > 1 and loss_obj.peer:
+                # the exchange is part of the reduction kernel: P2P stores into the peers' mailboxes over NVLink
+                buf = loss_obj.engine.elbo_step1_totals(
+                    mu.detach().contiguous(), sig2.detach().contiguous(), loss_obj.e_data, y_batch.contiguous(),
+                    loss_obj.sig_e, lo, hi)
+            else:
+                sums, gmu, gsig2, _ = loss_obj.engine.elbo_step1_partials(
+                    mu.detach().contiguous(), sig2.detach().contiguous(), loss_obj.e_data, y_batch.contiguous(),
+                    loss_obj.sig_e, lo, hi)
+                buf = torch.cat([sums, gmu.reshape(-1), gsig2.reshape(-1)])
+                if loss_obj.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=loss_obj.group)
             ctx.save_for_backward(buf[3:3 + 2 * B].reshape(B, 2), buf[3 + 2 * B:].reshape(B, 2))
             return -term2_from_sums(buf[:3], y_batch, B * S, loss_obj.sig_e)
 
@@ -88,9 +94,15 @@ class Step1Loss:
     ``group``/``rank``/``world`` describe the torch.distributed process group
     whose ranks share the Monte-Carlo samples."""
 
-    def __init__(self, engine, e_data, sig_e, group=None, rank=0, world=1):
+    def __init__(self, engine, e_data, sig_e, group=None, rank=0, world=1, peer=None):
         self.engine, self.e_data, self.sig_e = engine, e_data.contiguous(), float(sig_e)
         self.group, self.rank, self.world = group, int(rank), int(world)
+        # peer mailboxes connected for this world (engine.peer_connect_group): exchange inside the reduction kernel;
+        # otherwise (or with peer=False) one torch.distributed all-reduce after it
+        connected = int(getattr(engine, "peer_world", 0)) == self.world and self.world > 1
+        if peer and not connected:
+            raise ValueError("peer exchange requested but the engine has no peer mailboxes for this world size")
+        self.peer = connected if peer is None else bool(peer)
 
     def __call__(self, y_batch, theta_mean, theta_sig, log_theta_sig):
         global _NegTerm2
@@ -300,11 +312,15 @@ class Step2Loss:
     def __call__(self, theta_mean, theta_sig, z_mean, z_sig, log_z_sig, logz_mean_post, logz_sig_post):
         B, S = theta_mean.shape[0], self.e_data.shape[0]
         lo, hi = shard_range(B * S, self.rank, self.world)
-        sums, _ = self.engine.elbo_step2_partials(theta_mean.detach().contiguous(), theta_sig.detach().contiguous(),
-                                                  self.e_data, lo, hi)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        if self.world > 1 and int(getattr(self.engine, "peer_world", 0)) == self.world:
+            sums = self.engine.elbo_step2_totals(theta_mean.detach().contiguous(), theta_sig.detach().contiguous(),
+                                                 self.e_data, lo, hi)
+        else:
+            sums, _ = self.engine.elbo_step2_partials(theta_mean.detach().contiguous(),
+                                                      theta_sig.detach().contiguous(), self.e_data, lo, hi)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
         t5 = term5_from_sums(sums, z_mean, z_sig, B * S, self.sig_eta)
         return (term4(z_mean, log_z_sig) - t5) * self.alpha + add_loss(z_mean, z_sig, logz_mean_post, logz_sig_post)
 

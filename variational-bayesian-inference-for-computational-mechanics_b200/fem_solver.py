@@ -312,6 +312,87 @@ class CookFemEngine:
         self.launches += 2
         return sums, h
 
+    # ------------------------------------------------ all-reduce over NVLink peer memory (include/vbfem.h)
+    peer_world = 0
+
+    def peer_open(self, rank, world, cap_doubles):
+        """Allocate this rank's mailbox; returns (ipc_handle: bytes[64], mailbox address)."""
+        hbuf = ctypes.create_string_buffer(64)
+        addr = ctypes.c_void_p()
+        _lib.check(self.lib.vbfem_peer_open(self._h, int(rank), int(world), int(cap_doubles),
+                                            ctypes.cast(hbuf, ctypes.c_void_p), ctypes.byref(addr)), "vbfem_peer_open")
+        self._peer_geom = (int(rank), int(world), int(cap_doubles))
+        return hbuf.raw, int(addr.value)
+
+    def peer_connect(self, ipc_handles=None, mailboxes=None):
+        """Map the peers' mailboxes: ``ipc_handles`` = list of the world's 64-byte handles in rank order
+        (one process per GPU), or ``mailboxes`` = list of addresses (engines of this process)."""
+        rank, world, _ = self._peer_geom
+        if mailboxes is not None:
+            arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(a)) for a in mailboxes])
+            rc = self.lib.vbfem_peer_connect(self._h, ctypes.c_void_p(0), arr)
+        else:
+            blob = b"".join(bytes(hd) for hd in ipc_handles)
+            if len(blob) != 64 * world:
+                raise ValueError("need one 64-byte IPC handle per rank")
+            self._peer_blob = ctypes.create_string_buffer(blob, len(blob))
+            rc = self.lib.vbfem_peer_connect(self._h, ctypes.cast(self._peer_blob, ctypes.c_void_p), None)
+        _lib.check(rc, "vbfem_peer_connect")
+        self.peer_world = world
+
+    def peer_connect_group(self, group=None, cap_doubles=1024):
+        """One process per GPU under torch.distributed: open the mailbox, all-gather the IPC handles over the
+        process group (host-side objects), map the peers, barrier.  Afterwards ``peer_allreduce`` and the
+        ``*_totals`` ELBO calls exchange over NVLink peer memory without a collective library on the data path."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handle, _ = self.peer_open(rank, world, cap_doubles)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_connect(ipc_handles=handles)
+        dist.barrier(group=group)   # every mailbox is zeroed and mapped before the first exchange
+
+    def peer_allreduce(self, buf):
+        """In-place sum of the contiguous float64 device tensor ``buf`` over the ranks (rank order: bit-identical
+        totals everywhere)."""
+        t = self.torch
+        if buf.device != self.device or buf.dtype != t.float64 or not buf.is_contiguous():
+            raise ValueError(f"buf must be a contiguous float64 tensor on {self.device}")
+        _lib.check(self.lib.vbfem_peer_allreduce(self._h, ctypes.c_void_p(buf.data_ptr()), int(buf.numel()),
+                                                 self._stream()), "vbfem_peer_allreduce")
+        self.launches += 1
+        return buf
+
+    def peer_status(self):
+        """Synchronises; exchanges done so far.  Raises if a peer never arrived."""
+        n = int(self.lib.vbfem_peer_status(self._h))
+        _lib.check(n, "vbfem_peer_status")
+        return n
+
+    def elbo_step1_totals(self, mu, sig2, e_data, y_batch, sig_e, j_begin, j_end):
+        """``elbo_step1_partials`` with the sum over ranks fused into its reduction kernel (peer mailboxes):
+        returns totals[3 + 4B] = [sums | gmu | gsig2] over ALL ranks' sample ranges."""
+        B, S = int(mu.shape[0]), int(e_data.shape[0])
+        tot = self._new(3 + 4 * B)
+        _lib.check(self.lib.vbfem_elbo_step1_allreduce(
+            self._h, B, S, int(j_begin), int(j_end), self._chk(mu, B, "mu"), self._chk(sig2, B, "sig2"),
+            self._chk(e_data, S, "e_data"), self._chk(y_batch, B, "y_batch"), float(sig_e),
+            ctypes.c_void_p(tot.data_ptr()), ctypes.c_void_p(0), self._stream()), "vbfem_elbo_step1_allreduce")
+        self.launches += 3
+        return tot
+
+    def elbo_step2_totals(self, mu, sig2, e_data, j_begin, j_end):
+        """``elbo_step2_partials`` with the sum over ranks fused into its reduction kernel: totals[4]."""
+        B, S = int(mu.shape[0]), int(e_data.shape[0])
+        tot = self._new(4)
+        _lib.check(self.lib.vbfem_elbo_step2_allreduce(
+            self._h, B, S, int(j_begin), int(j_end), self._chk(mu, B, "mu"), self._chk(sig2, B, "sig2"),
+            self._chk(e_data, S, "e_data"), ctypes.c_void_p(tot.data_ptr()), ctypes.c_void_p(0), self._stream()),
+            "vbfem_elbo_step2_allreduce")
+        self.launches += 2
+        return tot
+
     def status(self, n):
         """Per-sample status words of the last launch; returns (n_bad, flags)."""
         flags = np.zeros(int(n), dtype=np.int32)
