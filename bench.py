@@ -399,10 +399,22 @@ def run_cuda(args):
     # box does not allow CUDA IPC between the rank processes
     peer_note = None
     if world > 1:
+        os.environ.setdefault("VBFEM_PEER_TIMEOUT_MS", "3000")
         try:
             eng.peer_connect_group(cap_doubles=3 + 4 * B)
+            # self-test against NCCL before the exchange is trusted with the training step
+            probe = torch.tensor(np.random.default_rng(50 + rank).standard_normal(3 + 4 * B), device=dev)
+            want = probe.clone()
+            eng.peer_allreduce(probe)
+            dist.all_reduce(want)
+            eng.peer_status()
+            ok = torch.tensor([float((probe - want).abs().max() <= 1e-13 * want.abs().max())], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) != 1.0:
+                raise RuntimeError("peer all-reduce disagrees with NCCL")
         except Exception as exc:   # noqa: BLE001 -- reported in the JSON line
             peer_note = repr(exc)[:200]
+            eng.peer_world = 0
     use_peer = world > 1 and eng.peer_world == world
 
     def time_elbo(S, seed, graphed=True, pipelined=True, peer=None):

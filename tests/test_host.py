@@ -254,8 +254,14 @@ def test_plan_layout_on_host(pkg, golden_model, monkeypatch):
     the observation set-up (middle block on the observed element, observed node in the bottom front)."""
     plan = pkg.fem_solver.plan_layout(golden_model)
     assert plan["kernel_variant"] == 4 and plan["nfree"] == 440 and plan["half_bw"] == 25
+    # second generation of the warp kernel: the (K_lam, K_mu) band table [440][26] x 16 B in shared memory + per warp
+    # 640 B (last panel's Minv^T, 1/d, flag) + 1152 B (small vectors) + the 40-row window of u and four adjoints
+    assert plan["smem_bytes"] == 440 * 26 * 16 + 12 * (640 + 1152 + 40 * 5 * 8)
+    # first generation (element matrices per sample, gather table): what a smaller shared memory falls back to
     per_warp = 640 + 4 * 512 + (44 * 36 + 2) * 8     # last panel's Minv^T / 1/d / flag, staging area, ring of 44 element matrices
-    assert plan["smem_bytes"] == 12 * per_warp + 3816 * 8 + 56 * 8   # twelve warps + the packed gather table + row table
+    monkeypatch.setenv("VBFEM_WARP_V1", "1")
+    assert pkg.fem_solver.plan_layout(golden_model)["smem_bytes"] == 12 * per_warp + 3816 * 8 + 56 * 8   # twelve warps + the packed gather table + row table
+    monkeypatch.delenv("VBFEM_WARP_V1")
     # a supported observed node has no unit vectors: warp kernel; a node in the middle of the band order: front kernel
     assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=50)["kernel_variant"] == 4
     assert pkg.fem_solver.plan_layout(golden_model, node_id=1, ele_id=60)["kernel_variant"] == 4

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(REPO, "include")
 LIB_PATH = os.environ.get("VBFEM_LIB", os.path.join(CSRC, "libvbfem.so"))  # VBFEM_LIB: profiling builds
 SOURCES = ["vbfem.cu"]
 HEADERS = ["vbfem_math.cuh", "vbfem_front.cuh", "vbfem_front_kernel.cuh", "vbfem_panel.cuh", "vbfem_panel2.cuh",
-           "vbfem_warp.cuh", "vbfem_peer.cuh",
+           "vbfem_warp.cuh", "vbfem_warp2.cuh", "vbfem_peer.cuh",
            os.path.join(INCLUDE, "vbfem.h")]
 
 NVCC_FLAGS = [

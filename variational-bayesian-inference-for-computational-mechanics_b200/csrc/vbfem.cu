@@ -203,6 +203,7 @@ __device__ __forceinline__ double obs_eval(const DevModel &M, const Lame &mat, c
 #include "vbfem_panel.cuh"
 #include "vbfem_panel2.cuh"
 #include "vbfem_warp.cuh"
+#include "vbfem_warp2.cuh"
 #include "vbfem_peer.cuh"
 namespace vbfem {
 
@@ -1574,6 +1575,46 @@ static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
            (size_t)NW * warp_kernel_smem(P) + warp_kernel_tab_bytes(P) <= smem_per_block;
 }
 
+// Second generation of the warp kernel (vbfem_warp2.cuh): the (K_lam, K_mu) band table must fit in shared memory
+// next to the per-warp areas of twelve (or eight) warps.
+struct Warp2Plan {
+    bool ok = false;
+    int NW = 0, hb = 0, ldt = 0, tab_bytes = 0, warp_smem = 0;
+    size_t smem = 0;
+};
+static Warp2Plan warp2_plan(const PanelPlan &P, size_t smem_per_block) {
+    Warp2Plan W;
+    if (!P.ok || P.NB != kWarpNB || P.NQ <= kWarpNB || P.NQ > 128 || getenv("VBFEM_WARP_V1")) return W;
+    int hb = 0;
+    for (int e = 0; e < P.nele; ++e) {
+        int lo = 1 << 30, hi = -1;
+        for (int a = 0; a < 8; ++a) {
+            const int r = P.elm[8 * e + a];
+            if (r >= 0) {
+                lo = std::min(lo, r);
+                hi = std::max(hi, r);
+            }
+        }
+        if (hi >= 0) hb = std::max(hb, hi - lo);
+    }
+    W.hb = hb;
+    W.ldt = (hb + 2) & ~1;  // even row stride: rows hb + 1 apart land an odd number of 16-byte units apart
+    W.tab_bytes = P.npad * W.ldt * 16;
+    W.warp_smem = warp2_smem_per_warp(5);
+    int nw = 0;
+    if (const char *e = getenv("VBFEM_WARP_NW")) nw = atoi(e);
+    for (int NW : {12, 8}) {
+        if (nw && NW != nw) continue;
+        if ((size_t)W.tab_bytes + (size_t)NW * W.warp_smem + 64 <= smem_per_block) {
+            W.NW = NW;
+            W.smem = (size_t)W.tab_bytes + (size_t)NW * W.warp_smem;
+            W.ok = true;
+            break;
+        }
+    }
+    return W;
+}
+
 extern "C" const char *vbfem_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vbfem_create(vbfem_t **out, const vbfem_mesh *m, int device) {
@@ -1801,6 +1842,98 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
         PanelPlan P = plan_panel(m, dof2band, n, kWarpNB, warp_kernel_batch());
         const int NW = warp_kernel_warps(P, (size_t)prop.sharedMemPerBlockOptin);
         const int warp_smem = warp_kernel_smem(P);
+        const Warp2Plan W2 = warp2_plan(P, (size_t)prop.sharedMemPerBlockOptin);
+        if (warp_kernel_ok(P, NW, (size_t)prop.sharedMemPerBlockOptin) && W2.ok) {
+            // ---- second generation: K = lambda K_lam + mu K_mu from the band table in shared memory
+            WarpModel &Q = h->WM;
+            Q.n = P.n;
+            Q.off = P.off;
+            Q.npad = P.npad;
+            Q.NQ = P.NQ;
+            Q.R = 0;
+            Q.nele = ne;
+            Q.batch = 0;
+            Q.obs_loc[0] = P.obs_loc[0];
+            Q.obs_loc[1] = P.obs_loc[1];
+            Q.warp_smem = W2.warp_smem;
+            Q.tab_bytes = W2.tab_bytes;
+            Q.ldt = W2.ldt;
+            Q.hb = W2.hb;
+            Q.cmagic = 65536u / (unsigned)(W2.hb + 1) + 1u;
+            bool magic_ok = true;
+            for (int id = 0; id < 8 * (W2.hb + 1); ++id)
+                magic_ok &= (int)(((unsigned)id * Q.cmagic) >> 16) == id / (W2.hb + 1);
+            Q.rhsmask[0] = Q.rhsmask[1] = 0;
+            for (int q = 0; q < P.NQ; ++q)
+                for (int i = 0; i < 64; ++i)
+                    if (P.rhs0[(size_t)q * 64 + i] != 0.0) Q.rhsmask[q >> 6] |= 1ull << (q & 63);
+            warp_fn ks[3];
+            if (W2.NW == 8) {
+                ks[0] = fem_warp2_kernel<0, 8>; ks[1] = fem_warp2_kernel<1, 8>; ks[2] = fem_warp2_kernel<2, 8>;
+            } else {
+                ks[0] = fem_warp2_kernel<0, 12>; ks[1] = fem_warp2_kernel<1, 12>; ks[2] = fem_warp2_kernel<2, 12>;
+            }
+            bool fits = magic_ok;
+            for (int q = 0; q < 3 && fits; ++q) {
+                cudaError_t e1 = allow_max_smem(ks[q]);
+                int nb = 0;
+                if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ks[q], W2.NW * 32, W2.smem);
+                if (e1 != cudaSuccess || nb < 1) {
+                    fits = false;
+                    cudaGetLastError();
+                }
+                h->kern_warp[q] = ks[q];
+            }
+            if (fits) {
+                // unit element matrices on the device (the same shapef_q4 / accumulate_kt as every kernel), summed on
+                // the host in element order into the band table
+                int rc2 = upload(h, P.ecoord, &Q.ecoord);
+                if (rc2) return -2;
+                double *dke = nullptr;
+                CU(cudaMalloc(&dke, (size_t)ne * 72 * sizeof(double)));
+                warp2_unit_element_kernel<<<(ne + 63) / 64, 64>>>(Q.ecoord, ne, m->thk, dke);
+                std::vector<double> hke((size_t)ne * 72);
+                cudaError_t ce = cudaMemcpy(hke.data(), dke, hke.size() * sizeof(double), cudaMemcpyDeviceToHost);
+                cudaFree(dke);
+                CU(ce);
+                std::vector<double> tab((size_t)P.npad * W2.ldt * 2, 0.0);
+                for (int r = 0; r < P.off; ++r) tab[((size_t)r * W2.ldt) * 2 + 1] = 1.0;  // pad rows: pivot mu, decoupled
+                std::vector<int> pos(ne);
+                for (int k = 0; k < ne; ++k) pos[P.eord[k]] = k;
+                for (int e = 0; e < ne; ++e)
+                    for (int a = 0; a < 8; ++a)
+                        for (int q = 0; q <= a; ++q) {
+                            const int ra = P.elm[8 * e + a], rq = P.elm[8 * e + q];
+                            if (ra < 0 || rq < 0) continue;
+                            const int rr = std::max(ra, rq), cc = std::min(ra, rq);
+                            double *dst = &tab[((size_t)rr * W2.ldt + (rr - cc)) * 2];
+                            dst[0] += hke[(size_t)pos[e] * 72 + tri(a, q)];
+                            dst[1] += hke[(size_t)pos[e] * 72 + 36 + tri(a, q)];
+                        }
+                const double *dtab = nullptr;
+                rc2 |= upload(h, tab, &dtab);
+                Q.ktab = reinterpret_cast<const double2 *>(dtab);
+                rc2 |= upload(h, P.rhs0, &Q.rhs0);
+                if (rc2) return -2;
+                const long long nwarps = (long long)h->num_sms * W2.NW;
+                Q.lws_stride = (long long)P.NQ * (kWarpNB + 2) * 64;
+                void *pl = nullptr;
+                CU(cudaMalloc(&pl, (size_t)nwarps * Q.lws_stride * sizeof(double)));
+                h->dev_allocs.push_back(pl);
+                Q.lws = (double *)pl;
+                h->warp_nw = W2.NW;
+                h->block = W2.NW * 32;
+                h->ctas_per_sm = 1;
+                h->smem_bytes = W2.smem;
+                h->variant = 4;
+                h->n_real = n;
+                h->PM.NB = kWarpNB;
+                h->PM.R = 0;
+                guard.p = nullptr;
+                *out = h;
+                return 0;
+            }
+        }
         if (warp_kernel_ok(P, NW, (size_t)prop.sharedMemPerBlockOptin)) {
             WarpModel &Q = h->WM;
             Q.n = P.n;
@@ -2104,9 +2237,11 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
         const size_t per_block = (size_t)std::min<int64_t>(smem_per_sm > 0 ? smem_per_sm : 233472, 232448);
         const int NW = warp_kernel_warps(Q, per_block);
         if (warp_kernel_ok(Q, NW, per_block)) {
+            const Warp2Plan W2 = warp2_plan(Q, per_block);
             out[0] = 4;
             out[3] = out[4] = out[5] = 0;
-            out[6] = (int64_t)NW * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
+            out[6] = W2.ok ? (int64_t)W2.smem : (int64_t)NW * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
+            out[7] = W2.ok ? 2 : 1;  // generation of the warp kernel
             return 0;
         }
     }

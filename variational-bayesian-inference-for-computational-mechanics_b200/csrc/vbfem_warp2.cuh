@@ -1,152 +1,105 @@
-// vbfem_warp.cuh -- narrow bands (Cook 20x10: n = 440, half bandwidth 25): ONE WARP per Monte-Carlo sample,
-// a dozen samples in flight per SM, the whole elimination window in REGISTERS.
+// vbfem_warp2.cuh -- the warp-per-sample kernel (vbfem_warp.cuh), second generation: NO per-sample element kernels.
 //
-// Same mathematics as the blocked panel kernel (vbfem_panel.cuh): 8x8 blocks, per panel the diagonal block is
-// factored (LDL^T) and its unit factor inverted, the blocks below become V = X L11^-T (two FP64 tensor-core
-// MMAs m8n8k4 per block) and the trailing window takes C -= L V^T (two more per block).  What is different:
-//   * the window -- (NB+1)(NB+2)/2 = 10 blocks for NB = 3, plus NB+1 right-hand-side blocks -- never leaves
-//     the register file: an 8x8 block in the MMA's C-fragment layout (lane (g, t) holds [g][2t], [g][2t+1]) IS
-//     the A and the B fragment of the next product when the contraction index is split {0,2,4,6} / {1,3,5,7},
-//     so solve -> scale -> update chain from registers to registers;
-//   * the window slides for free: the update of block (I, J) is written to the registers of block
-//     (I-1, J-1) (the MMA's D operand), nothing is copied;
-//   * there is no block barrier and no cross-warp traffic in the sample loop.  Warps of a CTA share nothing
-//     but the read-only tables; each pulls its next sample from a shared-memory counter;
-//   * shared memory per warp is the ring of element matrices (just-in-time batches of 32, lane = element:
-//     the per-element Q4 Gauss-point kernels of src/mat_subroutine_tf.py:23-110 upstream), the staging area
-//     of the block row that enters the window (atomics-free gather, same host table as the panel kernel) and
-//     a 1.5 KB exchange area for the diagonal block: ~17 KB, so 12-13 samples are resident per SM where the
-//     on-chip two-front kernel (97 KB of factor per sample) holds two.  The latency of one sample's pivot
-//     chain is hidden by the other samples; DMMA work (tensor pipe) and the diagonal-block factorisation
-//     (FP64 pipe) of different warps overlap.
-// With an adjoint (fused or Jacobian mode) the scaled panels leave for a per-warp slab in global memory as
-// plain 16-byte stores from the fragments and come back, fragment by fragment, in ONE reverse pass that
-// back-substitutes u and the adjoint vectors together -- again registers only.
-// Replaces tf.linalg.solve (src/fem_solver_tf.py:137 upstream) and its gradient.
+// The material of this path is isotropic plane strain with ONE (E, nu) per sample (src/mat_subroutine_tf.py:283-330
+// upstream): C_t = lambda m m^T + mu diag(2, 2, 1), hence K(sample) = lambda K_lam + mu K_mu with two
+// SAMPLE-INDEPENDENT band matrices.  They are assembled once per mesh (element matrices by the same device routines
+// the other kernels use -- shapef_q4 / accumulate_kt with (lambda, mu) = (1, 0) and (0, 1) -- summed on the host in
+// element order) and live in shared memory as (K_lam, K_mu) pairs in band form, [row][row - col], 183 KB for Cook
+// 20x10, shared by the twelve warps of the CTA.  Per sample:
+//   * the block row entering the register window is eight predicated 16-byte loads and sixteen FMAs per lane --
+//     the first generation computed 200 element matrices per sample (Gauss loops, 36 accumulators, a ring of 44
+//     matrices in shared memory per warp) and gathered the row through a packed index table;
+//   * the adjoint contraction -psi^T (dK/dlambda, dK/dmu) u = -(psi^T K_lam u, psi^T K_mu u) runs INSIDE the
+//     reverse pass on the same table: as soon as panel p of u and psi leaves the back substitution it enters a
+//     40-row window in shared memory and block column p of the band (208 entries) is contracted, seven entries per
+//     lane.  No solution vector is ever stored, no shape function re-evaluated.
+// Everything else -- the 8x8 blocked LDL^T in registers, FP64 tensor-core MMAs, the factor slab, the observation
+// trick -- is the first generation's.  Results differ from it by rounding only (1e-13 relative).
 #pragma once
-#include "vbfem_panel.cuh"
+#include "vbfem_warp.cuh"
 
 namespace vbfem {
 
-constexpr int kWarpNB = 3;      // block half bandwidth of the register window (8x8 blocks)
-constexpr int kWarpBatch = 32;  // element matrices per just-in-time batch (lane = element); WarpModel::batch may be smaller
-constexpr int kWarpFixed = 640 + (kWarpNB + 1) * 512;  // bytes per warp ahead of the element ring: Minv^T and 1/d of the last panel, flag, staging area
+constexpr int kWarp2Fixed = 640;          // Minv^T and 1/d of the last panel, flag
+constexpr int kWarp2Small = 1152;         // small vectors of the observation / reverse pass
+constexpr int kWarp2WinRows = 40;         // rows of u / psi the contraction of one block column can touch (33) -> 5 panels
+__host__ __device__ constexpr int warp2_smem_per_warp(int nv) { return kWarp2Fixed + kWarp2Small + kWarp2WinRows * nv * 8; }
 
-struct WarpModel {
-    int n, off, npad, NQ, R, nele;
-    int batch;                   // element matrices per just-in-time batch (<= 32: lanes >= batch idle)
-    int obs_loc[2];              // row inside the last panel of the observed node's (x, y) dof, -1 if supported
-    int warp_smem;               // bytes of shared memory per warp
-    int nent, tab_bytes;         // gather entries; bytes of the CTA-shared tables ahead of the per-warp areas
-    // Gather table, one 64-bit word per target entry of the lower band: bits [0, 44) four 11-bit element-ring
-    // entries slot * 36 + tri (unused: the zero entry), bits [44, 52) the target d * 64 + g * 8 + c (d: block
-    // diagonal).  Row table: {first gather entry of block row q, elements (first-use order) the row needs
-    // | 1 << 30 if the row has a non-zero initial right-hand-side block}.  Both are copied to shared memory once
-    // per CTA.
-    const unsigned long long *gpack;
-    const int2 *rowtab;          // [NQ+1]
-    const double *rhs0;          // [NQ][64] initial right-hand-side blocks [a][c]
-    const double *ecoord;        // [nele][4][2] nodal coordinates, first-use order
-    const int *elm;              // [nele][8] padded band row of each element dof, -1 if supported; first-use order
-    int x_in_smem;               // fused adjoint: u and psi live in the (then idle) element ring instead of xws
-    double *lws;                 // per-warp factor slab [NQ][NB+2][64]
-    long long lws_stride;
-    double *xws;                 // per-warp solution vectors [5][npad]
-    long long xws_stride;
-    // second generation (vbfem_warp2.cuh): K = lambda K_lam + mu K_mu from a sample-independent band table
-    const double2 *ktab;         // (K_lam, K_mu)[npad][ldt], entry (r, c) at [r][r - c]; copied to shared memory per CTA
-    int ldt, hb;                 // row stride (even, >= hb + 1), half bandwidth in padded rows
-    unsigned cmagic;             // id / (hb + 1) == (id * cmagic) >> 16 for id < 8 (hb + 1)
-    unsigned long long rhsmask[2];  // bit q: block row q has a non-zero initial right-hand-side block
-};
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// One just-in-time batch of element matrices (lane = element, first-use order) into the ring.  Kept out of line:
-// the 36 accumulators and the shape-function state would otherwise sit on top of the register window.
-__device__ __noinline__ void warp_element_batch(const double *__restrict__ ecoord, double *__restrict__ ke, int k,
-                                                int nele, int R, double thk, double lam, double mu) {
+// Element matrices for unit Lame parameters: out[k][0][36] = K_lam of element k, out[k][1][36] = K_mu (lower triangle,
+// tri(a, q)); elements in the order of `ecoord`.  Runs once per mesh.
+__global__ void warp2_unit_element_kernel(const double *__restrict__ ecoord, int nele, double thk, double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nele) return;
-    Lame mat;
-    mat.lam = lam;
-    mat.mu = mu;
-    mat.szz = lam;
-    double xl[4], yl[4], kev[36];
-#pragma unroll
+    double xl[4], yl[4];
     for (int a = 0; a < 4; ++a) {
-        const double2 xy = reinterpret_cast<const double2 *>(ecoord + (size_t)8 * k)[a];
-        xl[a] = xy.x;
-        yl[a] = xy.y;
+        xl[a] = ecoord[8 * k + 2 * a];
+        yl[a] = ecoord[8 * k + 2 * a + 1];
     }
-#pragma unroll
-    for (int q = 0; q < 36; ++q) kev[q] = 0.0;
-#pragma unroll 1
-    for (int gp = 0; gp < 4; ++gp) {
-        ShapeQ4 sh;
-        shapef_q4(xl, yl, gp, thk, sh);
-        double sig[4];
-        Tangent C;
-        mat_isotropic_plane_strain(mat, 0.0, 0.0, 0.0, sig, C);
-        accumulate_kt(sh, C, kev);
+    for (int which = 0; which < 2; ++which) {
+        Lame mat;
+        mat.lam = which ? 0.0 : 1.0;
+        mat.mu = which ? 1.0 : 0.0;
+        mat.szz = mat.lam;
+        double kev[36];
+        for (int q = 0; q < 36; ++q) kev[q] = 0.0;
+        for (int gp = 0; gp < 4; ++gp) {
+            ShapeQ4 sh;
+            shapef_q4(xl, yl, gp, thk, sh);
+            double sig[4];
+            Tangent C;
+            mat_isotropic_plane_strain(mat, 0.0, 0.0, 0.0, sig, C);
+            accumulate_kt(sh, C, kev);
+        }
+        for (int q = 0; q < 36; ++q) out[(size_t)k * 72 + which * 36 + q] = kev[q];
     }
-    double2 *dst = reinterpret_cast<double2 *>(ke + (k % R) * 36);
-#pragma unroll
-    for (int q = 0; q < 18; ++q) dst[q] = make_double2(kev[2 * q], kev[2 * q + 1]);
 }
-
-#ifdef VBFEM_TIMELINE
-#define WTL_DECL long long wtl[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, wtl_t = clock64()
-#define WTL(i)                            \
-    do {                                  \
-        const long long now_ = clock64(); \
-        wtl[i] += now_ - wtl_t;           \
-        wtl_t = now_;                     \
-    } while (0)
-#define WTL_FLUSH                                                                   \
-    do {                                                                            \
-        if (A.timeline && lane == 0 && warp < 4)                                    \
-            for (int i_ = 0; i_ < 16; ++i_) A.timeline[(blockIdx.x * 4 + warp) * 16 + i_] = wtl[i_]; \
-    } while (0)
-#else
-#define WTL_DECL ((void)0)
-#define WTL(i) ((void)0)
-#define WTL_FLUSH ((void)0)
-#endif
 
 // MODE 0: y, h   MODE 1: y, h, gx = J^T (gy, gh)   MODE 2: y, h, J = d(y, h)/dx
 template <int MODE, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_constant__ DevModel M,
-                                                              const __grid_constant__ WarpModel Q,
-                                                              const __grid_constant__ Args A) {
+__global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_constant__ DevModel M,
+                                                               const __grid_constant__ WarpModel Q,
+                                                               const __grid_constant__ Args A) {
     constexpr int NB = kWarpNB, NB1 = NB + 1, LPB = (NB + 2) * 64;
     constexpr int NV = (MODE == 2) ? 5 : 2;
+    constexpr int NADJ = NV - 1;
+    constexpr int WR = kWarp2WinRows;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int next_i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const unsigned long long *gtab = reinterpret_cast<const unsigned long long *>(smraw);
-    const int2 *rowtab = reinterpret_cast<const int2 *>(smraw + (size_t)Q.nent * 8);
+    const double2 *ktab = reinterpret_cast<const double2 *>(smraw);  // (K_lam, K_mu)[row][row - col], row stride Q.ldt
+    const int ldt = Q.ldt;
     unsigned char *wsm = smraw + Q.tab_bytes + (size_t)warp * Q.warp_smem;
     double *stg = reinterpret_cast<double *>(wsm), *rd = stg + 64;  // the last panel's Minv^T and 1 / d (observations)
     int *flagp = reinterpret_cast<int *>(wsm + 576);
-    double *stage = reinterpret_cast<double *>(wsm + 640);  // NB+1 blocks of the entering row, by block diagonal
-    double *ke = reinterpret_cast<double *>(wsm + kWarpFixed);  // R element matrices (36 each), then 0.0, 1.0
-    // after the forward pass the staging area holds the small vectors of the observation / reverse pass
-    double *sW = stage, *nodew = stage + 64, *nodeL = stage + 80, *sG = stage + 96, *lf_last = stage + 104,
-           *obs = stage + 112;
+    double *small = reinterpret_cast<double *>(wsm + kWarp2Fixed);
+    double *sW = small, *nodew = small + 64, *nodeL = small + 80, *sG = small + 96, *lf_last = small + 104,
+           *obs = small + 112;
+    double *win = reinterpret_cast<double *>(wsm + kWarp2Fixed + kWarp2Small);  // [WR][NV]: u and the adjoint vectors
     const int NQ = Q.NQ;
     const int wid = blockIdx.x * NW + warp;
     double *lws = Q.lws + (size_t)wid * Q.lws_stride;
-    double *xws = Q.xws + (size_t)wid * Q.xws_stride;
     const double2 z2 = make_double2(0.0, 0.0);
     if (threadIdx.x == 0) next_i = 0;
-    for (int i = threadIdx.x; i < Q.nent; i += NW * 32) reinterpret_cast<unsigned long long *>(smraw)[i] = Q.gpack[i];
-    for (int i = threadIdx.x; i <= Q.NQ; i += NW * 32) reinterpret_cast<int2 *>(smraw + (size_t)Q.nent * 8)[i] = Q.rowtab[i];
-    if (lane == 0) {
-        ke[Q.R * 36] = 0.0;
-        ke[Q.R * 36 + 1] = 1.0;
+    {
+        const int nvec = Q.tab_bytes / 16;
+        const double2 *src = Q.ktab;
+        double2 *dst = reinterpret_cast<double2 *>(smraw);
+        for (int i = threadIdx.x; i < nvec; i += NW * 32) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+
+    // Entry (r, c) of the lower band sits at ktab[r * ldt + r - c].  Lane (g, t) of block (q, q - d) holds
+    // (r, c) = (8 q + g, 8 (q - d) + 2 t + {0, 1}): the in-row offsets 8 d + g - 2 t - {0, 1} do not depend on q.
+    // Outside [0, hb] (and above the diagonal of the diagonal block) the entry is zero.
+    int koff[NB1];
+    unsigned kmask = 0;
+#pragma unroll
+    for (int d = 0; d < NB1; ++d) {
+        const int o0 = 8 * d + g - 2 * t;  // component x; component y is o0 - 1
+        koff[d] = o0;
+        if (o0 >= 0 && o0 <= Q.hb) kmask |= 1u << (2 * d);
+        if (o0 - 1 >= 0 && o0 - 1 <= Q.hb) kmask |= 2u << (2 * d);
+    }
 
     for (;;) {
         int it = 0;
@@ -173,38 +126,23 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
             nu_ = 0.5 / (1.0 + exp(-M.theta_std[1] * x1 - M.theta_mean[1]));
         }
         const Lame mat = lame_from_E_nu(E_, nu_);
+        const double lam = mat.lam, mu = mat.mu;
         if (lane == 0) *flagp = 0;
         WTL_DECL;
 
-        int computed = 0;  // element matrices (first-use order) in the ring so far
-        // Block row q enters the window in two steps around a warp barrier: (a) the element matrices the row is the
-        // first to need (just-in-time batch) and a cleared staging area, (b) the atomics-free gather of the row's
-        // lower-band entries from the ring (at most 96 per row: three predicated trips, no loop, so that the
-        // scheduler can interleave them with the diagonal block's factorisation).
-        auto row_prepare = [&](int q) {
-            const int need = rowtab[q].y & 0x3fffffff;
-            while (computed < need) {
-                warp_element_batch(Q.ecoord, ke, lane < Q.batch ? computed + lane : Q.nele, Q.nele, Q.R, M.thk, mat.lam,
-                                   mat.mu);
-                computed += Q.batch;
+        // block (q, q - d) of K = lambda K_lam + mu K_mu in the fragment layout
+        auto kblock = [&](int q, int d) -> double2 {
+            const double2 *row = ktab + (size_t)(8 * q + g) * ldt + koff[d];
+            double2 r = z2;
+            if (kmask & (1u << (2 * d))) {
+                const double2 a = row[0];
+                r.x = fma(lam, a.x, mu * a.y);
             }
-            double2 *st2 = reinterpret_cast<double2 *>(stage);
-#pragma unroll
-            for (int i = 0; i < NB1; ++i) st2[i * 32 + lane] = z2;
-        };
-        auto row_gather = [&](int q) {
-            const int e0 = rowtab[q].x, e1 = rowtab[q + 1].x;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int i = e0 + lane + 32 * r;
-                if (i < e1) {
-                    const unsigned long long w = gtab[i];
-                    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
-                    const double v = ((ke[lo & 2047u] + ke[(lo >> 11) & 2047u]) + ke[(unsigned)(w >> 22) & 2047u]) +
-                                     ke[(hi >> 1) & 2047u];
-                    stage[(hi >> 12) & 255u] = v;
-                }
+            if (kmask & (2u << (2 * d))) {
+                const double2 a = row[-1];
+                r.y = fma(lam, a.x, mu * a.y);
             }
+            return r;
         };
 
         // ---------------- the window: block (p+I, p+J) in W[I][J] (J <= I), right-hand sides of block column p+J in Rh[J]
@@ -217,20 +155,14 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
         }
 #pragma unroll
         for (int q = 0; q < NB1; ++q) {
-            row_prepare(q);
-            __syncwarp();
-            row_gather(q);
-            __syncwarp();
 #pragma unroll
-            for (int d = 0; d <= q; ++d) W[q][q - d] = reinterpret_cast<const double2 *>(stage)[d * 32 + lane];
-            if (rowtab[q].y >> 30) Rh[q] = __ldg(reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64) + lane);
-            __syncwarp();
+            for (int d = 0; d <= q; ++d) W[q][q - d] = kblock(q, d);
+            if ((Q.rhsmask[q >> 6] >> (q & 63)) & 1) Rh[q] = __ldg(reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64) + lane);
         }
 
         WTL(0);
         // ---------------- panels
         double gacc = 0.0;  // partial sum over this lane's columns of G[g] = q_g^T K^-1 f
-        const double2 idf = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);  // identity fragment
         double2 mi, mit, r2;  // of the current panel: Minv[g][2t..2t+1], its transpose, 1 / d of columns 2t, 2t+1
         warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);  // diagonal block of panel 0
 #pragma unroll 1
@@ -256,14 +188,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
             }
             if (MODE > 0) {
                 // the scaled panel leaves for the slab: [0] Minv^T, [1..NB] L^T blocks, [NB+1] D^-1 z rows, transposed
-                // on the tensor core (I * L^T leaves the transposed block in the C-fragment layout)
+                // in the fragment layout by four shuffles per block
                 double2 *pan = reinterpret_cast<double2 *>(lws + (size_t)p * LPB);
                 __stcs(pan + lane, mit);
 #pragma unroll
                 for (int b = 0; b < NB1; ++b) {
-                    // transpose in the fragment layout: lane (g, t) needs (L[2t][g], L[2t+1][g]), held by lanes
-                    // (2t, g >> 1) and (2t + 1, g >> 1) in component g & 1 -- four shuffles instead of two MMAs on
-                    // the shared FP64 / tensor pipe
                     const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
                     const double ax = __shfl_sync(kFull, Ln[b].x, s0), ay = __shfl_sync(kFull, Ln[b].y, s0);
                     const double bx = __shfl_sync(kFull, Ln[b].x, s1), by = __shfl_sync(kFull, Ln[b].y, s1);
@@ -290,30 +219,21 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 Rh[J - 1] = c;
             }
             WTL(4);
-            // ---- the diagonal block of panel p+1 is factored WHILE block row p+NB+1 is gathered into the staging area:
-            //      one instruction stream, two independent dependency chains
+            // ---- block row p+NB+1 enters the window (table loads, independent of everything in flight) while the
+            //      diagonal block of panel p+1 is factored: one instruction stream, two independent chains
             const int q = p + NB1;
-            if (p + 1 < NQ) {
-                if (q < NQ) {
-                    row_prepare(q);
-                    __syncwarp();
-                    row_gather(q);
-                }
-                warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);
-                __syncwarp();
-            }
-            WTL(2);
             if (q < NQ) {
 #pragma unroll
-                for (int d = 0; d <= NB; ++d) W[NB][NB - d] = reinterpret_cast<const double2 *>(stage)[d * 32 + lane];
+                for (int d = 0; d <= NB; ++d) W[NB][NB - d] = kblock(q, d);
                 Rh[NB] = z2;
-                if (rowtab[q].y >> 30) Rh[NB] = __ldg(reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64) + lane);
+                if ((Q.rhsmask[q >> 6] >> (q & 63)) & 1) Rh[NB] = __ldg(reinterpret_cast<const double2 *>(Q.rhs0 + (size_t)q * 64) + lane);
             } else {
 #pragma unroll
                 for (int d = 0; d <= NB; ++d) W[NB][d] = z2;
                 Rh[NB] = z2;
             }
-            WTL(8);
+            if (p + 1 < NQ) warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);
+            WTL(2);
         }
 
         WTL(1);
@@ -364,6 +284,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
             sW[lane] = 0.0;
             sW[32 + lane] = 0.0;
             if (lane < 16) nodew[lane] = 0.0;
+            for (int i = lane; i < WR * NV; i += 32) win[i] = 0.0;
             __syncwarp();
             if (lane == 0) {
                 sW[0] = 1.0;
@@ -408,8 +329,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
             double2 X[NB1];  // X[b] = -x_(p+b), b = 1..NB
 #pragma unroll
             for (int b = 0; b < NB1; ++b) X[b] = z2;
-            // u and the adjoint vectors: in the element ring (idle after the forward pass) when they fit, else global
-            double *xv = (MODE == 1 && Q.x_in_smem) ? ke : xws;
+            double sl[NADJ], sm[NADJ];  // psi_v^T K_lam u, psi_v^T K_mu u: this lane's share
+#pragma unroll
+            for (int v = 0; v < NADJ; ++v) sl[v] = sm[v] = 0.0;
+            // contraction entries of one block column: (c, o) = local column, row - column, 8 x (hb + 1) of them
+            const int hb1 = Q.hb + 1, ncon = 8 * hb1;
+            int wbase = (8 * (NQ - 1)) % WR;  // window slot of row 8 p
             double2 cur[NB + 2], nxt[NB + 2], nx2[NB + 2];  // panels p, p-1, p-2: loads two panels ahead of their use
             constexpr int kAhead = 4;  // panels on their way into L2 ahead of the register buffers
             if (lane < (NB + 2) * 4)
@@ -452,57 +377,40 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp_kernel(const __grid_const
                 }
                 double2 x = z2;
                 block_mma<true>(x, d, cur[0], lane);
-                if (g < NV) *reinterpret_cast<double2 *>(xv + (size_t)g * Q.npad + 8 * p + 2 * t) = x;
 #pragma unroll
                 for (int b = NB; b > 1; --b) X[b] = X[b - 1];
                 X[1] = make_double2(-x.x, -x.y);
+                // ---- panel p of u and the adjoint vectors enters the window; block column p of the band is contracted
+                __syncwarp();  // the previous column's reads of the slots about to be overwritten are done
+                if (g < NV) {
+                    win[(wbase + 2 * t) * NV + g] = x.x;
+                    win[(wbase + 2 * t + 1) * NV + g] = x.y;
+                }
+                __syncwarp();
+                for (int id = lane; id < ncon; id += 32) {
+                    const int c = (int)(((unsigned)id * Q.cmagic) >> 16), o = id - c * hb1;
+                    const int r = 8 * p + c + o;
+                    if (r < Q.npad) {
+                        const double2 kk = ktab[(size_t)r * ldt + o];
+                        int sr = wbase + c + o;
+                        sr -= (sr >= WR) ? WR : 0;
+                        const double *xr = win + sr * NV, *xc = win + (wbase + c) * NV;
+                        const double ur = xr[0], uc = xc[0];
+#pragma unroll
+                        for (int v = 0; v < NADJ; ++v) {
+                            const double pr = xr[1 + v], pc = xc[1 + v];
+                            const double sv = o ? fma(pr, uc, pc * ur) : pr * ur;
+                            sl[v] = fma(kk.x, sv, sl[v]);
+                            sm[v] = fma(kk.y, sv, sm[v]);
+                        }
+                    }
+                }
+                wbase -= 8;
+                wbase += (wbase < 0) ? WR : 0;
             }
             __syncwarp();
 
             WTL(6);
-            // ---------------- element-wise contraction -psi^T (dK/dp) u + explicit dh/dp, chained to x
-            constexpr int NADJ = NV - 1;
-            double sl[NADJ], sm[NADJ];
-#pragma unroll
-            for (int v = 0; v < NADJ; ++v) sl[v] = sm[v] = 0.0;
-            for (int e = lane; e < Q.nele; e += 32) {  // first-use order: coordinates and band rows are contiguous records
-                double xl[4], yl[4], ue[8];
-                int lm[8];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double2 xy = __ldg(reinterpret_cast<const double2 *>(Q.ecoord + (size_t)8 * e) + a);
-                    xl[a] = xy.x;
-                    yl[a] = xy.y;
-                }
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const int4 r4 = __ldg(reinterpret_cast<const int4 *>(Q.elm + (size_t)8 * e) + a);
-                    lm[4 * a] = r4.x;
-                    lm[4 * a + 1] = r4.y;
-                    lm[4 * a + 2] = r4.z;
-                    lm[4 * a + 3] = r4.w;
-                }
-#pragma unroll
-                for (int a = 0; a < 8; ++a) ue[a] = (lm[a] >= 0) ? xv[lm[a]] : 0.0;
-#pragma unroll 1
-                for (int gp = 0; gp < 4; ++gp) {
-                    ShapeQ4 sh;
-                    shapef_q4(xl, yl, gp, M.thk, sh);
-                    double uxx, uyy, uxy;
-                    strain_q4(sh, ue, uxx, uyy, uxy);
-#pragma unroll
-                    for (int v = 0; v < NADJ; ++v) {
-                        const double *pv = xv + (size_t)(v + 1) * Q.npad;
-                        double pe[8], pxx, pyy, pxy, cl, cm;
-#pragma unroll
-                        for (int a = 0; a < 8; ++a) pe[a] = (lm[a] >= 0) ? pv[lm[a]] : 0.0;
-                        strain_q4(sh, pe, pxx, pyy, pxy);
-                        mat_tangent_param_contract(pxx, pyy, pxy, uxx, uyy, uxy, cl, cm);
-                        sl[v] = fma(sh.dvol, cl, sl[v]);
-                        sm[v] = fma(sh.dvol, cm, sm[v]);
-                    }
-                }
-            }
 #pragma unroll
             for (int v = 0; v < NADJ; ++v)
 #pragma unroll
