@@ -31,7 +31,13 @@ names = ["window fill (first 4 rows: elements, gather) + first diagonal block", 
          "solve + G + panel store", "trailing update", "reverse-pass set-up", "reverse pass", "contraction + store",
          "entering row: fragments from the staging area"]
 idx = [0, 1, 2, 3, 4, 8, 5, 6, 7]
-tot = t[:, :9].sum(1).mean()
+if eng.info["panel_ring"] == 0:   # second generation (vbfem_warp2.cuh)
+    names = ["window fill (first 4 rows from the band table) + first diagonal block", "loop top / observations",
+             "entering row from the band table || next diagonal block (LDL^T, inverse)", "solve + G + panel store",
+             "trailing update", "reverse-pass set-up", "final reduction + store", "status", "-",
+             "reverse pass: slab loads + back substitution MMAs", "reverse pass: window write + band contraction"]
+    idx = [0, 1, 2, 3, 4, 5, 9, 10, 6, 7]
+tot = t[:, :11].sum(1).mean()
 print(f"{mode}: {t.shape[0]} warps, mean cycles per sample {tot:.0f}  ({eng.info})")
 for i in idx:
     v = t[:, i].mean()

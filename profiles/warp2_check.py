@@ -32,7 +32,10 @@ yg = torch.tensor(g["x"], device=dev)
 yy, hh = eng.forward(yg); torch.cuda.synchronize()
 print("golden y", float(np.max(np.abs(yy.cpu().numpy() - g["y"]) / np.abs(g["y"]))), "h", float(np.max(np.abs(hh.cpu().numpy() - g["h"]) / np.abs(g["h"]))))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, e in (("v1", ref), ("v2", eng)):
+os.environ["VBFEM_WARP2_NW16"] = "0"
+e12 = pkg.CookFemEngine(md, device=0)
+del os.environ["VBFEM_WARP2_NW16"]
+for name, e in (("v1", ref), ("v2 12 warps", e12), ("v2", eng)):
     for mode in ("fwd", "adj", "jac"):
         f = {"fwd": lambda: e.forward(x), "adj": lambda: e.forward_backward(x, gy, gh), "jac": lambda: e.forward_jac(x)}[mode]
         f(); f(); torch.cuda.synchronize()

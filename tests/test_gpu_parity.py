@@ -130,6 +130,36 @@ def test_front_kernel_full_batch_vs_warp_kernel(pkg, engine, golden_model, monke
     front.close()
 
 
+def test_warp_kernel_generations_agree(pkg, engine, golden_model, torch_oracle, monkeypatch):
+    """Second generation of the warp kernel (K = lambda K_lam + mu K_mu from the band table, contraction on the same
+    table) against the first (VBFEM_WARP_V1=1: element matrices per sample, element-wise contraction) on all 4096
+    benchmark samples, in all three modes, with sixteen and with twelve warps per SM; the oracle on a slice."""
+    import bench
+    assert engine.info["kernel_variant"] == 4 and engine.info["panel_ring"] == 0      # the default is generation 2
+    monkeypatch.setenv("VBFEM_WARP_V1", "1")
+    v1 = pkg.CookFemEngine(golden_model, device=0)
+    monkeypatch.delenv("VBFEM_WARP_V1")
+    monkeypatch.setenv("VBFEM_WARP2_NW16", "0")
+    v2_12 = pkg.CookFemEngine(golden_model, device=0)
+    assert v1.info["panel_ring"] == 44 and v2_12.info["panel_ring"] == 0
+    x, gy, gh = (_t(a, engine) for a in bench.inputs(0))
+    ref = v1.forward_backward(x, gy, gh)
+    jref = v1.forward_jac(x)[2]
+    for eng in (engine, v2_12):
+        for u, v in zip(eng.forward_backward(x, gy, gh), ref):
+            assert relerr(u.cpu().numpy(), v.cpu().numpy()) < 1e-11
+        for u, v in zip(eng.forward(x), ref[:2]):
+            assert relerr(u.cpu().numpy(), v.cpu().numpy()) < 1e-11
+        assert relerr(eng.forward_jac(x)[2].cpu().numpy(), jref.cpu().numpy()) < 1e-11
+        assert eng.status(x.shape[0])[0] == 0
+    xs, gys, ghs = (a[:96] for a in bench.inputs(0))
+    yo, ho, gxo = torch_oracle.vjp(xs, gys, ghs)
+    y, h, gx = v2_12.forward_backward(_t(xs, engine), _t(gys, engine), _t(ghs, engine))
+    assert max(relerr(y.cpu().numpy(), yo), relerr(h.cpu().numpy(), ho), relerr(gx.cpu().numpy(), gxo)) < TOL
+    v1.close()
+    v2_12.close()
+
+
 def test_jacobian_vs_reference_finite_differences(engine, golden):
     """Gradient pinned to the reference's OWN code: d(y, h)/dx from the CUDA Jacobian mode against
     central differences of the unmodified reference NumPy twin (golden fd_x / fd_jac)."""

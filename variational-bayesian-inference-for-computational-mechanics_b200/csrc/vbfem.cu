@@ -1021,6 +1021,10 @@ struct vbfem_handle {
     WarpModel WM{};
     warp_fn kern_warp[3] = {nullptr, nullptr, nullptr};
     int warp_nw = 0;
+    // second generation, forward / fused-adjoint modes: sixteen warps per SM when registers (128) and shared memory allow
+    warp_fn kern_warp16[2] = {nullptr, nullptr};
+    size_t warp16_smem = 0;
+    int warp16_per_warp = 0;
     // generic kernel configuration (fields mode, meshes neither fast kernel takes)
     DevModel M_gen{};
     int gen_block = 0, gen_ctas = 0;
@@ -1915,7 +1919,33 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
                 Q.ktab = reinterpret_cast<const double2 *>(dtab);
                 rc2 |= upload(h, P.rhs0, &Q.rhs0);
                 if (rc2) return -2;
-                const long long nwarps = (long long)h->num_sms * W2.NW;
+                long long nwarps = (long long)h->num_sms * W2.NW;
+                {   // sixteen warps for MODE 0 / 1 (per-warp window of u and ONE adjoint vector)
+                    const int pw = warp2_smem_per_warp(2);
+                    const size_t sm16 = (size_t)W2.tab_bytes + (size_t)16 * pw;
+                    const char *e16 = getenv("VBFEM_WARP2_NW16");
+                    if (W2.NW == 12 && sm16 + 64 <= (size_t)prop.sharedMemPerBlockOptin && !(e16 && atoi(e16) == 0) &&
+                        !getenv("VBFEM_WARP_NW")) {
+                        warp_fn k16[2] = {fem_warp2_kernel<0, 16>, fem_warp2_kernel<1, 16>};
+                        bool ok16 = true;
+                        for (int q = 0; q < 2 && ok16; ++q) {
+                            cudaError_t e1 = allow_max_smem(k16[q]);
+                            int nb = 0;
+                            if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k16[q], 512, sm16);
+                            if (e1 != cudaSuccess || nb < 1) {
+                                ok16 = false;
+                                cudaGetLastError();
+                            }
+                        }
+                        if (ok16) {
+                            h->kern_warp16[0] = k16[0];
+                            h->kern_warp16[1] = k16[1];
+                            h->warp16_smem = sm16;
+                            h->warp16_per_warp = pw;
+                            nwarps = (long long)h->num_sms * 16;
+                        }
+                    }
+                }
                 Q.lws_stride = (long long)P.NQ * (kWarpNB + 2) * 64;
                 void *pl = nullptr;
                 CU(cudaMalloc(&pl, (size_t)nwarps * Q.lws_stride * sizeof(double)));
@@ -2425,7 +2455,13 @@ static int launch(vbfem_handle *h, Args &a, void *stream) {
         CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * 4 * 16 * sizeof(long long), st));
         a.timeline = h->timeline;
 #endif
-        h->kern_warp[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->WM, a);
+        if (mode < 2 && h->kern_warp16[mode]) {
+            WarpModel wm = h->WM;
+            wm.warp_smem = h->warp16_per_warp;
+            h->kern_warp16[mode]<<<(unsigned)grid, 512, h->warp16_smem, st>>>(h->M_gen, wm, a);
+        } else {
+            h->kern_warp[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->WM, a);
+        }
     } else if (h->variant == 3 && !fields) {
         const long long grid = std::min<long long>(a.N, (long long)h->num_sms * h->ctas_per_sm);
 #ifdef VBFEM_TIMELINE

@@ -167,6 +167,65 @@ __device__ __forceinline__ void warp_diag_fragment(double2 D, double2 &Minv, dou
     MinvT = make_double2((g & 1) ? ay : ax, (g & 1) ? by : bx);
 }
 
+// The same factorisation with 2x2 PIVOT BLOCKS: columns (k, k+1) are eliminated together.  With a = D[k][k],
+// b = D[k+1][k], c = D[k+1][k+1] and det = a c - b^2 (= a d_(k+1)), the trailing entries take
+//     D[i][j] -= (p_i (c p_j - b q_j) + q_i (a q_j - b p_j)) / det,      p = D[.][k], q = D[.][k+1],
+// where everything but 1 / det is computed while the reciprocal is in flight: the dependency chain of a PAIR of
+// pivots is shuffle -> det (2 FP64) -> reciprocal -> one FMA, against two times shuffle -> reciprocal -> multiply ->
+// FMA column by column.  A pivot pair sits in ONE set of lanes (t == k / 2, components x and y), so the shuffles
+// stay the same in number.  Mathematically identical to two LDL^T steps (1 / d_k = 1 / a, 1 / d_(k+1) = a / det,
+// L[i][k] = p_i / a, L[i][k+1] = (a q_i - b p_i) / det); the pivot check covers a and det (both must be positive).
+__device__ __forceinline__ void warp_diag_fragment_pairs(double2 D, double2 &Minv, double2 &MinvT, double2 &r2, int *flag,
+                                                         int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double2 M = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);
+    r2 = make_double2(0.0, 0.0);
+    int bad = 0;
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+        const int k = 2 * kp;
+        const double a = __shfl_sync(kFull, D.x, 4 * k + kp);
+        const double b = __shfl_sync(kFull, D.x, 4 * (k + 1) + kp);
+        const double c = __shfl_sync(kFull, D.y, 4 * (k + 1) + kp);
+        const double pg = __shfl_sync(kFull, D.x, 4 * g + kp), qg = __shfl_sync(kFull, D.y, 4 * g + kp);
+        const double det = fma(a, c, -b * b);
+        bad |= (unsigned)(__double2hiint(a) - 0x00200000) >= 0x7fd00000u;
+        bad |= (unsigned)(__double2hiint(det) - 0x00200000) >= 0x7fd00000u;
+        const double rdet = fast_rcp3(det);
+        if (kp < 3) {
+            const double p0 = __shfl_sync(kFull, D.x, 8 * t + kp), q0 = __shfl_sync(kFull, D.y, 8 * t + kp);
+            const double p1 = __shfl_sync(kFull, D.x, 8 * t + 4 + kp), q1 = __shfl_sync(kFull, D.y, 8 * t + 4 + kp);
+            const double ns0 = fma(c, p0, -b * q0), nt0 = fma(a, q0, -b * p0);
+            const double ns1 = fma(c, p1, -b * q1), nt1 = fma(a, q1, -b * p1);
+            const double w0 = fma(pg, ns0, qg * nt0), w1 = fma(pg, ns1, qg * nt1);
+            if (t > kp) {
+                D.x = fma(-w0, rdet, D.x);
+                D.y = fma(-w1, rdet, D.y);
+            }
+        }
+        const double ra = fast_rcp3(a);
+        const double lgk = (g > k) ? pg * ra : 0.0;                            // L[g][k]
+        const double lgk1 = (g > k + 1) ? fma(a, qg, -b * pg) * rdet : 0.0;    // L[g][k+1]
+        if (t == kp) r2 = make_double2(ra, a * rdet);
+        {
+            const double mkx = __shfl_sync(kFull, M.x, 4 * k + t), mky = __shfl_sync(kFull, M.y, 4 * k + t);
+            M.x = fma(-lgk, mkx, M.x);
+            M.y = fma(-lgk, mky, M.y);
+        }
+        if (kp < 3) {
+            const double mkx = __shfl_sync(kFull, M.x, 4 * (k + 1) + t), mky = __shfl_sync(kFull, M.y, 4 * (k + 1) + t);
+            M.x = fma(-lgk1, mkx, M.x);
+            M.y = fma(-lgk1, mky, M.y);
+        }
+    }
+    if (bad && lane == 0) *flag = 1;
+    Minv = M;
+    const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
+    const double ax = __shfl_sync(kFull, M.x, s0), ay = __shfl_sync(kFull, M.y, s0);
+    const double bx = __shfl_sync(kFull, M.x, s1), by = __shfl_sync(kFull, M.y, s1);
+    MinvT = make_double2((g & 1) ? ay : ax, (g & 1) ? by : bx);
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");

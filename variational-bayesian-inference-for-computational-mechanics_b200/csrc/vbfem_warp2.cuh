@@ -20,6 +20,14 @@
 
 namespace vbfem {
 
+// Diagonal block: column by column.  The 2x2-pivot form (warp_diag_fragment_pairs, -DVBFEM_DIAG_PAIRS) halves the
+// dependency chain but issues more FP64 instructions: +5 % forward with twelve warps per SM, -3 % with sixteen
+// (measured, profiles/README.md) -- with sixteen warps the FP64 pipe, not the chain, is the limit.
+#ifdef VBFEM_DIAG_PAIRS
+#define WARP2_DIAG warp_diag_fragment_pairs
+#else
+#define WARP2_DIAG warp_diag_fragment
+#endif
 constexpr int kWarp2Fixed = 640;          // Minv^T and 1/d of the last panel, flag
 constexpr int kWarp2Small = 1152;         // small vectors of the observation / reverse pass
 constexpr int kWarp2WinRows = 40;         // rows of u / psi the contraction of one block column can touch (33) -> 5 panels
@@ -132,6 +140,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
 
         // block (q, q - d) of K = lambda K_lam + mu K_mu in the fragment layout
         auto kblock = [&](int q, int d) -> double2 {
+            // predicated loads: a branch-free form (clamped address, select) measured 12 % slower in forward mode
             const double2 *row = ktab + (size_t)(8 * q + g) * ldt + koff[d];
             double2 r = z2;
             if (kmask & (1u << (2 * d))) {
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
         // ---------------- panels
         double gacc = 0.0;  // partial sum over this lane's columns of G[g] = q_g^T K^-1 f
         double2 mi, mit, r2;  // of the current panel: Minv[g][2t..2t+1], its transpose, 1 / d of columns 2t, 2t+1
-        warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);  // diagonal block of panel 0
+        WARP2_DIAG(W[0][0], mi, mit, r2, flagp, lane);  // diagonal block of panel 0
 #pragma unroll 1
         for (int p = 0; p < NQ; ++p) {
             WTL(1);
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                 for (int d = 0; d <= NB; ++d) W[NB][d] = z2;
                 Rh[NB] = z2;
             }
-            if (p + 1 < NQ) warp_diag_fragment(W[0][0], mi, mit, r2, flagp, lane);
+            if (p + 1 < NQ) WARP2_DIAG(W[0][0], mi, mit, r2, flagp, lane);
             WTL(2);
         }
 
@@ -332,9 +341,41 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
             double sl[NADJ], sm[NADJ];  // psi_v^T K_lam u, psi_v^T K_mu u: this lane's share
 #pragma unroll
             for (int v = 0; v < NADJ; ++v) sl[v] = sm[v] = 0.0;
-            // contraction entries of one block column: (c, o) = local column, row - column, 8 x (hb + 1) of them
-            const int hb1 = Q.hb + 1, ncon = 8 * hb1;
+            // Contraction of block column p of the band: lane (g, t) owns local column cc (g with its two low bits
+            // swapped: the (K_lam, K_mu) pairs of a quarter-warp then fall into eight different 16-byte bank groups) and
+            // the offsets o = t + 4 j below the diagonal, rows 8 p + cc + o.
+            const int cc = (g & 4) | ((g & 1) << 1) | ((g >> 1) & 1);
+            constexpr int kTrips = 8;  // offsets up to 31 = the widest band three block sub-diagonals can hold
             int wbase = (8 * (NQ - 1)) % WR;  // window slot of row 8 p
+            auto contract = [&](int pc, int wb) {
+                const double *xc = win + (wb + cc) * NV;
+                double uc = xc[0], pcv[NADJ];
+#pragma unroll
+                for (int v = 0; v < NADJ; ++v) pcv[v] = xc[1 + v];
+                const double2 *kcol = ktab + (size_t)(8 * pc + cc + t) * ldt + t;
+#pragma unroll
+                for (int j = 0; j < kTrips; ++j) {
+                    // branch-free: an entry outside the band (or below the last row) reads entry 0 of the table and
+                    // counts with a zero coefficient, so that all loads of the column are in flight together
+                    const int o = t + 4 * j;
+                    const bool valid = o <= Q.hb && 8 * pc + cc + o < Q.npad;
+                    const double2 kr = valid ? kcol[(size_t)4 * j * (ldt + 1)] : ktab[0];
+                    const double kx = valid ? kr.x : 0.0, ky = valid ? kr.y : 0.0;
+                    int sr = wb + cc + o;
+                    sr -= (sr >= WR) ? WR : 0;
+                    const double *xr = win + sr * NV;
+                    const double ur = xr[0];
+#pragma unroll
+                    for (int v = 0; v < NADJ; ++v) {
+                        const double pr = xr[1 + v];
+                        double sv = pr * ur;                                          // diagonal entry: psi_r K_rr u_r
+                        if (j > 0) sv = fma(pr, uc, pcv[v] * ur);                     // o >= 4 > 0
+                        else sv = (t == 0) ? sv : fma(pr, uc, pcv[v] * ur);
+                        sl[v] = fma(kx, sv, sl[v]);
+                        sm[v] = fma(ky, sv, sm[v]);
+                    }
+                }
+            };
             double2 cur[NB + 2], nxt[NB + 2], nx2[NB + 2];  // panels p, p-1, p-2: loads two panels ahead of their use
             constexpr int kAhead = 4;  // panels on their way into L2 ahead of the register buffers
             if (lane < (NB + 2) * 4)
@@ -380,34 +421,22 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
 #pragma unroll
                 for (int b = NB; b > 1; --b) X[b] = X[b - 1];
                 X[1] = make_double2(-x.x, -x.y);
-                // ---- panel p of u and the adjoint vectors enters the window; block column p of the band is contracted
-                __syncwarp();  // the previous column's reads of the slots about to be overwritten are done
+                WTL(9);
+                // ---- block column p + 1 of the band is contracted (its rows 8 (p+1) .. 8 (p+1) + hb + 7 are in the window):
+                //      independent of the back-substitution chain above, one basic block with it
+                if (p + 1 < NQ) contract(p + 1, wbase + 8 >= WR ? wbase + 8 - WR : wbase + 8);
+                // ---- panel p of u and the adjoint vectors enters the window (the slot of panel p + 5)
+                __syncwarp();
                 if (g < NV) {
                     win[(wbase + 2 * t) * NV + g] = x.x;
                     win[(wbase + 2 * t + 1) * NV + g] = x.y;
                 }
                 __syncwarp();
-                for (int id = lane; id < ncon; id += 32) {
-                    const int c = (int)(((unsigned)id * Q.cmagic) >> 16), o = id - c * hb1;
-                    const int r = 8 * p + c + o;
-                    if (r < Q.npad) {
-                        const double2 kk = ktab[(size_t)r * ldt + o];
-                        int sr = wbase + c + o;
-                        sr -= (sr >= WR) ? WR : 0;
-                        const double *xr = win + sr * NV, *xc = win + (wbase + c) * NV;
-                        const double ur = xr[0], uc = xc[0];
-#pragma unroll
-                        for (int v = 0; v < NADJ; ++v) {
-                            const double pr = xr[1 + v], pc = xc[1 + v];
-                            const double sv = o ? fma(pr, uc, pc * ur) : pr * ur;
-                            sl[v] = fma(kk.x, sv, sl[v]);
-                            sm[v] = fma(kk.y, sv, sm[v]);
-                        }
-                    }
-                }
                 wbase -= 8;
                 wbase += (wbase < 0) ? WR : 0;
+                WTL(10);
             }
+            contract(0, wbase + 8 >= WR ? wbase + 8 - WR : wbase + 8);
             __syncwarp();
 
             WTL(6);
