@@ -131,8 +131,23 @@ def make_step1_model(num_neuron=20, num_layers=3, y_dim=2, theta_dim=2, device=N
         def __init__(self):
             super().__init__()
             self.mean_net, self.logsig_net = mlp(), mlp()
+            self.parallel_nets, self._side = True, None
 
         def forward(self, y):
+            if y.is_cuda and self.parallel_nets:
+                # the two nets are independent: the log-variance net runs on a side stream (forward here, and --
+                # autograd replays each op on the stream of its forward -- backward too).  In a captured training
+                # step the ~80 small kernels of the nets then form two parallel branches of the graph.
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=y.device)
+                cur = torch.cuda.current_stream(y.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    ls = self.logsig_net(y)
+                    sig = torch.exp(ls)
+                m = self.mean_net(y)
+                cur.wait_stream(self._side)
+                return m, sig, ls
             m, ls = self.mean_net(y), self.logsig_net(y)
             return m, torch.exp(ls), ls
 
@@ -159,7 +174,13 @@ def make_step1_optimizer_capturable(model, lr=1e-3):
     the whole training step can be captured in a CUDA graph."""
     import torch
 
-    return torch.optim.Adam(model.parameters(), lr=lr, betas=(0.99, 0.999), eps=1e-10, capturable=True)
+    params = list(model.parameters())
+    if params and params[0].is_cuda:
+        try:   # one multi-tensor kernel for all 16 parameter tensors instead of a dozen foreach launches
+            return torch.optim.Adam(params, lr=lr, betas=(0.99, 0.999), eps=1e-10, capturable=True, fused=True)
+        except (RuntimeError, ValueError):
+            pass
+    return torch.optim.Adam(params, lr=lr, betas=(0.99, 0.999), eps=1e-10, capturable=True)
 
 
 class GraphedStep1:
