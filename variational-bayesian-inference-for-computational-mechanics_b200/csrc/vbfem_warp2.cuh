@@ -28,6 +28,10 @@ namespace vbfem {
 #else
 #define WARP2_DIAG warp_diag_fragment
 #endif
+// sign flip on the integer pipe (the compiler's own -x is a DADD on the FP64 pipe, the kernel's bottleneck)
+__device__ __forceinline__ double neg_alu(double x) {
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
 constexpr int kWarp2Fixed = 640;          // Minv^T and 1/d of the last panel, flag
 constexpr int kWarp2Small = 1152;         // small vectors of the observation / reverse pass
 constexpr int kWarp2WinRows = 40;         // rows of u / psi the contraction of one block column can touch (33) -> 5 panels
@@ -178,21 +182,22 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
         for (int p = 0; p < NQ; ++p) {
             WTL(1);
             // ---- solve: V = X L11^-T for the right-hand sides (b = 0) and the blocks below; Ln = -V D^-1
-            double2 V[NB1], Ln[NB1];
+            double2 V[NB1], Ln[NB1], Lp[NB1];
 #pragma unroll
             for (int b = 0; b < NB1; ++b) {
                 const double2 xv = b ? W[b][0] : Rh[0];
                 double2 v = z2;
                 block_mma<true>(v, xv, mi, lane);
                 V[b] = v;
-                Ln[b] = make_double2(-v.x * r2.x, -v.y * r2.y);
+                Lp[b] = make_double2(v.x * r2.x, v.y * r2.y);
+                Ln[b] = make_double2(neg_alu(Lp[b].x), neg_alu(Lp[b].y));
             }
             {  // strain rows against the load row: G[g] += sum_c V[g][c] L[0][c]
-                const double lfx = __shfl_sync(kFull, Ln[0].x, t), lfy = __shfl_sync(kFull, Ln[0].y, t);
-                gacc = fma(V[0].x, -lfx, fma(V[0].y, -lfy, gacc));
+                const double lfx = __shfl_sync(kFull, Lp[0].x, t), lfy = __shfl_sync(kFull, Lp[0].y, t);
+                gacc = fma(V[0].x, lfx, fma(V[0].y, lfy, gacc));
                 if (p == NQ - 1 && g == 0) {
-                    lf_last[2 * t] = -Ln[0].x;
-                    lf_last[2 * t + 1] = -Ln[0].y;
+                    lf_last[2 * t] = Lp[0].x;
+                    lf_last[2 * t + 1] = Lp[0].y;
                 }
             }
             if (MODE > 0) {
@@ -203,10 +208,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
 #pragma unroll
                 for (int b = 0; b < NB1; ++b) {
                     const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
-                    const double ax = __shfl_sync(kFull, Ln[b].x, s0), ay = __shfl_sync(kFull, Ln[b].y, s0);
-                    const double bx = __shfl_sync(kFull, Ln[b].x, s1), by = __shfl_sync(kFull, Ln[b].y, s1);
+                    const double ax = __shfl_sync(kFull, Lp[b].x, s0), ay = __shfl_sync(kFull, Lp[b].y, s0);
+                    const double bx = __shfl_sync(kFull, Lp[b].x, s1), by = __shfl_sync(kFull, Lp[b].y, s1);
                     const bool odd = g & 1;
-                    __stcs(pan + (b ? b : NB + 1) * 32 + lane, make_double2(-(odd ? ay : ax), -(odd ? by : bx)));
+                    __stcs(pan + (b ? b : NB + 1) * 32 + lane, make_double2(odd ? ay : ax, odd ? by : bx));
                 }
             }
             WTL(3);
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                 for (int j = 0; j < kTrips; ++j) {
                     // branch-free: an entry outside the band (or below the last row) reads entry 0 of the table and
                     // counts with a zero coefficient, so that all loads of the column are in flight together
+                    if (4 * j > Q.hb) break;  // uniform: the whole trip lies outside the band
                     const int o = t + 4 * j;
                     const bool valid = o <= Q.hb && 8 * pc + cc + o < Q.npad;
                     const double2 kr = valid ? kcol[(size_t)4 * j * (ldt + 1)] : ktab[0];
@@ -403,24 +409,18 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                     if (p - 2 - kAhead >= 0 && lane < (NB + 2) * 4)
                         prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(p - 2 - kAhead) * LPB) + 128 * lane);
                 }
+                // one accumulator; the block that needs the newest x (b = 1) comes last: the chain from panel p+1 to
+                // panel p is two block products, the others run ahead
                 double2 d = z2;
+                if (p == NQ - 1) d = make_double2(nw0 * nl0.x + nw1 * nl1.x, nw0 * nl0.y + nw1 * nl1.y);
                 block_mma<true>(d, Wf, cur[NB + 1], lane);
 #pragma unroll
-                for (int b = 1; b <= NB; ++b) {
-                    double2 c = z2;
-                    block_mma<true>(c, X[b], cur[b], lane);
-                    d.x += c.x;
-                    d.y += c.y;
-                }
-                if (p == NQ - 1) {
-                    d.x += nw0 * nl0.x + nw1 * nl1.x;
-                    d.y += nw0 * nl0.y + nw1 * nl1.y;
-                }
+                for (int b = NB; b >= 1; --b) block_mma<true>(d, X[b], cur[b], lane);
                 double2 x = z2;
                 block_mma<true>(x, d, cur[0], lane);
 #pragma unroll
                 for (int b = NB; b > 1; --b) X[b] = X[b - 1];
-                X[1] = make_double2(-x.x, -x.y);
+                X[1] = make_double2(neg_alu(x.x), neg_alu(x.y));
                 WTL(9);
                 // ---- block column p + 1 of the band is contracted (its rows 8 (p+1) .. 8 (p+1) + hb + 7 are in the window):
                 //      independent of the back-substitution chain above, one basic block with it
