@@ -37,7 +37,7 @@ BYTES_PER_SOLVE = 96                                                          # 
 # `ncu --set full` capture of the warp-per-sample kernel (profiles/r02_ncu_warp_adj_raw_selected.txt):
 # 371.7 MB read + 534.7 MB written -- the factor slab of the adjoint (141 KB per sample, written once, read once);
 # the forward-only launch moves the compulsory 48 B per sample.
-NCU_DRAM_BYTES_PER_LAUNCH = 371697152 + 534670336
+NCU_DRAM_BYTES_PER_LAUNCH = 411526400 + 542349824   # read + written, profiles/r02_ncu_warp_adj_raw_selected.txt
 # config 4 (80x40): DRAM bytes per fused forward+adjoint SOLVE from the committed capture of the panel kernel
 NCU_C4_DRAM_BYTES_PER_SOLVE = int((1.871130e9 + 1.928987e9) / 296)   # 12.84 MB (read 6.32 + written 6.52)
 
@@ -567,7 +567,7 @@ def run_cuda(args):
             "roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64.value, "unit": "TFLOP/s",
                          "frac": tflops / fp64.value if fp64.value else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, batch 4096, fused forward+adjoint): "
-                                         "220 KB per sample = the scaled factor panels streamed to a per-warp slab and read "
+                                         "236 KB per sample = the scaled factor panels streamed to a per-warp slab and read "
                                          "back once by the reverse pass (SURVEY 8d counts 4 n (b+1) 8 = 366 KB per sample for "
                                          "a streamed factor); compulsory I/O is 96 B per sample",
                          "peak_source": "DFMA loop measured on this GPU by vbfem_measure_peaks "

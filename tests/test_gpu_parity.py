@@ -34,7 +34,7 @@ def test_native_library_is_loaded(engine, pkg):
     maps = open("/proc/self/maps").read()
     assert "libvbfem.so" in maps
     assert engine.info["nfree"] == 440 and engine.info["half_bw"] == 25  # short-side numbering
-    assert engine.info["kernel_variant"] == 4 and engine.info["block_threads"] == 384   # warp-per-sample kernel, 12 warps
+    assert engine.info["kernel_variant"] == 4 and engine.info["block_threads"] == 512   # warp-per-sample kernel, 16 warps
     # the host-only plan (vbfem_plan, unit-tested without a GPU) is what vbfem_create built
     plan = pkg.fem_solver.plan_layout(golden_model_of(engine))
     for k in ("kernel_variant", "nfree", "half_bw", "twist_row", "smem_bytes"):

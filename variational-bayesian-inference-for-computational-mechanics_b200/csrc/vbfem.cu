@@ -1582,9 +1582,9 @@ static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
 // Second generation of the warp kernel (vbfem_warp2.cuh): the (K_lam, K_mu) band table must fit in shared memory
 // next to the per-warp areas of twelve (or eight) warps.
 struct Warp2Plan {
-    bool ok = false;
-    int NW = 0, hb = 0, ldt = 0, tab_bytes = 0, warp_smem = 0;
-    size_t smem = 0;
+    bool ok = false, ok16 = false;  // ok16: sixteen warps per SM in forward / fused-adjoint mode (one adjoint vector)
+    int NW = 0, hb = 0, ldt = 0, tab_bytes = 0, warp_smem = 0, warp16_smem = 0;
+    size_t smem = 0, smem16 = 0;
 };
 static Warp2Plan warp2_plan(const PanelPlan &P, size_t smem_per_block) {
     Warp2Plan W;
@@ -1616,6 +1616,10 @@ static Warp2Plan warp2_plan(const PanelPlan &P, size_t smem_per_block) {
             break;
         }
     }
+    W.warp16_smem = warp2_smem_per_warp(2);
+    W.smem16 = (size_t)W.tab_bytes + (size_t)16 * W.warp16_smem;
+    const char *e16 = getenv("VBFEM_WARP2_NW16");
+    W.ok16 = W.ok && W.NW == 12 && W.smem16 + 64 <= smem_per_block && !(e16 && atoi(e16) == 0) && !nw;
     return W;
 }
 
@@ -1921,11 +1925,9 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
                 if (rc2) return -2;
                 long long nwarps = (long long)h->num_sms * W2.NW;
                 {   // sixteen warps for MODE 0 / 1 (per-warp window of u and ONE adjoint vector)
-                    const int pw = warp2_smem_per_warp(2);
-                    const size_t sm16 = (size_t)W2.tab_bytes + (size_t)16 * pw;
-                    const char *e16 = getenv("VBFEM_WARP2_NW16");
-                    if (W2.NW == 12 && sm16 + 64 <= (size_t)prop.sharedMemPerBlockOptin && !(e16 && atoi(e16) == 0) &&
-                        !getenv("VBFEM_WARP_NW")) {
+                    const int pw = W2.warp16_smem;
+                    const size_t sm16 = W2.smem16;
+                    if (W2.ok16) {
                         warp_fn k16[2] = {fem_warp2_kernel<0, 16>, fem_warp2_kernel<1, 16>};
                         bool ok16 = true;
                         for (int q = 0; q < 2 && ok16; ++q) {
@@ -2270,7 +2272,9 @@ extern "C" int vbfem_plan(const vbfem_mesh *m, int64_t smem_per_sm, int64_t *out
             const Warp2Plan W2 = warp2_plan(Q, per_block);
             out[0] = 4;
             out[3] = out[4] = out[5] = 0;
-            out[6] = W2.ok ? (int64_t)W2.smem : (int64_t)NW * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
+            // shared memory of the fused / forward launches (sixteen warps when they fit; Jacobian mode runs twelve)
+            out[6] = W2.ok ? (int64_t)(W2.ok16 ? W2.smem16 : W2.smem)
+                           : (int64_t)NW * warp_kernel_smem(Q) + warp_kernel_tab_bytes(Q);
             out[7] = W2.ok ? 2 : 1;  // generation of the warp kernel
             return 0;
         }
@@ -2352,10 +2356,11 @@ extern "C" int vbfem_info(const vbfem_t *h, int64_t *out) {
     out[VBFEM_INFO_NELE] = h->M.nele;
     out[VBFEM_INFO_NCOLORS] = h->M.ncolors;
     out[VBFEM_INFO_BAND_IN_SMEM] = h->variant >= 3 ? 0 : h->M.band_in_smem;
-    out[VBFEM_INFO_SMEM_BYTES] = (int64_t)h->smem_bytes;
+    // the warp kernel's forward / fused-adjoint launches (the headline path) may run sixteen warps: report those
+    out[VBFEM_INFO_SMEM_BYTES] = h->kern_warp16[0] ? (int64_t)h->warp16_smem : (int64_t)h->smem_bytes;
     out[VBFEM_INFO_CTAS_PER_SM] = h->ctas_per_sm;
     out[VBFEM_INFO_NUM_SMS] = h->num_sms;
-    out[VBFEM_INFO_BLOCK_THREADS] = h->block;
+    out[VBFEM_INFO_BLOCK_THREADS] = h->kern_warp16[0] ? 512 : h->block;
     out[VBFEM_INFO_KERNEL_VARIANT] = h->variant;
     out[VBFEM_INFO_TWIST_ROW] = h->variant == 2 ? h->M.pT : 0;
     out[VBFEM_INFO_PANEL_BLOCKS] = h->variant >= 3 ? h->PM.NB : 0;
