@@ -219,6 +219,20 @@ int vbfem_elbo_step1_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin
                                const double *mu_dev, const double *sig2_dev, const double *e_dev,
                                const double *ybatch_dev, double sig_e, double *totals_dev,
                                double *f_dev /* optional */, void *stream);
+/* The whole step-1 loss in the library: vbfem_elbo_step1 (+ the exchange when allreduce != 0, else the
+ * range must be the whole step) followed by the closed-form KL terms (main_custom_training.py:183-185,
+ * 226-235) and the loss value, so that a training step needs no framework arithmetic between the nets'
+ * outputs and their gradients.  log_sig2_dev [B][2] is the log-variance net's output, sig2 = exp of it.
+ *   out_dev[0]              loss = term1 - term2 - term3
+ *   out_dev[1 .. 2B]        d loss / d mu            [B][2]
+ *   out_dev[1+2B .. 4B]     d loss / d sig2          [B][2]
+ *   out_dev[1+4B .. 6B]     d loss / d log_sig2      [B][2]  (direct dependence only; the caller chains sig2)
+ * out_dev must hold 4 + 10B doubles (the totals are staged behind the results).  B <= 128. */
+int vbfem_elbo_step1_loss(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
+                          const double *mu_dev, const double *sig2_dev, const double *log_sig2_dev,
+                          const double *e_dev, const double *ybatch_dev, double sig_e, int32_t allreduce,
+                          double *out_dev, void *stream);
+
 /* vbfem_elbo_step2 likewise: totals_dev[4] summed over all ranks. */
 int vbfem_elbo_step2_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,
                                const double *mu_dev, const double *sig2_dev, const double *e_dev,

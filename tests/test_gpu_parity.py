@@ -330,6 +330,14 @@ def test_elbo_step1_fused_vs_oracle(pkg, engine, torch_oracle):
     assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
     assert relerr(mu_c.grad.cpu().numpy(), mu_o.grad.numpy()) < TOL
     assert relerr(ls_c.grad.cpu().numpy(), ls_o.grad.numpy()) < TOL
+    # the same with the KL terms and the loss value in the framework (fused=False): both forms agree to rounding
+    mu_f = _t(mu, engine).requires_grad_(True)
+    ls_f = _t(ls, engine).requires_grad_(True)
+    loss_f = pkg.elbo.Step1Loss(engine, _t(e, engine), 0.1, fused=False)(_t(yb, engine), mu_f, torch.exp(ls_f), ls_f)
+    loss_f.backward()
+    assert abs(float(loss) - float(loss_f)) < 1e-13 * abs(float(loss_f))
+    assert relerr(mu_c.grad.cpu().numpy(), mu_f.grad.cpu().numpy()) < 1e-13
+    assert relerr(ls_c.grad.cpu().numpy(), ls_f.grad.cpu().numpy()) < 1e-13
     # shard-count invariance: partials of 1, 2, 3, 8 shards add up to the same numbers
     full = engine.elbo_step1_partials(mu_c.detach(), torch.exp(ls_c.detach()), _t(e, engine), _t(yb, engine), 0.1)
     for world in (2, 3, 8):

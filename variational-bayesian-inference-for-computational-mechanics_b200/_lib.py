@@ -38,7 +38,7 @@ SYMBOLS = [
     "vbfem_debug_panel_tables", "vbfem_forward_backward", "vbfem_fields", "vbfem_elbo_step1", "vbfem_elbo_step2", "vbfem_status", "vbfem_forward_host",
     "vbfem_forward_backward_host", "vbfem_measure_peaks",
     "vbfem_peer_open", "vbfem_peer_connect", "vbfem_peer_allreduce", "vbfem_peer_status",
-    "vbfem_elbo_step1_allreduce", "vbfem_elbo_step2_allreduce",
+    "vbfem_elbo_step1_allreduce", "vbfem_elbo_step2_allreduce", "vbfem_elbo_step1_loss",
 ]
 
 
@@ -156,6 +156,9 @@ def load():
     lib.vbfem_elbo_step1_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp,
                                                c_dp, c_dp, ctypes.c_double, c_dp, c_dp, c_dp]
     lib.vbfem_elbo_step1_allreduce.restype = ctypes.c_int
+    lib.vbfem_elbo_step1_loss.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp, c_dp,
+                                          c_dp, c_dp, ctypes.c_double, ctypes.c_int32, c_dp, c_dp]
+    lib.vbfem_elbo_step1_loss.restype = ctypes.c_int
     lib.vbfem_elbo_step2_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, i64, i64, c_dp, c_dp,
                                                c_dp, c_dp, c_dp, c_dp]
     lib.vbfem_elbo_step2_allreduce.restype = ctypes.c_int

@@ -953,6 +953,38 @@ __global__ void ysum_kernel(int B, const double *y, double *out) {
         double a = 0.0;
         for (int i = 0; i < B; ++i) a += y[2 * i + threadIdx.x];
         out[threadIdx.x] = a;
+    } else if (threadIdx.x == 2) {  // sum_b |y_b|^2 (the loss value of term2 needs it)
+        double a = 0.0;
+        for (int i = 0; i < 2 * B; ++i) a += y[i] * y[i];
+        out[2] = a;
+    }
+}
+
+// The step-1 loss and its gradient w.r.t. the nets' outputs from the (all-reduced) totals of the data term:
+//   loss = term1 - term2 - term3  (main_custom_training.py:183-185, 199-214, 226-235), theta_dim = y_dim = 2,
+//   out[0] = loss, out[1 + 2b + k] = d loss / d mu[b][k], out[1 + 2B + ...] = d loss / d sig2, out[1 + 4B + ...] =
+//   d loss / d log_sig2 (the direct dependence through term1 only; sig2 = exp(log_sig2) is chained by the caller).
+__global__ void elbo_loss_kernel(int B, double nsamp, double sig_e, const double *tot, const double *mu,
+                                 const double *sig2, const double *lsg, const double *ysum, double *out) {
+    const int idx = threadIdx.x;
+    const double invB = 1.0 / (double)B;
+    if (idx < 2 * B) {
+        out[1 + idx] = tot[3 + idx] + mu[idx] * invB;            // -term3 -> + mu / B
+        out[1 + 2 * B + idx] = tot[3 + 2 * B + idx] + 0.5 * invB;  // -term3 -> + 1 / (2 B)
+        out[1 + 4 * B + idx] = -0.5 * invB;                       // term1
+    }
+    if (idx == 0) {
+        const double log2pi = 1.8378770664093454835606594728112;
+        double sls = 0.0, s3 = 0.0;
+        for (int i = 0; i < 2 * B; ++i) {
+            sls += lsg[i];
+            s3 += sig2[i] + mu[i] * mu[i];
+        }
+        const double t1 = -0.5 * sls * invB - 0.5 * 2.0 * log2pi - 0.5 * 2.0;
+        const double t3 = -0.5 * 2.0 * log2pi - 0.5 * s3 * invB;
+        const double total = (double)B * tot[2] - 2.0 * (tot[0] * ysum[0] + tot[1] * ysum[1]) + nsamp * ysum[2];
+        const double t2 = -0.5 * 2.0 * log(2.0 * 3.14159265358979323846 * sig_e) - 0.5 / sig_e * total / ((double)B * nsamp);
+        out[0] = t1 - t2 - t3;
     }
 }
 
@@ -2657,6 +2689,23 @@ extern "C" int vbfem_elbo_step1(vbfem_t *h, int32_t B, int32_t S, int64_t j_begi
                                 const double *sig2, const double *e, const double *ybatch, double sig_e,
                                 double *sums, double *gmu, double *gsig2, double *f_out, void *stream) {
     return elbo_step1_impl(h, B, S, j_begin, j_end, mu, sig2, e, ybatch, sig_e, sums, gmu, gsig2, f_out, stream, false);
+}
+
+extern "C" int vbfem_elbo_step1_loss(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end, const double *mu,
+                                     const double *sig2, const double *log_sig2, const double *e, const double *ybatch,
+                                     double sig_e, int32_t allreduce, double *out, void *stream) {
+    if (!h || !log_sig2 || !out) return fail(-1, "null argument");
+    if (B > 128) return fail(-1, "vbfem_elbo_step1_loss: batch of %d observations, at most 128", B);
+    if (!allreduce && (j_begin != 0 || j_end != (int64_t)B * S))
+        return fail(-1, "vbfem_elbo_step1_loss without the exchange needs the whole sample range");
+    double *tot = out + 1 + 6 * (size_t)B;  // scratch behind the results: the totals [3 + 4B]
+    int rc = elbo_step1_impl(h, B, S, j_begin, j_end, mu, sig2, e, ybatch, sig_e, tot, tot + 3, tot + 3 + 2 * (size_t)B,
+                             nullptr, stream, allreduce != 0);
+    if (rc) return rc;
+    elbo_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(B, (double)B * (double)S, sig_e, tot, mu, sig2, log_sig2,
+                                                          h->elbo_ysum, out);
+    CU(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int vbfem_elbo_step1_allreduce(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, int64_t j_end,

@@ -81,10 +81,30 @@ def _data_term_function():
             gmu, gsig2 = ctx.saved_tensors
             return g * gmu, g * gsig2, None, None
 
-    return NegTerm2
+    class Step1Fused(torch.autograd.Function):
+        """The whole step-1 loss (term1 - term2 - term3) and its gradient w.r.t. (mu, sig2, log_sig2) from the
+        library: reparameterisation, FEM, adjoint, reductions, the ranks' exchange and the closed-form KL terms
+        without any framework arithmetic in between (main_custom_training.py:183-235)."""
+
+        @staticmethod
+        def forward(ctx, mu, sig2, log_sig2, loss_obj, y_batch):
+            B, S = mu.shape[0], loss_obj.e_data.shape[0]
+            lo, hi = shard_range(B * S, loss_obj.rank, loss_obj.world)
+            loss, dmu, dsig2, dls = loss_obj.engine.elbo_step1_loss(
+                mu.detach().contiguous(), sig2.detach().contiguous(), log_sig2.detach().contiguous(), loss_obj.e_data,
+                y_batch.contiguous(), loss_obj.sig_e, lo, hi, loss_obj.world > 1)
+            ctx.save_for_backward(dmu, dsig2, dls)
+            return loss.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            dmu, dsig2, dls = ctx.saved_tensors
+            return g * dmu, g * dsig2, g * dls, None, None
+
+    return NegTerm2, Step1Fused
 
 
-_NegTerm2 = None
+_NegTerm2 = _Step1Fused = None
 
 
 class Step1Loss:
@@ -94,7 +114,7 @@ class Step1Loss:
     ``group``/``rank``/``world`` describe the torch.distributed process group
     whose ranks share the Monte-Carlo samples."""
 
-    def __init__(self, engine, e_data, sig_e, group=None, rank=0, world=1, peer=None):
+    def __init__(self, engine, e_data, sig_e, group=None, rank=0, world=1, peer=None, fused=True):
         self.engine, self.e_data, self.sig_e = engine, e_data.contiguous(), float(sig_e)
         self.group, self.rank, self.world = group, int(rank), int(world)
         # peer mailboxes connected for this world (engine.peer_connect_group): exchange inside the reduction kernel;
@@ -103,11 +123,17 @@ class Step1Loss:
         if peer and not connected:
             raise ValueError("peer exchange requested but the engine has no peer mailboxes for this world size")
         self.peer = connected if peer is None else bool(peer)
+        # the KL terms and the loss value in the library too (one ranks' exchange or a single rank); fused=False keeps
+        # them in the framework (the form the tests compare against)
+        self.fused = bool(fused)
 
     def __call__(self, y_batch, theta_mean, theta_sig, log_theta_sig):
-        global _NegTerm2
+        global _NegTerm2, _Step1Fused
         if _NegTerm2 is None:
-            _NegTerm2 = _data_term_function()
+            _NegTerm2, _Step1Fused = _data_term_function()
+        if self.fused and (self.world == 1 or self.peer) and y_batch.shape[0] <= 128 \
+                and hasattr(self.engine, "elbo_step1_loss"):
+            return _Step1Fused.apply(theta_mean, theta_sig, log_theta_sig, self, y_batch)
         neg_t2 = _NegTerm2.apply(theta_mean, theta_sig, self, y_batch)
         return term1(log_theta_sig) + neg_t2 - term3(theta_mean, theta_sig)
 

@@ -382,6 +382,20 @@ class CookFemEngine:
         self.launches += 3
         return tot
 
+    def elbo_step1_loss(self, mu, sig2, log_sig2, e_data, y_batch, sig_e, j_begin, j_end, allreduce):
+        """The whole step-1 loss in the library (``vbfem_elbo_step1_loss``): returns (loss[()], dmu[B,2], dsig2[B,2],
+        dlog_sig2[B,2]) -- views of one buffer.  ``allreduce``: the exchange over the peer mailboxes is part of it;
+        otherwise [j_begin, j_end) must be the whole B*S range."""
+        B, S = int(mu.shape[0]), int(e_data.shape[0])
+        out = self._new(4 + 10 * B)
+        _lib.check(self.lib.vbfem_elbo_step1_loss(
+            self._h, B, S, int(j_begin), int(j_end), self._chk(mu, B, "mu"), self._chk(sig2, B, "sig2"),
+            self._chk(log_sig2, B, "log_sig2"), self._chk(e_data, S, "e_data"), self._chk(y_batch, B, "y_batch"),
+            float(sig_e), int(bool(allreduce)), ctypes.c_void_p(out.data_ptr()), self._stream()), "vbfem_elbo_step1_loss")
+        self.launches += 4
+        return (out[0], out[1:1 + 2 * B].view(B, 2), out[1 + 2 * B:1 + 4 * B].view(B, 2),
+                out[1 + 4 * B:1 + 6 * B].view(B, 2))
+
     def elbo_step2_totals(self, mu, sig2, e_data, j_begin, j_end):
         """``elbo_step2_partials`` with the sum over ranks fused into its reduction kernel: totals[4]."""
         B, S = int(mu.shape[0]), int(e_data.shape[0])
