@@ -593,6 +593,7 @@ def run_cuda(args):
                                     "rank order (csrc/vbfem_peer.cuh; a node of the captured graph)" if use_peer else
                                     "one NCCL all-reduce of 3 + 4B doubles per step INSIDE the timed region (a node of "
                                     "the captured graph); peer mailboxes unavailable: " + str(peer_note)),
+                     # A/B: range-restricted partials, one NCCL all-reduce node, KL terms and loss value in torch
                      "nccl_all_reduce_steps_per_s": (elbo_steps / elbo_nccl_s) if use_peer and elbo_nccl_s else None,
                      "nccl_last_loss": nccl_loss,
                      "roofline": {"bound": "fp64", "achieved": elbo_tflops, "peak": fp64.value * world,
@@ -600,7 +601,7 @@ def run_cuda(args):
                                   "note": "0.716 MFLOP per reparameterised sample (FEM forward + adjoint); the two "
                                           "1884-parameter MLPs and Adam are < 0.1 % of the flops"},
                      "cpu_baseline": cpu_elbo,
-                     "what": "every step: pinned batch H2D -> NN fwd -> reparam -> FEM fwd -> loss -> FEM adjoint -> NN bwd "
+                     "what": "every step: pinned batch H2D -> NN fwd -> [library: reparam -> FEM fwd -> data-term cotangent -> FEM adjoint -> reductions (+ the ranks' exchange) -> KL terms, loss] -> NN bwd "
                              "-> Adam (one CUDA graph replay) -> loss D2H into pinned memory; the host launches up to four "
                              "steps ahead and reads each loss afterwards (GraphedStep1.step_async); "
                              "host_synchronised_every_step_steps_per_s = the same with float(loss) after every step",
