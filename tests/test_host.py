@@ -255,11 +255,11 @@ def test_plan_layout_on_host(pkg, golden_model, monkeypatch):
     plan = pkg.fem_solver.plan_layout(golden_model)
     assert plan["kernel_variant"] == 4 and plan["nfree"] == 440 and plan["half_bw"] == 25
     # second generation of the warp kernel: the (K_lam, K_mu) band table [440][26] x 16 B in shared memory + per warp
-    # 640 B (last panel's Minv^T, 1/d, flag) + 1152 B (small vectors) + the 40-row window of u and four adjoints
+    # 640 B (last panel's Minv^T, 1/d, flag) + 1088 B (small vectors) + the 40-row window of u and four adjoints
     # (forward / fused-adjoint launches: sixteen warps, one adjoint vector; Jacobian mode: twelve warps, four)
-    assert plan["smem_bytes"] == 440 * 26 * 16 + 16 * (640 + 1152 + 40 * 2 * 8)
+    assert plan["smem_bytes"] == 440 * 26 * 16 + 16 * (640 + 1088 + 40 * 2 * 8)
     monkeypatch.setenv("VBFEM_WARP2_NW16", "0")
-    assert pkg.fem_solver.plan_layout(golden_model)["smem_bytes"] == 440 * 26 * 16 + 12 * (640 + 1152 + 40 * 5 * 8)
+    assert pkg.fem_solver.plan_layout(golden_model)["smem_bytes"] == 440 * 26 * 16 + 12 * (640 + 1088 + 40 * 5 * 8)
     monkeypatch.delenv("VBFEM_WARP2_NW16")
     # first generation (element matrices per sample, gather table): what a smaller shared memory falls back to
     per_warp = 640 + 4 * 512 + (44 * 36 + 2) * 8     # last panel's Minv^T / 1/d / flag, staging area, ring of 44 element matrices

@@ -1054,9 +1054,9 @@ struct vbfem_handle {
     warp_fn kern_warp[3] = {nullptr, nullptr, nullptr};
     int warp_nw = 0;
     // second generation, forward / fused-adjoint modes: sixteen warps per SM when registers (128) and shared memory allow
-    warp_fn kern_warp16[2] = {nullptr, nullptr};
-    size_t warp16_smem = 0;
-    int warp16_per_warp = 0;
+    warp_fn kern_warp16[3] = {nullptr, nullptr, nullptr};
+    size_t warp16_smem = 0, warp16j_smem = 0;   // j: Jacobian mode (five vectors in the window, the smallest ring)
+    int warp16_per_warp = 0, warp16j_per_warp = 0, warp16j_rows = 0;
     // generic kernel configuration (fields mode, meshes neither fast kernel takes)
     DevModel M_gen{};
     int gen_block = 0, gen_ctas = 0;
@@ -1614,9 +1614,9 @@ static bool warp_kernel_ok(const PanelPlan &P, int NW, size_t smem_per_block) {
 // Second generation of the warp kernel (vbfem_warp2.cuh): the (K_lam, K_mu) band table must fit in shared memory
 // next to the per-warp areas of twelve (or eight) warps.
 struct Warp2Plan {
-    bool ok = false, ok16 = false;  // ok16: sixteen warps per SM in forward / fused-adjoint mode (one adjoint vector)
-    int NW = 0, hb = 0, ldt = 0, tab_bytes = 0, warp_smem = 0, warp16_smem = 0;
-    size_t smem = 0, smem16 = 0;
+    bool ok = false, ok16 = false, ok16j = false;  // sixteen warps per SM: forward / fused-adjoint mode, Jacobian mode
+    int NW = 0, hb = 0, ldt = 0, tab_bytes = 0, warp_smem = 0, warp16_smem = 0, warp16j_smem = 0, rows16j = 0;
+    size_t smem = 0, smem16 = 0, smem16j = 0;
 };
 static Warp2Plan warp2_plan(const PanelPlan &P, size_t smem_per_block) {
     Warp2Plan W;
@@ -1652,6 +1652,10 @@ static Warp2Plan warp2_plan(const PanelPlan &P, size_t smem_per_block) {
     W.smem16 = (size_t)W.tab_bytes + (size_t)16 * W.warp16_smem;
     const char *e16 = getenv("VBFEM_WARP2_NW16");
     W.ok16 = W.ok && W.NW == 12 && W.smem16 + 64 <= smem_per_block && !(e16 && atoi(e16) == 0) && !nw;
+    W.rows16j = std::max(hb + 8, kWarp2WinRowsMin);
+    W.warp16j_smem = warp2_smem_per_warp(5, W.rows16j);
+    W.smem16j = (size_t)W.tab_bytes + (size_t)16 * W.warp16j_smem;
+    W.ok16j = W.ok16 && W.rows16j <= kWarp2WinRows && W.smem16j + 64 <= smem_per_block;
     return W;
 }
 
@@ -1899,6 +1903,7 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
             Q.tab_bytes = W2.tab_bytes;
             Q.ldt = W2.ldt;
             Q.hb = W2.hb;
+            Q.win_rows = kWarp2WinRows;
             Q.cmagic = 65536u / (unsigned)(W2.hb + 1) + 1u;
             bool magic_ok = true;
             for (int id = 0; id < 8 * (W2.hb + 1); ++id)
@@ -1977,6 +1982,21 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
                             h->warp16_smem = sm16;
                             h->warp16_per_warp = pw;
                             nwarps = (long long)h->num_sms * 16;
+                            if (W2.ok16j) {
+                                warp_fn kj = fem_warp2_kernel<2, 16>;
+                                cudaError_t e1 = allow_max_smem(kj);
+                                int nb = 0;
+                                if (e1 == cudaSuccess)
+                                    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kj, 512, W2.smem16j);
+                                if (e1 == cudaSuccess && nb >= 1) {
+                                    h->kern_warp16[2] = kj;
+                                    h->warp16j_smem = W2.smem16j;
+                                    h->warp16j_per_warp = W2.warp16j_smem;
+                                    h->warp16j_rows = W2.rows16j;
+                                } else {
+                                    cudaGetLastError();
+                                }
+                            }
                         }
                     }
                 }
@@ -2492,10 +2512,11 @@ static int launch(vbfem_handle *h, Args &a, void *stream) {
         CU(cudaMemsetAsync(h->timeline, 0, (size_t)h->num_sms * 4 * 16 * sizeof(long long), st));
         a.timeline = h->timeline;
 #endif
-        if (mode < 2 && h->kern_warp16[mode]) {
+        if (h->kern_warp16[mode]) {
             WarpModel wm = h->WM;
-            wm.warp_smem = h->warp16_per_warp;
-            h->kern_warp16[mode]<<<(unsigned)grid, 512, h->warp16_smem, st>>>(h->M_gen, wm, a);
+            wm.warp_smem = mode == 2 ? h->warp16j_per_warp : h->warp16_per_warp;
+            if (mode == 2) wm.win_rows = h->warp16j_rows;
+            h->kern_warp16[mode]<<<(unsigned)grid, 512, mode == 2 ? h->warp16j_smem : h->warp16_smem, st>>>(h->M_gen, wm, a);
         } else {
             h->kern_warp[mode]<<<(unsigned)grid, h->block, h->smem_bytes, st>>>(h->M_gen, h->WM, a);
         }

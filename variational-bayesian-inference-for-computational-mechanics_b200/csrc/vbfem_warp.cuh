@@ -56,6 +56,7 @@ struct WarpModel {
     // second generation (vbfem_warp2.cuh): K = lambda K_lam + mu K_mu from a sample-independent band table
     const double2 *ktab;         // (K_lam, K_mu)[npad][ldt], entry (r, c) at [r][r - c]; copied to shared memory per CTA
     int ldt, hb;                 // row stride (even, >= hb + 1), half bandwidth in padded rows
+    int win_rows;                // ring of u / psi rows per warp (reverse pass): 40, or hb + 8 when shared memory is tight
     unsigned cmagic;             // id / (hb + 1) == (id * cmagic) >> 16 for id < 8 (hb + 1)
     unsigned long long rhsmask[2];  // bit q: block row q has a non-zero initial right-hand-side block
 };

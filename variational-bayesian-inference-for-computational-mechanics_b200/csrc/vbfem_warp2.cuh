@@ -33,9 +33,12 @@ __device__ __forceinline__ double neg_alu(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
 constexpr int kWarp2Fixed = 640;          // Minv^T and 1/d of the last panel, flag
-constexpr int kWarp2Small = 1152;         // small vectors of the observation / reverse pass
-constexpr int kWarp2WinRows = 40;         // rows of u / psi the contraction of one block column can touch (33) -> 5 panels
-__host__ __device__ constexpr int warp2_smem_per_warp(int nv) { return kWarp2Fixed + kWarp2Small + kWarp2WinRows * nv * 8; }
+constexpr int kWarp2Small = 1088;         // small vectors of the observation / reverse pass (136 doubles)
+constexpr int kWarp2WinRows = 40;         // ring of u / psi rows: five panels; the contraction of one block column touches
+constexpr int kWarp2WinRowsMin = 33;      // hb + 8 <= 33 rows, which is the smallest ring that works (WarpModel::win_rows)
+__host__ __device__ constexpr int warp2_smem_per_warp(int nv, int rows = kWarp2WinRows) {
+    return (kWarp2Fixed + kWarp2Small + rows * nv * 8 + 15) & ~15;
+}
 
 // Element matrices for unit Lame parameters: out[k][0][36] = K_lam of element k, out[k][1][36] = K_mu (lower triangle,
 // tri(a, q)); elements in the order of `ecoord`.  Runs once per mesh.
@@ -74,7 +77,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
     constexpr int NB = kWarpNB, NB1 = NB + 1, LPB = (NB + 2) * 64;
     constexpr int NV = (MODE == 2) ? 5 : 2;
     constexpr int NADJ = NV - 1;
-    constexpr int WR = kWarp2WinRows;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int next_i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
     double *sW = small, *nodew = small + 64, *nodeL = small + 80, *sG = small + 96, *lf_last = small + 104,
            *obs = small + 112;
     double *win = reinterpret_cast<double *>(wsm + kWarp2Fixed + kWarp2Small);  // [WR][NV]: u and the adjoint vectors
-    const int NQ = Q.NQ;
+    const int NQ = Q.NQ, WR = Q.win_rows;
     const int wid = blockIdx.x * NW + warp;
     double *lws = Q.lws + (size_t)wid * Q.lws_stride;
     const double2 z2 = make_double2(0.0, 0.0);
@@ -353,7 +355,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
             constexpr int kTrips = 8;  // offsets up to 31 = the widest band three block sub-diagonals can hold
             int wbase = (8 * (NQ - 1)) % WR;  // window slot of row 8 p
             auto contract = [&](int pc, int wb) {
-                const double *xc = win + (wb + cc) * NV;
+                int sc = wb + cc;
+                sc -= (sc >= WR) ? WR : 0;
+                const double *xc = win + sc * NV;
                 double uc = xc[0], pcv[NADJ];
 #pragma unroll
                 for (int v = 0; v < NADJ; ++v) pcv[v] = xc[1 + v];
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                     const bool valid = o <= Q.hb && 8 * pc + cc + o < Q.npad;
                     const double2 kr = valid ? kcol[(size_t)4 * j * (ldt + 1)] : ktab[0];
                     const double kx = valid ? kr.x : 0.0, ky = valid ? kr.y : 0.0;
-                    int sr = wb + cc + o;
+                    int sr = sc + o;
                     sr -= (sr >= WR) ? WR : 0;
                     const double *xr = win + sr * NV;
                     const double ur = xr[0];
@@ -428,8 +432,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                 // ---- panel p of u and the adjoint vectors enters the window (the slot of panel p + 5)
                 __syncwarp();
                 if (g < NV) {
-                    win[(wbase + 2 * t) * NV + g] = x.x;
-                    win[(wbase + 2 * t + 1) * NV + g] = x.y;
+                    int r0 = wbase + 2 * t, r1 = r0 + 1;
+                    r0 -= (r0 >= WR) ? WR : 0;
+                    r1 -= (r1 >= WR) ? WR : 0;
+                    win[r0 * NV + g] = x.x;
+                    win[r1 * NV + g] = x.y;
                 }
                 __syncwarp();
                 wbase -= 8;
