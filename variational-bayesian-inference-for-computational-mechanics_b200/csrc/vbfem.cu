@@ -887,19 +887,36 @@ __global__ void elbo_reduce_kernel(int B, int S, long long j_begin, long long j_
             else sums[tid] = sh[tid][0];
         }
     } else {
-        const int idx = (blockIdx.x - 1) * blockDim.x + tid;  // (b, k)
-        if (idx < 2 * B) {
-            const int bb = idx >> 1, k = idx & 1;
-            long long lo = (long long)bb * S, hi = lo + S;
-            lo = lo > j_begin ? lo : j_begin;
-            hi = hi < j_end ? hi : j_end;
-            double gm = 0.0, gs = 0.0;
-            for (long long j = lo; j < hi; ++j) {
-                const double g = gth[2 * (j - j_begin) + k];
-                gm += g;
-                gs += g * e[2 * (j - (long long)bb * S) + k];
-            }
-            const double gs2 = gs * 0.5 / sqrt(sig2[idx]);
+        // one block per observation row b: its (up to S) samples of the local range, strided over the threads, then a
+        // fixed-order tree -- a rank that owns few rows with many samples each (S = 128 x GPUs) is as fast as one GPU
+        const int bb = blockIdx.x - 1;
+        long long lo = (long long)bb * S, hi = lo + S;
+        lo = lo > j_begin ? lo : j_begin;
+        hi = hi < j_end ? hi : j_end;
+        double gm0 = 0.0, gm1 = 0.0, gs0 = 0.0, gs1 = 0.0;
+        for (long long j = lo + tid; j < hi; j += blockDim.x) {
+            const double2 g = *reinterpret_cast<const double2 *>(gth + 2 * (j - j_begin));
+            const double2 ee = *reinterpret_cast<const double2 *>(e + 2 * (j - (long long)bb * S));
+            gm0 += g.x;
+            gm1 += g.y;
+            gs0 = fma(g.x, ee.x, gs0);
+            gs1 = fma(g.y, ee.y, gs1);
+        }
+        __shared__ double sh4[4][256];
+        sh4[0][tid] = gm0;
+        sh4[1][tid] = gm1;
+        sh4[2][tid] = gs0;
+        sh4[3][tid] = gs1;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (tid < o)
+                for (int q4 = 0; q4 < 4; ++q4) sh4[q4][tid] += sh4[q4][tid + o];
+            __syncthreads();
+        }
+        if (tid < 2) {
+            const int idx = 2 * bb + tid;
+            const double gm = sh4[tid][0];
+            const double gs2 = sh4[2 + tid][0] * 0.5 / sqrt(sig2[idx]);
             if (PEER) {
                 peer_push(P, q, 3 + idx, gm);
                 peer_push(P, q, 3 + 2 * B + idx, gs2);
@@ -2695,7 +2712,7 @@ static int elbo_step1_impl(vbfem_t *h, int32_t B, int32_t S, int64_t j_begin, in
     a.gx = h->elbo_g;
     rc = launch(h, a, stream);
     if (rc) return rc;
-    const int nblk = 1 + (2 * B + 255) / 256;
+    const int nblk = 1 + B;  // block 0: sums of f; block 1 + b: observation row b
     if (peer)
         elbo_reduce_kernel<true><<<nblk, 256, 0, st>>>(B, S, j_begin, j_end, a.f_out, h->elbo_g, e, sig2, sums, nullptr,
                                                        nullptr, h->peer);
