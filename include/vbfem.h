@@ -95,7 +95,8 @@ int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *mesh, const vbfem_options *
  * a GPU (unit tests of the numbering / orientation / front split): out[0] = kernel variant (4 = warp-per-sample
  * kernel, 2 = on-chip two-front kernel, 3 = blocked panel kernel, 0 = generic kernel), out[1] = order n, out[2] = half bandwidth, out[3] = first
  * middle row pT, out[4] = bottom-front columns nB, out[5] = 1 if the band order was reversed so that
- * it ends at the observed node, out[6] = shared memory per CTA in bytes, out[7] reserved.
+ * it ends at the observed node, out[6] = shared memory per CTA in bytes (of the
+ * forward / fused-adjoint launches), out[7] = generation of the warp kernel (1, 2; 0 for the other kernels).
  * smem_per_sm: shared memory per SM assumed for the fit test (<= 0: 233472, B200). */
 int vbfem_plan(const vbfem_mesh *mesh, int64_t smem_per_sm, int64_t *out /* [8] */);
 void vbfem_destroy(vbfem_t *h);

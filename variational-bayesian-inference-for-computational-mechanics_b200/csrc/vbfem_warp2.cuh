@@ -5,14 +5,17 @@
 // SAMPLE-INDEPENDENT band matrices.  They are assembled once per mesh (element matrices by the same device routines
 // the other kernels use -- shapef_q4 / accumulate_kt with (lambda, mu) = (1, 0) and (0, 1) -- summed on the host in
 // element order) and live in shared memory as (K_lam, K_mu) pairs in band form, [row][row - col], 183 KB for Cook
-// 20x10, shared by the twelve warps of the CTA.  Per sample:
+// 20x10, shared by the sixteen warps of the CTA.  Per sample:
 //   * the block row entering the register window is eight predicated 16-byte loads and sixteen FMAs per lane --
 //     the first generation computed 200 element matrices per sample (Gauss loops, 36 accumulators, a ring of 44
 //     matrices in shared memory per warp) and gathered the row through a packed index table;
 //   * the adjoint contraction -psi^T (dK/dlambda, dK/dmu) u = -(psi^T K_lam u, psi^T K_mu u) runs INSIDE the
 //     reverse pass on the same table: as soon as panel p of u and psi leaves the back substitution it enters a
-//     40-row window in shared memory and block column p of the band (208 entries) is contracted, seven entries per
-//     lane.  No solution vector is ever stored, no shape function re-evaluated.
+//     ring of 40 (or hb + 8) rows in shared memory, and block column p + 1 of the band is contracted against the
+//     ring in the same basic block as the back substitution of panel p (independent instruction streams): each
+//     lane owns a column and every fourth offset below the diagonal, one 16-byte table load and one 16-byte ring
+//     load per entry, branch-free.  No solution vector is ever stored, no shape function re-evaluated.
+// Without the element kernels the kernel fits 128 registers without spills: sixteen warps per SM in every mode.
 // Everything else -- the 8x8 blocked LDL^T in registers, FP64 tensor-core MMAs, the factor slab, the observation
 // trick -- is the first generation's.  Results differ from it by rounding only (1e-13 relative).
 #pragma once
