@@ -584,6 +584,8 @@ def test_elbo_step2_fused_vs_oracle(pkg, engine, torch_oracle):
     (20, 9, 4, "1"),    # n = 400, b = 23
     (20, 9, 2, "0"),    #          other front lengths
     (16, 8, 4, "1"),    # n = 288
+    (14, 8, 4, "1"),    # n = 252 = 4 mod 8: four leading pad rows (pivot mu in the band table of the warp kernel)
+    (10, 8, 4, "1"),    # n = 180 = 4 mod 8, 23 panels
     (16, 8, 3, "0"),    #          too small for the front kernel's shared-memory layout -> blocked panel kernel
     (30, 10, 4, "1"),   # n = 660: the larger gather table leaves room for eight warps
     (30, 10, 3, "0"),   #          the band no longer fits twice per SM -> blocked panel kernel
