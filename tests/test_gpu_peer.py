@@ -31,7 +31,13 @@ def two_ranks(pkg, golden_model):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     engs = [pkg.CookFemEngine(golden_model, device=0) for _ in range(2)]
+    old = os.environ.get("VBFEM_PEER_TIMEOUT_MS")
+    os.environ["VBFEM_PEER_TIMEOUT_MS"] = "5000"   # read by vbfem_peer_open: a box that serialises kernels fails fast
     boxes = [e.peer_open(r, 2, 3 + 4 * 64)[1] for r, e in enumerate(engs)]
+    if old is None:
+        del os.environ["VBFEM_PEER_TIMEOUT_MS"]
+    else:
+        os.environ["VBFEM_PEER_TIMEOUT_MS"] = old
     for e in engs:
         e.peer_connect(mailboxes=boxes)
         e.reserve(4096)   # no buffer growth (cudaDeviceSynchronize) while the other "rank" waits in its kernel
