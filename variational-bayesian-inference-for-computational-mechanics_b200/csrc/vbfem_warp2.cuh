@@ -35,6 +35,15 @@ namespace vbfem {
 __device__ __forceinline__ double neg_alu(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
+// A/B build (-DVBFEM_REV_DFMA): the fused mode's back substitution as per-lane FMAs on its two useful vectors instead of
+// 8-row MMA fragments.  A quarter of the pipe time, but a longer dependency chain from panel to panel (shuffles, a
+// shared-memory round trip for the older panels): 9.3 against 10.8 M fwd+adjoint solves/s -- the reverse pass is bound
+// by its chain, not by the pipe.  The tensor-core form is the default.
+#ifdef VBFEM_REV_DFMA
+constexpr bool kWarp2RevDfma = true;
+#else
+constexpr bool kWarp2RevDfma = false;
+#endif
 constexpr int kWarp2Fixed = 640;          // Minv^T and 1/d of the last panel, flag
 constexpr int kWarp2Small = 1088;         // small vectors of the observation / reverse pass (136 doubles)
 constexpr int kWarp2WinRows = 40;         // ring of u / psi rows: five panels; the contraction of one block column touches
@@ -389,62 +398,159 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                     }
                 }
             };
-            double2 cur[NB + 2], nxt[NB + 2], nx2[NB + 2];  // panels p, p-1, p-2: loads two panels ahead of their use
             constexpr int kAhead = 4;  // panels on their way into L2 ahead of the register buffers
             if (lane < (NB + 2) * 4)
                 for (int i = 2; i <= 1 + kAhead && NQ - 1 - i >= 0; ++i)
                     prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(NQ - 1 - i) * LPB) + 128 * lane);
-            {
-                const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 1) * LPB);
+            if constexpr (MODE == 1 && kWarp2RevDfma) {
+                // ---- Fused mode carries TWO vectors (u, psi): as 8-row MMA fragments six of eight rows would be zeros
+                // (10 DMMAs per panel on the pipe that bounds the kernel).  Here lane (v, c, h) = (lane >> 4,
+                // (lane >> 1) & 7, lane & 1) owns entry c of vector v and half h of every contraction index: the stored
+                // blocks are row-major [c][k] (L^T, Minv^T, the transposed D^-1 z rows), so a lane's four coefficients of
+                // a block are 32 contiguous bytes of the slab; 16 + 4 FMAs per lane and panel, two xor-shuffle sums.
+                const int v = lane >> 4, c = (lane >> 1) & 7, h = lane & 1;
+                double wf[4];
 #pragma unroll
-                for (int b = 0; b < NB + 2; ++b) nxt[b] = __ldcs(pan + b * 32 + lane);
-                const double2 *pa2 = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 2) * LPB);
+                for (int j = 0; j < 4; ++j) wf[j] = sW[v * 8 + 4 * h + j];
+                const double nwa = nodew[2 * v], nwb = nodew[2 * v + 1], nla = nodeL[c], nlb = nodeL[8 + c];
+                double2 ca[NB + 2], cb[NB + 2], na[NB + 2], nb[NB + 2];  // panels p and p-1: k = 4h, 4h+1 | 4h+2, 4h+3
+                const int lo2 = c * 4 + 2 * h;                            // double2 index of S[c][4h] inside a block
+                {
+                    const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 1) * LPB) + lo2;
 #pragma unroll
-                for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pa2 + b * 32 + lane);
-            }
+                    for (int bk = 0; bk < NB + 2; ++bk) {
+                        na[bk] = __ldcs(pan + bk * 32);
+                        nb[bk] = __ldcs(pan + bk * 32 + 1);
+                    }
+                }
+                double xprev = 0.0;  // x_(p+1)[v][c] (both halves hold it)
 #pragma unroll 1
-            for (int p = NQ - 1; p >= 0; --p) {
+                for (int p = NQ - 1; p >= 0; --p) {
 #pragma unroll
-                for (int b = 0; b < NB + 2; ++b) {
-                    cur[b] = nxt[b];
-                    nxt[b] = nx2[b];
+                    for (int bk = 0; bk < NB + 2; ++bk) {
+                        ca[bk] = na[bk];
+                        cb[bk] = nb[bk];
+                    }
+                    if (p > 0) {
+                        const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 1) * LPB) + lo2;
+#pragma unroll
+                        for (int bk = 0; bk < NB + 2; ++bk) {
+                            na[bk] = __ldcs(pan + bk * 32);
+                            nb[bk] = __ldcs(pan + bk * 32 + 1);
+                        }
+                        if (p - 1 - kAhead >= 0 && lane < (NB + 2) * 4)
+                            prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(p - 1 - kAhead) * LPB) + 128 * lane);
+                    }
+                    // right-hand-side rows, then the older panels from the ring (their rows 8 (p+b) + 4h + j), the newest
+                    // panel last and straight from the registers of its owners
+                    double d0 = wf[0] * ca[NB + 1].x, d1 = wf[1] * ca[NB + 1].y;
+                    d0 = fma(wf[2], cb[NB + 1].x, d0);
+                    d1 = fma(wf[3], cb[NB + 1].y, d1);
+#pragma unroll
+                    for (int bk = NB; bk >= 2; --bk) {
+                        int r = wbase + 8 * bk + 4 * h;
+                        r -= (r >= WR) ? WR : 0;   // WR >= 33: the four rows r .. r+3 may still wrap
+                        double xr[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            int rj = r + j;
+                            rj -= (rj >= WR) ? WR : 0;
+                            xr[j] = (p + bk < NQ) ? win[rj * NV + v] : 0.0;
+                        }
+                        d0 = fma(-xr[0], ca[bk].x, d0);
+                        d1 = fma(-xr[1], ca[bk].y, d1);
+                        d0 = fma(-xr[2], cb[bk].x, d0);
+                        d1 = fma(-xr[3], cb[bk].y, d1);
+                    }
+                    {
+                        const int src = (v << 4) + 8 * h;  // lane of (v, 4h + j, 0) is src + 2 j
+                        const double x0 = __shfl_sync(kFull, xprev, src), x1 = __shfl_sync(kFull, xprev, src + 2);
+                        const double x2 = __shfl_sync(kFull, xprev, src + 4), x3 = __shfl_sync(kFull, xprev, src + 6);
+                        d0 = fma(-x0, ca[1].x, d0);
+                        d1 = fma(-x1, ca[1].y, d1);
+                        d0 = fma(-x2, cb[1].x, d0);
+                        d1 = fma(-x3, cb[1].y, d1);
+                    }
+                    double d = d0 + d1;
+                    d += __shfl_xor_sync(kFull, d, 1);
+                    if (p == NQ - 1) d += nwa * nla + nwb * nlb;
+                    double x;
+                    {
+                        const int src = (v << 4) + 8 * h;
+                        const double e0 = __shfl_sync(kFull, d, src), e1 = __shfl_sync(kFull, d, src + 2);
+                        const double e2 = __shfl_sync(kFull, d, src + 4), e3 = __shfl_sync(kFull, d, src + 6);
+                        const double y0 = fma(e2, cb[0].x, e0 * ca[0].x), y1 = fma(e3, cb[0].y, e1 * ca[0].y);
+                        x = y0 + y1;
+                        x += __shfl_xor_sync(kFull, x, 1);
+                    }
+                    xprev = x;
+                    WTL(9);
+                    if (p + 1 < NQ) contract(p + 1, wbase + 8 >= WR ? wbase + 8 - WR : wbase + 8);
+                    __syncwarp();
+                    if (h == 0) {
+                        int r0 = wbase + c;
+                        r0 -= (r0 >= WR) ? WR : 0;
+                        win[r0 * NV + v] = x;
+                    }
+                    __syncwarp();
+                    wbase -= 8;
+                    wbase += (wbase < 0) ? WR : 0;
+                    WTL(10);
                 }
-                if (p > 1) {
-                    const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 2) * LPB);
-#pragma unroll
-                    for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pan + b * 32 + lane);
-                    if (p - 2 - kAhead >= 0 && lane < (NB + 2) * 4)
-                        prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(p - 2 - kAhead) * LPB) + 128 * lane);
+            } else {
+                double2 cur[NB + 2], nxt[NB + 2], nx2[NB + 2];  // panels p, p-1, p-2: loads two panels ahead of their use
+                {
+                    const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 1) * LPB);
+    #pragma unroll
+                    for (int b = 0; b < NB + 2; ++b) nxt[b] = __ldcs(pan + b * 32 + lane);
+                    const double2 *pa2 = reinterpret_cast<const double2 *>(lws + (size_t)(NQ - 2) * LPB);
+    #pragma unroll
+                    for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pa2 + b * 32 + lane);
                 }
-                // one accumulator; the block that needs the newest x (b = 1) comes last: the chain from panel p+1 to
-                // panel p is two block products, the others run ahead
-                double2 d = z2;
-                if (p == NQ - 1) d = make_double2(nw0 * nl0.x + nw1 * nl1.x, nw0 * nl0.y + nw1 * nl1.y);
-                block_mma<true>(d, Wf, cur[NB + 1], lane);
-#pragma unroll
-                for (int b = NB; b >= 1; --b) block_mma<true>(d, X[b], cur[b], lane);
-                double2 x = z2;
-                block_mma<true>(x, d, cur[0], lane);
-#pragma unroll
-                for (int b = NB; b > 1; --b) X[b] = X[b - 1];
-                X[1] = make_double2(neg_alu(x.x), neg_alu(x.y));
-                WTL(9);
-                // ---- block column p + 1 of the band is contracted (its rows 8 (p+1) .. 8 (p+1) + hb + 7 are in the window):
-                //      independent of the back-substitution chain above, one basic block with it
-                if (p + 1 < NQ) contract(p + 1, wbase + 8 >= WR ? wbase + 8 - WR : wbase + 8);
-                // ---- panel p of u and the adjoint vectors enters the window (the slot of panel p + 5)
-                __syncwarp();
-                if (g < NV) {
-                    int r0 = wbase + 2 * t, r1 = r0 + 1;
-                    r0 -= (r0 >= WR) ? WR : 0;
-                    r1 -= (r1 >= WR) ? WR : 0;
-                    win[r0 * NV + g] = x.x;
-                    win[r1 * NV + g] = x.y;
+    #pragma unroll 1
+                for (int p = NQ - 1; p >= 0; --p) {
+    #pragma unroll
+                    for (int b = 0; b < NB + 2; ++b) {
+                        cur[b] = nxt[b];
+                        nxt[b] = nx2[b];
+                    }
+                    if (p > 1) {
+                        const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 2) * LPB);
+    #pragma unroll
+                        for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pan + b * 32 + lane);
+                        if (p - 2 - kAhead >= 0 && lane < (NB + 2) * 4)
+                            prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(p - 2 - kAhead) * LPB) + 128 * lane);
+                    }
+                    // one accumulator; the block that needs the newest x (b = 1) comes last: the chain from panel p+1 to
+                    // panel p is two block products, the others run ahead
+                    double2 d = z2;
+                    if (p == NQ - 1) d = make_double2(nw0 * nl0.x + nw1 * nl1.x, nw0 * nl0.y + nw1 * nl1.y);
+                    block_mma<true>(d, Wf, cur[NB + 1], lane);
+    #pragma unroll
+                    for (int b = NB; b >= 1; --b) block_mma<true>(d, X[b], cur[b], lane);
+                    double2 x = z2;
+                    block_mma<true>(x, d, cur[0], lane);
+    #pragma unroll
+                    for (int b = NB; b > 1; --b) X[b] = X[b - 1];
+                    X[1] = make_double2(neg_alu(x.x), neg_alu(x.y));
+                    WTL(9);
+                    // ---- block column p + 1 of the band is contracted (its rows 8 (p+1) .. 8 (p+1) + hb + 7 are in the window):
+                    //      independent of the back-substitution chain above, one basic block with it
+                    if (p + 1 < NQ) contract(p + 1, wbase + 8 >= WR ? wbase + 8 - WR : wbase + 8);
+                    // ---- panel p of u and the adjoint vectors enters the window (the slot of panel p + 5)
+                    __syncwarp();
+                    if (g < NV) {
+                        int r0 = wbase + 2 * t, r1 = r0 + 1;
+                        r0 -= (r0 >= WR) ? WR : 0;
+                        r1 -= (r1 >= WR) ? WR : 0;
+                        win[r0 * NV + g] = x.x;
+                        win[r1 * NV + g] = x.y;
+                    }
+                    __syncwarp();
+                    wbase -= 8;
+                    wbase += (wbase < 0) ? WR : 0;
+                    WTL(10);
                 }
-                __syncwarp();
-                wbase -= 8;
-                wbase += (wbase < 0) ? WR : 0;
-                WTL(10);
             }
             contract(0, wbase + 8 >= WR ? wbase + 8 - WR : wbase + 8);
             __syncwarp();
