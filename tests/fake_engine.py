@@ -43,3 +43,24 @@ class OracleEngine:
             _, h = self.oracle.fem_fh(theta)
         sums = torch.cat([h.sum(0), (h ** 2).sum(0)]) if j_end > j_begin else torch.zeros(4, dtype=torch.float64)
         return sums, (h if want_h else None)
+
+
+class OracleEngineFused(OracleEngine):
+    """Adds the test double of CookFemEngine.elbo_step1_loss (the whole step-1 loss and its gradient w.r.t. the nets'
+    outputs, main_custom_training.py:183-235), from the oracle's own statement-by-statement loss and torch autograd with
+    (mu, sig2, log_sig2) as independent leaves -- what vbfem_elbo_step1_loss returns."""
+
+    def elbo_step1_loss(self, mu, sig2, log_sig2, e_data, y_batch, sig_e, j_begin, j_end, allreduce):
+        import math
+        B, S = mu.shape[0], e_data.shape[0]
+        assert not allreduce and j_begin == 0 and j_end == B * S
+        with torch.enable_grad():
+            m = mu.clone().requires_grad_(True)
+            s2 = sig2.clone().requires_grad_(True)
+            ls = log_sig2.clone().requires_grad_(True)
+            _, _, t2, t3 = fo.elbo_step1_torch(self.oracle, y_batch, m, s2, e_data, sig_e)
+            t1 = -0.5 * ls.sum(dim=-1).mean(dim=0) - 0.5 * 2 * math.log(2.0 * math.pi) - 0.5 * 2
+            loss = t1 - t2 - t3
+            dmu, dsig2, dls = torch.autograd.grad(loss, [m, s2, ls])
+        return loss.detach(), dmu, dsig2, dls
+

@@ -172,6 +172,30 @@ def test_step1_loss_sharded_over_gloo_ranks(tmp_path, world):
         assert "ERR" in o
 
 
+def test_step1_loss_library_side_form_equals_framework_form(pkg):
+    """Step1Loss with the whole loss from the engine (elbo_step1_loss: KL terms and loss value next to the data term)
+    against the form that keeps term1 / term3 in the framework: same value, same gradients through exp(log_sig2) --
+    the autograd glue of elbo.Step1Fused on the CPU, with the oracle as the engine."""
+    import torch
+    from fake_engine import OracleEngine, OracleEngineFused
+    rng = np.random.default_rng(17)
+    B, S = 3, 4
+    e = torch.tensor(rng.standard_normal((S, 2)))
+    yb = torch.tensor(rng.standard_normal((B, 2)) * 0.5 + np.array([-4.2, 5.7]))
+    res = []
+    for eng, fused in ((OracleEngineFused(), True), (OracleEngine(), True), (OracleEngineFused(), False)):
+        mu = torch.tensor(rng.standard_normal((B, 2)) * 0.0 + np.linspace(-0.3, 0.3, 2 * B).reshape(B, 2), requires_grad=True)
+        ls = torch.tensor(np.linspace(-0.4, 0.2, 2 * B).reshape(B, 2), requires_grad=True)
+        loss_fn = pkg.elbo.Step1Loss(eng, e, 0.1, fused=fused)
+        loss = 2.5 * loss_fn(yb, mu, torch.exp(ls), ls)      # a non-unit cotangent reaches the saved gradients
+        loss.backward()
+        res.append((float(loss), mu.grad.clone(), ls.grad.clone()))
+    for other in res[1:]:
+        assert abs(res[0][0] - other[0]) < 1e-12 * abs(other[0])
+        assert float((res[0][1] - other[1]).abs().max()) < 1e-12 * float(other[1].abs().max())
+        assert float((res[0][2] - other[2]).abs().max()) < 1e-12 * float(other[2].abs().max())
+
+
 def test_step2_loss_equals_oracle_broadcast(pkg):
     """Step2Loss (sufficient statistics of h) against the statement-by-statement restatement of
     main_custom_training.py:338-384 with its [B, B*S] broadcast: value and gradients w.r.t. the z nets."""
