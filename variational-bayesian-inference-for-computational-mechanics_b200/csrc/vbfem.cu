@@ -1929,6 +1929,9 @@ extern "C" int vbfem_create_ex(vbfem_t **out, const vbfem_mesh *m, const vbfem_o
             for (int q = 0; q < P.NQ; ++q)
                 for (int i = 0; i < 64; ++i)
                     if (P.rhs0[(size_t)q * 64 + i] != 0.0) Q.rhsmask[q >> 6] |= 1ull << (q & 63);
+            Q.rhs_first = P.NQ;
+            for (int q = P.NQ - 1; q >= 0; --q)
+                if ((Q.rhsmask[q >> 6] >> (q & 63)) & 1) Q.rhs_first = q;
             warp_fn ks[3];
             if (W2.NW == 8) {
                 ks[0] = fem_warp2_kernel<0, 8>; ks[1] = fem_warp2_kernel<1, 8>; ks[2] = fem_warp2_kernel<2, 8>;

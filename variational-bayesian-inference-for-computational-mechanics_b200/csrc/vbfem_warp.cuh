@@ -59,6 +59,7 @@ struct WarpModel {
     int win_rows;                // ring of u / psi rows per warp (reverse pass): 40, or hb + 8 when shared memory is tight
     unsigned cmagic;             // id / (hb + 1) == (id * cmagic) >> 16 for id < 8 (hb + 1)
     unsigned long long rhsmask[2];  // bit q: block row q has a non-zero initial right-hand-side block
+    int rhs_first;               // first such block row (NQ if none): the right-hand-side rows are zero above it
 };
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

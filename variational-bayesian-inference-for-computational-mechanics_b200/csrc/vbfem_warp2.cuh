@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
     constexpr int NB = kWarpNB, NB1 = NB + 1, LPB = (NB + 2) * 64;
     constexpr int NV = (MODE == 2) ? 5 : 2;
     constexpr int NADJ = NV - 1;
+    // Skipping the all-zero right-hand-side work above WarpModel::rhs_first pays with up to three warps per scheduler
+    // (+6 % forward, +4 % fused with twelve warps) and in Jacobian mode (+2 %); with four warps per scheduler in
+    // forward / fused mode the skipped MMAs were hidden anyway and the extra branches cost 1 %: compiled out there.
+    constexpr bool kSkipRhs = NW < 16 || MODE == 2;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int next_i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -196,9 +200,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
         for (int p = 0; p < NQ; ++p) {
             WTL(1);
             // ---- solve: V = X L11^-T for the right-hand sides (b = 0) and the blocks below; Ln = -V D^-1
+            // The right-hand-side rows (load vector, strain functionals) are zero up to their first non-zero block row and
+            // stay zero under the elimination until then: for p < rhs_first their solve, their three updates, their slab
+            // block and (reverse pass) their product are skipped -- on Cook 20x10 with the reference's observation set-up
+            // that is 8 of the 26 forward MMAs for more than half of the panels.
+            const bool rhs_live = !kSkipRhs || p >= Q.rhs_first;
             double2 V[NB1], Ln[NB1], Lp[NB1];
+            V[0] = Lp[0] = Ln[0] = z2;
 #pragma unroll
             for (int b = 0; b < NB1; ++b) {
+                if (b == 0 && !rhs_live) continue;
                 const double2 xv = b ? W[b][0] : Rh[0];
                 double2 v = z2;
                 block_mma<true>(v, xv, mi, lane);
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                 Lp[b] = make_double2(v.x * r2.x, v.y * r2.y);
                 Ln[b] = make_double2(neg_alu(Lp[b].x), neg_alu(Lp[b].y));
             }
-            {  // strain rows against the load row: G[g] += sum_c V[g][c] L[0][c]
+            if (rhs_live) {  // strain rows against the load row: G[g] += sum_c V[g][c] L[0][c]
                 const double lfx = __shfl_sync(kFull, Lp[0].x, t), lfy = __shfl_sync(kFull, Lp[0].y, t);
                 gacc = fma(V[0].x, lfx, fma(V[0].y, lfy, gacc));
                 if (p == NQ - 1 && g == 0) {
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                 __stcs(pan + lane, mit);
 #pragma unroll
                 for (int b = 0; b < NB1; ++b) {
+                    if (b == 0 && !rhs_live) continue;
                     const int s0 = 8 * t + (g >> 1), s1 = s0 + 4;
                     const double ax = __shfl_sync(kFull, Lp[b].x, s0), ay = __shfl_sync(kFull, Lp[b].y, s0);
                     const double bx = __shfl_sync(kFull, Lp[b].x, s1), by = __shfl_sync(kFull, Lp[b].y, s1);
@@ -242,8 +254,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
 #pragma unroll
             for (int J = 1; J <= NB; ++J) {
                 double2 c = Rh[J];
-                dmma884(c.x, c.y, Ln[0].x, V[J].x);
-                dmma884(c.x, c.y, Ln[0].y, V[J].y);
+                if (rhs_live) {
+                    dmma884(c.x, c.y, Ln[0].x, V[J].x);
+                    dmma884(c.x, c.y, Ln[0].y, V[J].y);
+                }
                 Rh[J - 1] = c;
             }
             WTL(4);
@@ -443,9 +457,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                     }
                     // right-hand-side rows, then the older panels from the ring (their rows 8 (p+b) + 4h + j), the newest
                     // panel last and straight from the registers of its owners
-                    double d0 = wf[0] * ca[NB + 1].x, d1 = wf[1] * ca[NB + 1].y;
-                    d0 = fma(wf[2], cb[NB + 1].x, d0);
-                    d1 = fma(wf[3], cb[NB + 1].y, d1);
+                    double d0 = 0.0, d1 = 0.0;
+                    if (!kSkipRhs || p >= Q.rhs_first) {   // no z rows stored below rhs_first
+                        d0 = fma(wf[2], cb[NB + 1].x, wf[0] * ca[NB + 1].x);
+                        d1 = fma(wf[3], cb[NB + 1].y, wf[1] * ca[NB + 1].y);
+                    }
 #pragma unroll
                     for (int bk = NB; bk >= 2; --bk) {
                         int r = wbase + 8 * bk + 4 * h;
@@ -517,7 +533,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                     if (p > 1) {
                         const double2 *pan = reinterpret_cast<const double2 *>(lws + (size_t)(p - 2) * LPB);
     #pragma unroll
-                        for (int b = 0; b < NB + 2; ++b) nx2[b] = __ldcs(pan + b * 32 + lane);
+                        for (int b = 0; b < NB + 2; ++b)
+                            if (b <= NB || !kSkipRhs || p - 2 >= Q.rhs_first) nx2[b] = __ldcs(pan + b * 32 + lane);  // no z rows stored below rhs_first
                         if (p - 2 - kAhead >= 0 && lane < (NB + 2) * 4)
                             prefetch_l2(reinterpret_cast<const char *>(lws + (size_t)(p - 2 - kAhead) * LPB) + 128 * lane);
                     }
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fem_warp2_kernel(const __grid_cons
                     // panel p is two block products, the others run ahead
                     double2 d = z2;
                     if (p == NQ - 1) d = make_double2(nw0 * nl0.x + nw1 * nl1.x, nw0 * nl0.y + nw1 * nl1.y);
-                    block_mma<true>(d, Wf, cur[NB + 1], lane);
+                    if (!kSkipRhs || p >= Q.rhs_first) block_mma<true>(d, Wf, cur[NB + 1], lane);
     #pragma unroll
                     for (int b = NB; b >= 1; --b) block_mma<true>(d, X[b], cur[b], lane);
                     double2 x = z2;
